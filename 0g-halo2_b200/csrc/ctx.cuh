@@ -1,0 +1,72 @@
+// Per-GPU context: stream, SRS window tables, twiddle-table cache, grow-only workspace.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+#include <array>
+#include "../../include/zg_b200.h"
+#include "msm.cuh"
+#include "ntt.cuh"
+
+namespace zg {
+
+struct Domain {       // twiddle table for one (log_n, omega)
+  Fr* tw = nullptr;   // stage-major, n-1 entries
+};
+
+struct Workspace {
+  uint8_t* p = nullptr;
+  size_t cap = 0;
+};
+
+// host-side field helpers (portable path of field.cuh)
+Fr host_fr_from_u64(uint64_t x);
+Fr host_fr_root_of_unity();      // order 2^28
+Fr host_fr_zeta();
+Fr host_omega(uint32_t k);       // ROOT_OF_UNITY ^ (2^(28-k))
+
+}  // namespace zg
+
+struct zg_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  uint64_t launches = 0;
+
+  // SRS
+  uint32_t srs_k = 0;
+  bool srs_loaded = false;
+  zg::G1Affine* base[2] = {nullptr, nullptr};
+  zg::MsmTable table[2];
+
+  // twiddle tables keyed by (log_n, omega limbs)
+  std::map<std::array<uint32_t, 9>, zg::Domain> domains;
+
+  zg::Workspace ws_msm, ws_ntt, ws_stage;
+  zg::G1Jac* d_msm_out = nullptr;  // small result staging (64 results)
+
+  int fail(int code, const std::string& msg) {
+    err = msg;
+    return code;
+  }
+  int cuda_fail(cudaError_t e, const char* what) {
+    err = std::string(what) + ": " + cudaGetErrorString(e);
+    return ZG_E_CUDA;
+  }
+};
+
+namespace zg {
+int ws_reserve(zg_ctx* ctx, Workspace& w, size_t bytes);
+int get_domain(zg_ctx* ctx, uint32_t logn, const Fr& omega, Domain** out);
+}  // namespace zg
+
+#define ZG_CUDA(call)                                             \
+  do {                                                            \
+    cudaError_t e__ = (call);                                     \
+    if (e__ != cudaSuccess) return ctx->cuda_fail(e__, #call);    \
+  } while (0)

@@ -1,0 +1,418 @@
+// BN254 prime-field arithmetic for sm_100a: 8 x 32-bit limbs, Montgomery form R = 2^256.
+//
+// The byte layout of one element is identical to halo2curves' `Fr([u64; 4])` / `Fq([u64; 4])`
+// (little-endian limbs, Montgomery form), so host buffers cross the C ABI unconverted.
+// Replaces (on device) the field arithmetic of halo2curves tag 0.3.3 `bn256::{fr,fq}` that
+// /root/reference/Cargo.toml:14-18 pins; call sites reach it through create_proof
+// (/root/reference/src/wnn.rs:242-259).
+//
+// Two multiplier bodies:
+//   * a portable 64-bit-accumulator CIOS (host + device; the host build is what the CPU-side
+//     unit tests exercise against Python big integers), and
+//   * a PTX mad.lo.cc / madc.hi.cc carry-chain CIOS (device only, selected with ZG_MUL_PTX).
+// Both compute the same function bit for bit; tests/test_gpu_field.py checks one against the other.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define ZG_HD __host__ __device__ __forceinline__
+#define ZG_D __device__ __forceinline__
+#else
+#define ZG_HD inline
+#define ZG_D inline
+#endif
+
+#ifndef ZG_MUL_PTX
+#define ZG_MUL_PTX 0
+#endif
+
+namespace zg {
+
+struct FrParams {
+  static constexpr uint32_t INV = 0xefffffffu;
+  ZG_HD static constexpr uint32_t mod(int i) {
+    constexpr uint32_t m[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u,
+                               0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+    return m[i];
+  }
+  ZG_HD static constexpr uint32_t one(int i) {  // R mod r
+    constexpr uint32_t m[8] = {0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u,
+                               0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+    return m[i];
+  }
+  ZG_HD static constexpr uint32_t r2(int i) {  // R^2 mod r
+    constexpr uint32_t m[8] = {0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u,
+                               0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u};
+    return m[i];
+  }
+  ZG_HD static constexpr uint32_t r3(int i) {  // R^3 mod r
+    constexpr uint32_t m[8] = {0xb4bf0040u, 0x5e94d8e1u, 0x1cfbb6b8u, 0x2a489cbeu,
+                               0xa19fcfedu, 0x893cc664u, 0x7fcc657cu, 0x0cf8594bu};
+    return m[i];
+  }
+};
+
+struct FqParams {
+  static constexpr uint32_t INV = 0xe4866389u;
+  ZG_HD static constexpr uint32_t mod(int i) {
+    constexpr uint32_t m[8] = {0xd87cfd47u, 0x3c208c16u, 0x6871ca8du, 0x97816a91u,
+                               0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+    return m[i];
+  }
+  ZG_HD static constexpr uint32_t one(int i) {
+    constexpr uint32_t m[8] = {0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u,
+                               0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+    return m[i];
+  }
+  ZG_HD static constexpr uint32_t r2(int i) {
+    constexpr uint32_t m[8] = {0x538afa89u, 0xf32cfc5bu, 0xd44501fbu, 0xb5e71911u,
+                               0x0a417ff6u, 0x47ab1effu, 0xcab8351fu, 0x06d89f71u};
+    return m[i];
+  }
+  ZG_HD static constexpr uint32_t r3(int i) {
+    constexpr uint32_t m[8] = {0xda1530dfu, 0xb1cd6dafu, 0xa7283db6u, 0x62f210e6u,
+                               0x0ada0afbu, 0xef7f0b0cu, 0x2d592544u, 0x20fd6e90u};
+    return m[i];
+  }
+};
+
+template <class P>
+struct alignas(16) Fp {
+  uint32_t v[8];
+};
+using Fr = Fp<FrParams>;
+using Fq = Fp<FqParams>;
+
+template <class P>
+ZG_HD Fp<P> fp_zero() {
+  Fp<P> r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = 0;
+  return r;
+}
+template <class P>
+ZG_HD Fp<P> fp_one() {
+  Fp<P> r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = P::one(i);
+  return r;
+}
+template <class P>
+ZG_HD bool fp_is_zero(const Fp<P>& a) {
+  uint32_t o = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) o |= a.v[i];
+  return o == 0;
+}
+template <class P>
+ZG_HD bool fp_eq(const Fp<P>& a, const Fp<P>& b) {
+  uint32_t o = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) o |= a.v[i] ^ b.v[i];
+  return o == 0;
+}
+
+// r = (t >= p) ? t - p : t, for t < 2p
+template <class P>
+ZG_HD void fp_final_sub(uint32_t (&t)[8]) {
+  uint32_t u[8];
+#if defined(__CUDA_ARCH__)
+  uint32_t borrow;
+  asm("sub.cc.u32 %0, %9, %17;\n\t"
+      "subc.cc.u32 %1, %10, %18;\n\t"
+      "subc.cc.u32 %2, %11, %19;\n\t"
+      "subc.cc.u32 %3, %12, %20;\n\t"
+      "subc.cc.u32 %4, %13, %21;\n\t"
+      "subc.cc.u32 %5, %14, %22;\n\t"
+      "subc.cc.u32 %6, %15, %23;\n\t"
+      "subc.cc.u32 %7, %16, %24;\n\t"
+      "subc.u32 %8, 0, 0;"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]),
+        "=r"(u[7]), "=r"(borrow)
+      : "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]), "r"(t[4]), "r"(t[5]), "r"(t[6]), "r"(t[7]),
+        "n"(P::mod(0)), "n"(P::mod(1)), "n"(P::mod(2)), "n"(P::mod(3)), "n"(P::mod(4)),
+        "n"(P::mod(5)), "n"(P::mod(6)), "n"(P::mod(7)));
+  bool keep = borrow != 0;  // t < p
+#else
+  uint64_t bw = 0;
+  for (int i = 0; i < 8; i++) {
+    uint64_t d = (uint64_t)t[i] - P::mod(i) - bw;
+    u[i] = (uint32_t)d;
+    bw = (d >> 63) & 1;
+  }
+  bool keep = bw != 0;
+#endif
+#pragma unroll
+  for (int i = 0; i < 8; i++) t[i] = keep ? t[i] : u[i];
+}
+
+template <class P>
+ZG_HD Fp<P> fp_add(const Fp<P>& a, const Fp<P>& b) {
+  uint32_t t[8];
+#if defined(__CUDA_ARCH__)
+  asm("add.cc.u32 %0, %8, %16;\n\t"
+      "addc.cc.u32 %1, %9, %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32 %7, %15, %23;"
+      : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]),
+        "=r"(t[7])
+      : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]),
+        "r"(a.v[6]), "r"(a.v[7]), "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]),
+        "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+#else
+  uint64_t c = 0;
+  for (int i = 0; i < 8; i++) {
+    c += (uint64_t)a.v[i] + b.v[i];
+    t[i] = (uint32_t)c;
+    c >>= 32;
+  }
+#endif
+  fp_final_sub<P>(t);  // a + b < 2p < 2^256: no carry out of limb 7
+  Fp<P> r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = t[i];
+  return r;
+}
+
+template <class P>
+ZG_HD Fp<P> fp_sub(const Fp<P>& a, const Fp<P>& b) {
+  uint32_t t[8];
+  Fp<P> r;
+#if defined(__CUDA_ARCH__)
+  uint32_t borrow;
+  asm("sub.cc.u32 %0, %9, %17;\n\t"
+      "subc.cc.u32 %1, %10, %18;\n\t"
+      "subc.cc.u32 %2, %11, %19;\n\t"
+      "subc.cc.u32 %3, %12, %20;\n\t"
+      "subc.cc.u32 %4, %13, %21;\n\t"
+      "subc.cc.u32 %5, %14, %22;\n\t"
+      "subc.cc.u32 %6, %15, %23;\n\t"
+      "subc.cc.u32 %7, %16, %24;\n\t"
+      "subc.u32 %8, 0, 0;"
+      : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]),
+        "=r"(t[7]), "=r"(borrow)
+      : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]),
+        "r"(a.v[6]), "r"(a.v[7]), "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]),
+        "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+  // add back p masked by the borrow (borrow is 0 or 0xffffffff)
+  asm("add.cc.u32 %0, %8, %16;\n\t"
+      "addc.cc.u32 %1, %9, %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32 %7, %15, %23;"
+      : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]),
+        "=r"(r.v[6]), "=r"(r.v[7])
+      : "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]), "r"(t[4]), "r"(t[5]), "r"(t[6]), "r"(t[7]),
+        "r"(P::mod(0) & borrow), "r"(P::mod(1) & borrow), "r"(P::mod(2) & borrow),
+        "r"(P::mod(3) & borrow), "r"(P::mod(4) & borrow), "r"(P::mod(5) & borrow),
+        "r"(P::mod(6) & borrow), "r"(P::mod(7) & borrow));
+#else
+  uint64_t bw = 0;
+  for (int i = 0; i < 8; i++) {
+    uint64_t d = (uint64_t)a.v[i] - b.v[i] - bw;
+    t[i] = (uint32_t)d;
+    bw = (d >> 63) & 1;
+  }
+  uint32_t mask = bw ? 0xffffffffu : 0u;
+  uint64_t c = 0;
+  for (int i = 0; i < 8; i++) {
+    c += (uint64_t)t[i] + (P::mod(i) & mask);
+    r.v[i] = (uint32_t)c;
+    c >>= 32;
+  }
+#endif
+  return r;
+}
+
+template <class P>
+ZG_HD Fp<P> fp_neg(const Fp<P>& a) {
+  return fp_sub<P>(fp_zero<P>(), a);
+}
+template <class P>
+ZG_HD Fp<P> fp_dbl(const Fp<P>& a) {
+  return fp_add<P>(a, a);
+}
+
+// ---- Montgomery multiplication -------------------------------------------------------
+// Portable fused CIOS ("no-carry" form: valid because the top modulus limb is < 2^31 - 1, so
+// the two per-row carries sum without overflow).  Inputs < p, output < p.
+template <class P>
+ZG_HD Fp<P> fp_mul_portable(const Fp<P>& a, const Fp<P>& b) {
+  uint32_t t[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) t[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    uint64_t A = (uint64_t)a.v[0] * b.v[i] + t[0];
+    uint32_t m = (uint32_t)A * P::INV;
+    uint64_t C = (uint64_t)m * P::mod(0) + (uint32_t)A;
+    A >>= 32;
+    C >>= 32;
+#pragma unroll
+    for (int j = 1; j < 8; j++) {
+      A += (uint64_t)a.v[j] * b.v[i] + t[j];
+      C += (uint64_t)m * P::mod(j) + (uint32_t)A;
+      A >>= 32;
+      t[j - 1] = (uint32_t)C;
+      C >>= 32;
+    }
+    t[7] = (uint32_t)(A + C);
+  }
+  fp_final_sub<P>(t);
+  Fp<P> r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = t[i];
+  return r;
+}
+
+#if defined(__CUDA_ARCH__)
+// One CIOS row as a single asm statement, so the carry flag never crosses a statement
+// boundary: t(9 limbs) += a * bi ; m = t0 * INV ; t += m * p ; (caller shifts by one limb).
+template <class P>
+__device__ __forceinline__ void mont_row_ptx(uint32_t (&t)[9], const Fp<P>& a, uint32_t bi) {
+  asm("{\n\t"
+      ".reg .u32 m;\n\t"
+      // low halves of a*bi
+      "mad.lo.cc.u32 %0, %9, %17, %0;\n\t"
+      "madc.lo.cc.u32 %1, %10, %17, %1;\n\t"
+      "madc.lo.cc.u32 %2, %11, %17, %2;\n\t"
+      "madc.lo.cc.u32 %3, %12, %17, %3;\n\t"
+      "madc.lo.cc.u32 %4, %13, %17, %4;\n\t"
+      "madc.lo.cc.u32 %5, %14, %17, %5;\n\t"
+      "madc.lo.cc.u32 %6, %15, %17, %6;\n\t"
+      "madc.lo.cc.u32 %7, %16, %17, %7;\n\t"
+      "addc.u32 %8, %8, 0;\n\t"
+      // high halves of a*bi
+      "mad.hi.cc.u32 %1, %9, %17, %1;\n\t"
+      "madc.hi.cc.u32 %2, %10, %17, %2;\n\t"
+      "madc.hi.cc.u32 %3, %11, %17, %3;\n\t"
+      "madc.hi.cc.u32 %4, %12, %17, %4;\n\t"
+      "madc.hi.cc.u32 %5, %13, %17, %5;\n\t"
+      "madc.hi.cc.u32 %6, %14, %17, %6;\n\t"
+      "madc.hi.cc.u32 %7, %15, %17, %7;\n\t"
+      "madc.hi.u32 %8, %16, %17, %8;\n\t"
+      // m = t0 * (-p^-1 mod 2^32)
+      "mul.lo.u32 m, %0, %18;\n\t"
+      // low halves of m*p
+      "mad.lo.cc.u32 %0, m, %19, %0;\n\t"
+      "madc.lo.cc.u32 %1, m, %20, %1;\n\t"
+      "madc.lo.cc.u32 %2, m, %21, %2;\n\t"
+      "madc.lo.cc.u32 %3, m, %22, %3;\n\t"
+      "madc.lo.cc.u32 %4, m, %23, %4;\n\t"
+      "madc.lo.cc.u32 %5, m, %24, %5;\n\t"
+      "madc.lo.cc.u32 %6, m, %25, %6;\n\t"
+      "madc.lo.cc.u32 %7, m, %26, %7;\n\t"
+      "addc.u32 %8, %8, 0;\n\t"
+      // high halves of m*p
+      "mad.hi.cc.u32 %1, m, %19, %1;\n\t"
+      "madc.hi.cc.u32 %2, m, %20, %2;\n\t"
+      "madc.hi.cc.u32 %3, m, %21, %3;\n\t"
+      "madc.hi.cc.u32 %4, m, %22, %4;\n\t"
+      "madc.hi.cc.u32 %5, m, %23, %5;\n\t"
+      "madc.hi.cc.u32 %6, m, %24, %6;\n\t"
+      "madc.hi.cc.u32 %7, m, %25, %7;\n\t"
+      "madc.hi.u32 %8, m, %26, %8;\n\t"
+      "}"
+      : "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]),
+        "+r"(t[7]), "+r"(t[8])
+      : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]),
+        "r"(a.v[6]), "r"(a.v[7]), "r"(bi), "n"(P::INV), "n"(P::mod(0)), "n"(P::mod(1)),
+        "n"(P::mod(2)), "n"(P::mod(3)), "n"(P::mod(4)), "n"(P::mod(5)), "n"(P::mod(6)),
+        "n"(P::mod(7)));
+}
+
+template <class P>
+__device__ __forceinline__ Fp<P> fp_mul_ptx(const Fp<P>& a, const Fp<P>& b) {
+  uint32_t t[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++) t[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    mont_row_ptx<P>(t, a, b.v[i]);
+#pragma unroll
+    for (int j = 0; j < 8; j++) t[j] = t[j + 1];  // t0 is zero after the row: shift one limb
+    t[8] = 0;
+  }
+  uint32_t u[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) u[i] = t[i];
+  fp_final_sub<P>(u);
+  Fp<P> r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = u[i];
+  return r;
+}
+#endif
+
+template <class P>
+ZG_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
+#if defined(__CUDA_ARCH__) && ZG_MUL_PTX
+  return fp_mul_ptx<P>(a, b);
+#else
+  return fp_mul_portable<P>(a, b);
+#endif
+}
+template <class P>
+ZG_HD Fp<P> fp_sqr(const Fp<P>& a) {
+  return fp_mul<P>(a, a);
+}
+
+// canonical (non-Montgomery) integer -> Montgomery form
+template <class P>
+ZG_HD Fp<P> fp_to_mont(const Fp<P>& raw) {
+  Fp<P> r2;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r2.v[i] = P::r2(i);
+  return fp_mul<P>(raw, r2);
+}
+// Montgomery form -> canonical integer limbs
+template <class P>
+ZG_HD Fp<P> fp_from_mont(const Fp<P>& a) {
+  Fp<P> o = fp_zero<P>();
+  o.v[0] = 1;
+  return fp_mul<P>(a, o);
+}
+template <class P>
+ZG_HD Fp<P> fp_from_u64(uint64_t x) {
+  Fp<P> raw = fp_zero<P>();
+  raw.v[0] = (uint32_t)x;
+  raw.v[1] = (uint32_t)(x >> 32);
+  return fp_to_mont<P>(raw);
+}
+
+// a^e for a 256-bit exponent given as 8 little-endian 32-bit limbs (square-and-multiply, MSB first)
+template <class P>
+ZG_HD Fp<P> fp_pow(const Fp<P>& a, const uint32_t* e, int nlimbs) {
+  Fp<P> acc = fp_one<P>();
+  for (int i = nlimbs - 1; i >= 0; i--) {
+    for (int b = 31; b >= 0; b--) {
+      acc = fp_sqr<P>(acc);
+      if ((e[i] >> b) & 1) acc = fp_mul<P>(acc, a);
+    }
+  }
+  return acc;
+}
+template <class P>
+ZG_HD Fp<P> fp_pow_u64(const Fp<P>& a, uint64_t e) {
+  uint32_t limbs[2] = {(uint32_t)e, (uint32_t)(e >> 32)};
+  return fp_pow<P>(a, limbs, 2);
+}
+// Fermat inverse a^(p-2); maps 0 -> 0 (same convention as ff::Field::invert().unwrap_or(0)
+// inside halo2's batch_invert, which skips zeros).
+template <class P>
+ZG_HD Fp<P> fp_inv(const Fp<P>& a) {
+  uint32_t e[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) e[i] = P::mod(i);
+  e[0] -= 2;  // low limb of both moduli is >= 2, no borrow
+  return fp_pow<P>(a, e, 8);
+}
+
+}  // namespace zg

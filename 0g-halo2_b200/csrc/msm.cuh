@@ -1,0 +1,38 @@
+// MSM descriptors shared by msm.cu and the context layer.
+#pragma once
+#include <cuda_runtime.h>
+#include "curve.cuh"
+
+namespace zg {
+
+// Fixed-base window table: pts[w * n + i] = 2^(c*w) * base[i], affine.
+struct MsmTable {
+  G1Affine* pts = nullptr;
+  uint32_t n = 0, c = 0, W = 0;
+};
+
+constexpr uint32_t MSM_INVALID_KEY = 0xffffffffu;
+
+inline uint32_t msm_windows(uint32_t c) { return (255 + c - 1) / c; }
+// window width used for a 2^k-point fixed-base MSM (overridable with ZG_MSM_C)
+uint32_t msm_pick_c(uint32_t k);
+
+struct MsmWorkspaceLayout {
+  size_t bytes = 0;
+  size_t off_hist, off_cursor, off_offsets, off_keys, off_vals, off_buckets;
+  size_t off_pkeys_a, off_ppts_a, off_pkeys_b, off_ppts_b, off_s1, off_t1, off_l2;
+  uint32_t L_max, K0, T0, slots_a, slots_b, NB, M;
+};
+MsmWorkspaceLayout msm_workspace_layout(uint32_t n, uint32_t c, uint32_t W, uint32_t M);
+
+cudaError_t msm_precompute_table(const G1Affine* base, uint32_t n, uint32_t c, uint32_t W,
+                                 G1Affine* table, cudaStream_t stream);
+
+// M MSMs over the same table; scalars are Montgomery-form Fr on the device,
+// polynomial m starts at scalars + m * scalar_stride.  `n_used` <= table.n scalars per MSM.
+// out[m] is Jacobian.  `ws` must hold msm_workspace_layout(...).bytes.
+cudaError_t msm_run(const MsmTable& table, const Fr* scalars, size_t scalar_stride, uint32_t n_used,
+                    uint32_t M, G1Jac* out, uint8_t* ws, const MsmWorkspaceLayout& lay,
+                    cudaStream_t stream, uint64_t* launch_counter);
+
+}  // namespace zg

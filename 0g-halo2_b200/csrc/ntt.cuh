@@ -1,0 +1,47 @@
+// NTT pass descriptors shared by ntt.cu and the context layer.
+#pragma once
+#include <cuda_runtime.h>
+#include "field.cuh"
+
+namespace zg {
+
+constexpr int NTT_THREADS = 256;
+constexpr uint32_t NTT_MAX_S = 8;  // index bits per pass (tile = 2^S rows)
+constexpr uint32_t NTT_LOGC = 2;   // columns per tile (4 x 32 B = one 128-B line)
+
+enum : uint32_t {
+  NTT_IN_COSET = 1,   // multiply input i by in_scale[i % 3]   (distribute_powers_zeta)
+  NTT_OUT_SCALE = 2,  // multiply output i by out_scale[0]      (1/n of the inverse transform)
+  NTT_OUT_MOD3 = 4,   // ... by out_scale[i % 3] instead         (1/n folded with zeta^-i)
+};
+
+struct NttPassArgs {
+  const Fr* in;
+  Fr* out;
+  size_t in_stride, out_stride;  // elements between consecutive polynomials of a batch
+  const Fr* tw;                  // stage-major twiddles
+  uint32_t logn, lo, S, logc, contiguous;
+  uint32_t n_in;   // inputs at index >= n_in read as zero (zero-padding of coeff_to_extended)
+  uint32_t n_out;  // outputs at index >= n_out are not stored (truncation of extended_to_coeff)
+  uint32_t flags;
+  Fr in_scale[3];
+  Fr out_scale[3];
+};
+
+struct NttPlan {
+  const Fr* in;
+  Fr* out;
+  Fr* tmp;  // scratch of batch * tmp_stride elements, needed when logn > NTT_MAX_S
+  size_t in_stride, out_stride, tmp_stride;
+  const Fr* tw;
+  uint32_t logn, batch;
+  uint32_t n_in, n_out, flags;
+  Fr in_scale[3];
+  Fr out_scale[3];
+};
+
+cudaError_t ntt_build_twiddles(Fr* tab, Fr* scratch_flat, const Fr& w, uint32_t logn,
+                               cudaStream_t stream);
+cudaError_t ntt_run(const NttPlan& plan, cudaStream_t stream, uint64_t* launch_counter);
+
+}  // namespace zg

@@ -1,0 +1,208 @@
+"""ctypes binding of libzg_b200.so (the C ABI declared in include/zg_b200.h).
+
+The same entry points a patched halo2_proofs would bind from Rust.  There is
+no CPU fallback: if the shared library or a CUDA device is missing, construction raises.
+
+Array conventions (numpy, dtype uint64):
+  Fr / Fq      -> (..., 4)   little-endian limbs, Montgomery form (halo2curves in-memory layout)
+  G1Affine     -> (..., 8)   x | y ; identity = all zero
+  G1 (Jacobian)-> (..., 12)  x | y | z ; identity z = 0
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libzg_b200.so")
+
+ZG_OK = 0
+BASIS_MONOMIAL = 0
+BASIS_LAGRANGE = 1
+
+EXPORTS = [
+    "zg_version", "zg_ctx_create", "zg_ctx_destroy", "zg_last_error", "zg_sync", "zg_launch_count",
+    "zg_dev_alloc", "zg_dev_free", "zg_h2d", "zg_d2h",
+    "zg_srs_load", "zg_msm", "zg_msm_batch", "zg_msm_dev",
+    "zg_ntt", "zg_ntt_dev", "zg_lagrange_to_coeff", "zg_lagrange_to_coeff_dev",
+    "zg_coeff_to_extended", "zg_coeff_to_extended_dev", "zg_extended_to_coeff", "zg_extended_to_coeff_dev",
+    "zg_bench_int_pipe", "zg_debug_field_op",
+]
+
+
+class ZgError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("zg_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def load_library() -> ctypes.CDLL:
+    """Loads libzg_b200.so; raises if it has not been built (no silent fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "libzg_b200.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C 0g-halo2_b200/csrc`")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, u32, u64, sz, ci = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_size_t, ctypes.c_int
+    L.zg_version.restype = ctypes.c_char_p
+    L.zg_last_error.restype = ctypes.c_char_p
+    L.zg_last_error.argtypes = [vp]
+    L.zg_launch_count.restype = u64
+    L.zg_launch_count.argtypes = [vp]
+    L.zg_ctx_create.argtypes = [ci, vp, ctypes.POINTER(vp)]
+    L.zg_ctx_destroy.argtypes = [vp]
+    L.zg_ctx_destroy.restype = None
+    L.zg_sync.argtypes = [vp]
+    L.zg_dev_alloc.argtypes = [vp, sz, ctypes.POINTER(vp)]
+    L.zg_dev_free.argtypes = [vp, vp]
+    L.zg_h2d.argtypes = [vp, vp, vp, sz]
+    L.zg_d2h.argtypes = [vp, vp, vp, sz]
+    L.zg_srs_load.argtypes = [vp, u32, vp, vp]
+    L.zg_msm.argtypes = [vp, ci, vp, sz, vp]
+    L.zg_msm_batch.argtypes = [vp, ci, vp, sz, sz, vp]
+    L.zg_msm_dev.argtypes = [vp, ci, vp, sz, sz, sz, vp]
+    L.zg_ntt.argtypes = [vp, vp, u32, vp]
+    L.zg_ntt_dev.argtypes = [vp, vp, vp, u32, vp, sz, sz]
+    L.zg_lagrange_to_coeff.argtypes = [vp, vp, u32]
+    L.zg_lagrange_to_coeff_dev.argtypes = [vp, vp, vp, u32, sz, sz]
+    L.zg_coeff_to_extended.argtypes = [vp, vp, u32, u32, vp]
+    L.zg_coeff_to_extended_dev.argtypes = [vp, vp, sz, u32, u32, vp, sz, sz]
+    L.zg_extended_to_coeff.argtypes = [vp, vp, u32, u32, sz, vp]
+    L.zg_extended_to_coeff_dev.argtypes = [vp, vp, u32, u32, sz, vp]
+    L.zg_bench_int_pipe.argtypes = [vp, ci, u32, ctypes.POINTER(ctypes.c_double)]
+    L.zg_debug_field_op.argtypes = [vp, ci, ci, vp, vp, vp, sz]
+    _lib = L
+    return L
+
+
+def _np(a, last):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    if a.shape[-1] != last:
+        raise ValueError("expected trailing dimension %d, got shape %s" % (last, a.shape))
+    return a
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class Context:
+    """One GPU, one stream.  `stream` may be a raw cudaStream_t handle (int), e.g.
+    torch.cuda.current_stream().cuda_stream, so that torch CUDA events time this context's work."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self._L = load_library()
+        h = ctypes.c_void_p()
+        rc = self._L.zg_ctx_create(device, ctypes.c_void_p(stream) if stream else None, ctypes.byref(h))
+        if rc != ZG_OK:
+            raise ZgError(rc, "zg_ctx_create failed (no CUDA device %d? there is no CPU fallback)" % device)
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.zg_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != ZG_OK:
+            raise ZgError(rc, self._L.zg_last_error(self._h).decode())
+
+    def sync(self):
+        self._ck(self._L.zg_sync(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.zg_launch_count(self._h))
+
+    # ---- SRS / MSM ----
+    def srs_load(self, k: int, g=None, g_lagrange=None):
+        n = 1 << k
+        g = None if g is None else _np(g, 8)
+        gl = None if g_lagrange is None else _np(g_lagrange, 8)
+        for a in (g, gl):
+            if a is not None and a.shape[0] != n:
+                raise ValueError("SRS basis must have 2^k points")
+        self._ck(self._L.zg_srs_load(self._h, k, None if g is None else _ptr(g), None if gl is None else _ptr(gl)))
+
+    def msm(self, basis: int, scalars) -> np.ndarray:
+        s = _np(scalars, 4)
+        out = np.zeros(12, dtype=np.uint64)
+        self._ck(self._L.zg_msm(self._h, basis, _ptr(s), s.shape[0], _ptr(out)))
+        return out
+
+    def msm_batch(self, basis: int, scalar_list) -> np.ndarray:
+        arrs = [_np(s, 4) for s in scalar_list]
+        n = arrs[0].shape[0]
+        assert all(a.shape[0] == n for a in arrs)
+        ptrs = (ctypes.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+        out = np.zeros((len(arrs), 12), dtype=np.uint64)
+        self._ck(self._L.zg_msm_batch(self._h, basis, ptrs, n, len(arrs), _ptr(out)))
+        return out
+
+    def msm_dev(self, basis: int, scalars_ptr: int, stride: int, n: int, count: int, out_ptr: int):
+        self._ck(self._L.zg_msm_dev(self._h, basis, scalars_ptr, stride, n, count, out_ptr))
+
+    # ---- NTT family ----
+    def ntt(self, a, log_n: int, omega) -> np.ndarray:
+        a = _np(a, 4).copy()
+        w = _np(omega, 4)
+        self._ck(self._L.zg_ntt(self._h, _ptr(a), log_n, _ptr(w)))
+        return a
+
+    def ntt_dev(self, in_ptr: int, out_ptr: int, log_n: int, omega, batch: int = 1, stride: int | None = None):
+        w = _np(omega, 4)
+        self._ck(self._L.zg_ntt_dev(self._h, in_ptr, out_ptr, log_n, _ptr(w), batch, stride or (1 << log_n)))
+
+    def lagrange_to_coeff(self, a, k: int) -> np.ndarray:
+        a = _np(a, 4).copy()
+        self._ck(self._L.zg_lagrange_to_coeff(self._h, _ptr(a), k))
+        return a
+
+    def lagrange_to_coeff_dev(self, in_ptr, out_ptr, k, batch=1, stride=None):
+        self._ck(self._L.zg_lagrange_to_coeff_dev(self._h, in_ptr, out_ptr, k, batch, stride or (1 << k)))
+
+    def coeff_to_extended(self, coeff, k: int, ext_k: int) -> np.ndarray:
+        c = _np(coeff, 4)
+        out = np.zeros((1 << ext_k, 4), dtype=np.uint64)
+        self._ck(self._L.zg_coeff_to_extended(self._h, _ptr(c), k, ext_k, _ptr(out)))
+        return out
+
+    def coeff_to_extended_dev(self, in_ptr, in_stride, k, ext_k, out_ptr, out_stride, batch=1):
+        self._ck(self._L.zg_coeff_to_extended_dev(self._h, in_ptr, in_stride, k, ext_k, out_ptr, out_stride, batch))
+
+    def extended_to_coeff(self, ext, k: int, ext_k: int, keep: int) -> np.ndarray:
+        e = _np(ext, 4)
+        out = np.zeros((keep, 4), dtype=np.uint64)
+        self._ck(self._L.zg_extended_to_coeff(self._h, _ptr(e), k, ext_k, keep, _ptr(out)))
+        return out
+
+    def extended_to_coeff_dev(self, ext_ptr, k, ext_k, keep, out_ptr):
+        self._ck(self._L.zg_extended_to_coeff_dev(self._h, ext_ptr, k, ext_k, keep, out_ptr))
+
+    # ---- micro-benchmarks ----
+    def bench_int_pipe(self, kind: int, iters: int = 4096) -> float:
+        v = ctypes.c_double()
+        self._ck(self._L.zg_bench_int_pipe(self._h, kind, iters, ctypes.byref(v)))
+        return v.value
+
+    def debug_field_op(self, field: int, op: int, a, b=None) -> np.ndarray:
+        a = _np(a, 4)
+        b = a if b is None else _np(b, 4)
+        out = np.zeros_like(a)
+        self._ck(self._L.zg_debug_field_op(self._h, field, op, _ptr(a), _ptr(b), _ptr(out), a.shape[0]))
+        return out

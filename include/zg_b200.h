@@ -1,0 +1,123 @@
+/* zg_b200 -- C ABI of the B200-native halo2/KZG proving backend for BN254.
+ *
+ * This is the drop-in boundary for the proving hot path that `zero_g` reaches through
+ * halo2_proofs (tag v2023_04_20) from /root/reference/src/wnn.rs:226-228 (keygen_vk/keygen_pk)
+ * and :242-259 (create_proof).  halo2_proofs has no plugin interface; the seams are its free
+ * functions / inherent methods, and each entry point below names the one it replaces.  A
+ * maintainer binds these from a patched halo2_proofs (Cargo `[patch]`, the mechanism the
+ * reference already uses at Cargo.toml:14-18); see INTEGRATION.md for the Rust `extern "C"` stub.
+ *
+ * Conventions
+ *  - every function returns 0 (ZG_OK) or a negative ZG_E_* code and never throws or aborts
+ *    across the boundary; zg_last_error(ctx) returns a message for the last failure.
+ *  - zg_fr / zg_fq: 4 x u64 little-endian limbs in Montgomery form (R = 2^256): the in-memory
+ *    layout of halo2curves 0.3.3 `bn256::Fr` / `Fq`, so Rust passes `&[Fr]` unconverted.
+ *  - zg_g1_affine = {x, y} (identity = (0,0)) = halo2curves `G1Affine`; zg_g1 = Jacobian
+ *    {x, y, z} (identity z = 0) = halo2curves `G1`.  A zg_g1 result is a valid representative of
+ *    the mathematically unique group element; only its affine normalisation is canonical.
+ *  - plain names take HOST pointers and include the host<->device copies; `_dev` names take
+ *    DEVICE pointers on the context's device and enqueue on the context's stream without
+ *    synchronising (the caller synchronises with zg_sync or its own stream primitives).
+ *  - a zg_ctx is bound to one CUDA device and one stream, is NOT thread-safe, and owns all the
+ *    device memory it allocates.  Distinct contexts are independent (one per GPU / per process).
+ *  - there is no CPU fallback: without a CUDA device zg_ctx_create fails with ZG_E_CUDA.
+ */
+#ifndef ZG_B200_H
+#define ZG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct zg_ctx zg_ctx;
+
+typedef struct { uint64_t l[4]; } zg_fr;
+typedef struct { uint64_t l[4]; } zg_fq;
+typedef struct { zg_fq x, y; } zg_g1_affine;
+typedef struct { zg_fq x, y, z; } zg_g1;
+
+enum {
+  ZG_OK = 0,
+  ZG_E_INVALID = -1,  /* bad argument */
+  ZG_E_CUDA = -2,     /* CUDA runtime error (message in zg_last_error) */
+  ZG_E_STATE = -3,    /* required object (SRS, pk) not loaded */
+  ZG_E_NOMEM = -4,
+  ZG_E_SYNTH = -5,    /* prover-level failure, e.g. lookup input not in table (plonk::Error) */
+};
+
+enum { ZG_BASIS_MONOMIAL = 0, ZG_BASIS_LAGRANGE = 1 };
+
+/* ---- context ------------------------------------------------------------------------- */
+/* `stream` is a cudaStream_t to enqueue on (e.g. the caller's current stream) or NULL to let the
+ * context create its own non-blocking stream. */
+int zg_ctx_create(int device, void* stream, zg_ctx** out);
+void zg_ctx_destroy(zg_ctx* ctx);
+const char* zg_last_error(const zg_ctx* ctx);
+int zg_sync(zg_ctx* ctx);
+/* number of kernels this context has launched so far (for bench.py's `gpu_launches`) */
+uint64_t zg_launch_count(const zg_ctx* ctx);
+const char* zg_version(void);
+
+/* raw device memory owned by the caller, on the context's device */
+int zg_dev_alloc(zg_ctx* ctx, size_t bytes, void** out);
+int zg_dev_free(zg_ctx* ctx, void* p);
+int zg_h2d(zg_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+int zg_d2h(zg_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+
+/* ---- SRS: halo2_proofs ParamsKZG<Bn256>::{g, g_lagrange}  (src/main.rs:232, src/io.rs:139-146)
+ * Uploads both bases (n = 2^k points each; either may be NULL) and builds the fixed-base window
+ * tables used by every MSM on that basis.  One SRS per context. */
+int zg_srs_load(zg_ctx* ctx, uint32_t k, const zg_g1_affine* g, const zg_g1_affine* g_lagrange);
+
+/* ---- MSM: arithmetic::best_multiexp via ParamsKZG::commit (basis 0) / commit_lagrange (1) --- */
+/* out = sum_i scalars[i] * basis[i], n <= 2^k */
+int zg_msm(zg_ctx* ctx, int basis, const zg_fr* scalars, size_t n, zg_g1* out);
+/* `count` MSMs of n scalars each (one Fiat-Shamir round's commitments) in one pipeline */
+int zg_msm_batch(zg_ctx* ctx, int basis, const zg_fr* const* scalars, size_t n, size_t count,
+                 zg_g1* out);
+/* device-resident scalars: polynomial j starts at scalars_dev + j*stride (elements);
+ * out_dev receives `count` zg_g1 */
+int zg_msm_dev(zg_ctx* ctx, int basis, const zg_fr* scalars_dev, size_t stride, size_t n,
+               size_t count, zg_g1* out_dev);
+
+/* ---- NTT: arithmetic::best_fft and the EvaluationDomain transforms ---------------------- */
+/* in place, natural order in and out, a[i] <- sum_j a[j] * omega^(ij); n = 2^log_n */
+int zg_ntt(zg_ctx* ctx, zg_fr* a, uint32_t log_n, const zg_fr* omega);
+/* `batch` transforms, polynomial j at in_dev + j*stride -> out_dev + j*stride (in == out allowed) */
+int zg_ntt_dev(zg_ctx* ctx, const zg_fr* in_dev, zg_fr* out_dev, uint32_t log_n, const zg_fr* omega,
+               size_t batch, size_t stride);
+/* EvaluationDomain::lagrange_to_coeff: inverse NTT over the 2^k domain (scaled by 1/n) */
+int zg_lagrange_to_coeff(zg_ctx* ctx, zg_fr* a, uint32_t k);
+int zg_lagrange_to_coeff_dev(zg_ctx* ctx, const zg_fr* in_dev, zg_fr* out_dev, uint32_t k,
+                             size_t batch, size_t stride);
+/* EvaluationDomain::coeff_to_extended: coeff (2^k) -> evaluations over the coset zeta*<omega_ext>
+ * of size 2^ext_k (zeta = Fr::ZETA, as upstream's distribute_powers_zeta) */
+int zg_coeff_to_extended(zg_ctx* ctx, const zg_fr* coeff, uint32_t k, uint32_t ext_k, zg_fr* out);
+int zg_coeff_to_extended_dev(zg_ctx* ctx, const zg_fr* coeff_dev, size_t in_stride, uint32_t k,
+                             uint32_t ext_k, zg_fr* out_dev, size_t out_stride, size_t batch);
+/* EvaluationDomain::extended_to_coeff: inverse of the above; writes the first `keep` coefficients */
+int zg_extended_to_coeff(zg_ctx* ctx, const zg_fr* ext, uint32_t k, uint32_t ext_k, size_t keep,
+                         zg_fr* out);
+int zg_extended_to_coeff_dev(zg_ctx* ctx, const zg_fr* ext_dev, uint32_t k, uint32_t ext_k,
+                             size_t keep, zg_fr* out_dev);
+
+/* ---- micro-benchmarks used for the integer-pipe roofline (bench.py) ---------------------- */
+/* runs `iters` dependent-free IMAD-class instructions per thread on every SM and returns the
+ * achieved rate in 1e9 thread-instructions per second; kind 0 = IMAD (32-bit), 1 = IMAD.WIDE,
+ * 2 = Fr Montgomery multiplications, portable body (result in 1e9 mulmod/s), 3 = same, PTX
+ * carry-chain body */
+int zg_bench_int_pipe(zg_ctx* ctx, int kind, uint32_t iters, double* giga_per_s);
+
+/* ---- diagnostics (parity tests) --------------------------------------------------------- */
+/* element-wise device field op on host arrays of n elements; field 0 = Fr, 1 = Fq;
+ * op 0 mul, 1 mul (portable body), 2 mul (PTX body), 3 add, 4 sub, 5 inverse(a), 6 from_mont(a),
+ * 7 to_mont(a) */
+int zg_debug_field_op(zg_ctx* ctx, int field, int op, const void* a, const void* b, void* out, size_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZG_B200_H */

@@ -1,0 +1,182 @@
+"""ctypes front-end of the C oracle (oracle/zg_oracle.c).  TEST INFRASTRUCTURE ONLY:
+imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference legs."""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _cpu_tag() -> str:
+    """-march=native output is only valid on the CPU that built it; the GPU box has another
+    host CPU, so the library name carries a hash of this machine's ISA flags."""
+    import hashlib
+    flags = ""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    flags = line
+                    break
+    except OSError:
+        pass
+    return hashlib.sha1(flags.encode()).hexdigest()[:10]
+
+
+_SO = os.path.join(_HERE, "build", "libzg_oracle-%s.so" % _cpu_tag())
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "zg_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "OUT=" + _SO])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(build())
+        _lib.zgo_num_threads.restype = ctypes.c_int
+    return _lib
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _fr(a) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    assert a.shape[-1] == 4
+    return a
+
+
+def num_threads() -> int:
+    return lib().zgo_num_threads()
+
+
+def best_multiexp(coeffs: np.ndarray, bases: np.ndarray, threads: int = 0) -> np.ndarray:
+    """halo2 best_multiexp; coeffs (n,4) Fr Montgomery, bases (n,8) G1Affine -> (12,) Jacobian."""
+    coeffs, bases = _fr(coeffs), np.ascontiguousarray(bases, dtype=np.uint64)
+    n = coeffs.shape[0]
+    assert bases.shape == (n, 8)
+    out = np.zeros(12, dtype=np.uint64)
+    lib().zgo_best_multiexp(_p(coeffs), _p(bases), ctypes.c_size_t(n), ctypes.c_int(threads), _p(out))
+    return out
+
+
+def msm_naive(coeffs, bases) -> np.ndarray:
+    coeffs, bases = _fr(coeffs), np.ascontiguousarray(bases, dtype=np.uint64)
+    out = np.zeros(12, dtype=np.uint64)
+    lib().zgo_msm_naive(_p(coeffs), _p(bases), ctypes.c_size_t(coeffs.shape[0]), _p(out))
+    return out
+
+
+def g1_to_affine(jac: np.ndarray) -> np.ndarray:
+    jac = np.ascontiguousarray(jac, dtype=np.uint64).reshape(-1, 12)
+    out = np.zeros((jac.shape[0], 8), dtype=np.uint64)
+    lib().zgo_g1_to_affine(_p(jac), _p(out), ctypes.c_size_t(jac.shape[0]))
+    return out
+
+
+def srs_monomial(s_mont: np.ndarray, gen_affine: np.ndarray, n: int) -> np.ndarray:
+    out = np.zeros((n, 8), dtype=np.uint64)
+    lib().zgo_srs_monomial(_p(_fr(s_mont)), _p(np.ascontiguousarray(gen_affine, dtype=np.uint64)), ctypes.c_size_t(n), _p(out))
+    return out
+
+
+def g1_mul_many(scalars: np.ndarray, gen_affine: np.ndarray) -> np.ndarray:
+    scalars = _fr(scalars)
+    out = np.zeros((scalars.shape[0], 8), dtype=np.uint64)
+    lib().zgo_g1_mul_many(_p(scalars), _p(np.ascontiguousarray(gen_affine, dtype=np.uint64)), ctypes.c_size_t(scalars.shape[0]), _p(out))
+    return out
+
+
+def best_fft(a: np.ndarray, omega: np.ndarray, log_n: int, threads: int = 0) -> np.ndarray:
+    """halo2 best_fft on a copy; a (n,4) Fr Montgomery."""
+    a = _fr(a).copy()
+    assert a.shape[0] == 1 << log_n
+    lib().zgo_best_fft(_p(a), _p(_fr(omega)), ctypes.c_uint32(log_n), ctypes.c_int(threads))
+    return a
+
+
+def _vec2(name):
+    def f(a, b):
+        a, b = _fr(a), _fr(b)
+        o = np.empty_like(a)
+        getattr(lib(), name)(_p(a), _p(b), _p(o), ctypes.c_size_t(a.shape[0]))
+        return o
+    return f
+
+
+fr_mul_vec = _vec2("zgo_fr_mul_vec")
+fr_add_vec = _vec2("zgo_fr_add_vec")
+fr_sub_vec = _vec2("zgo_fr_sub_vec")
+
+
+def fr_scale_vec(a, s):
+    a = _fr(a)
+    o = np.empty_like(a)
+    lib().zgo_fr_scale_vec(_p(a), _p(_fr(s)), _p(o), ctypes.c_size_t(a.shape[0]))
+    return o
+
+
+def fr_scale_mod3(a, pw3):
+    a = _fr(a).copy()
+    lib().zgo_fr_scale_mod3(_p(a), _p(_fr(pw3)), ctypes.c_size_t(a.shape[0]))
+    return a
+
+
+def fr_batch_invert(a):
+    a = _fr(a).copy()
+    lib().zgo_fr_batch_invert(_p(a), ctypes.c_size_t(a.shape[0]))
+    return a
+
+
+def fr_eval_poly(c, x):
+    c = _fr(c)
+    out = np.zeros(4, dtype=np.uint64)
+    lib().zgo_fr_eval_poly(_p(c), ctypes.c_size_t(c.shape[0]), _p(_fr(x)), _p(out))
+    return out
+
+
+def fr_from_mont(a):
+    a = _fr(a)
+    o = np.empty_like(a)
+    lib().zgo_fr_from_mont_vec(_p(a), _p(o), ctypes.c_size_t(a.reshape(-1, 4).shape[0]))
+    return o
+
+
+def fr_to_mont(a):
+    a = _fr(a)
+    o = np.empty_like(a)
+    lib().zgo_fr_to_mont_vec(_p(a), _p(o), ctypes.c_size_t(a.reshape(-1, 4).shape[0]))
+    return o
+
+
+def fq_from_mont(a):
+    a = _fr(a)
+    o = np.empty_like(a)
+    lib().zgo_fq_from_mont_vec(_p(a), _p(o), ctypes.c_size_t(a.reshape(-1, 4).shape[0]))
+    return o
+
+
+def fq_to_mont(a):
+    a = _fr(a)
+    o = np.empty_like(a)
+    lib().zgo_fq_to_mont_vec(_p(a), _p(o), ctypes.c_size_t(a.reshape(-1, 4).shape[0]))
+    return o
+
+
+def g1_sequence(gen_affine: np.ndarray, n: int) -> np.ndarray:
+    """[1]G, [2]G, ... [n]G affine: cheap synthetic bases for MSM timing."""
+    out = np.zeros((n, 8), dtype=np.uint64)
+    lib().zgo_g1_sequence(_p(np.ascontiguousarray(gen_affine, dtype=np.uint64)), ctypes.c_size_t(n), _p(out))
+    return out

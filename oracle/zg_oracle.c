@@ -1,0 +1,506 @@
+/* zg_oracle.c -- CPU restatement of the halo2 proving arithmetic.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this library; the product (libzg_b200.so) never links or calls it.
+ *
+ * The algorithms restated here live in third-party crates that /root/reference pins but does
+ * not vendor (Cargo.toml:14-28): halo2_proofs tag v2023_04_20 (`arithmetic::{best_multiexp,
+ * multiexp_serial, best_fft, recursive_butterfly_arithmetic, eval_polynomial, kate_division}`,
+ * `poly::EvaluationDomain`) and halo2curves tag 0.3.3 (`bn256::{Fr,Fq,G1}` 4x64-bit Montgomery).
+ * They are reached from /root/reference/src/wnn.rs:226-228 and :242-259.  The reference cannot
+ * be compiled here (no Rust toolchain), so this is a "port" baseline, and PARITY IS UNPINNED
+ * against the real crate: what pins this file are mathematical identities (tests/test_oracle.py:
+ * naive DFT, double-and-add MSM, Python big-int field arithmetic).
+ *
+ * Threading mirrors upstream's rayon use with OpenMP: best_multiexp splits the points into one
+ * contiguous chunk per thread and runs the serial Pippenger (window c = ceil(ln n)) on each;
+ * best_fft bit-reverses, precomputes n/2 twiddles serially, then recurses on halves in parallel.
+ */
+#include <math.h>
+#include <omp.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef unsigned __int128 u128;
+typedef struct { uint64_t l[4]; } fe;           /* Montgomery form, R = 2^256 */
+typedef struct { fe x, y; } g1a;                /* affine, identity = (0,0) */
+typedef struct { fe x, y, z; } g1j;             /* Jacobian, identity z = 0 */
+
+typedef struct { uint64_t p[4]; uint64_t inv; fe r, r2; } field_t;
+
+static const field_t FR = {
+  {0x43e1f593f0000001ull, 0x2833e84879b97091ull, 0xb85045b68181585dull, 0x30644e72e131a029ull},
+  0xc2e1f593efffffffull,
+  {{0xac96341c4ffffffbull, 0x36fc76959f60cd29ull, 0x666ea36f7879462eull, 0x0e0a77c19a07df2full}},
+  {{0x1bb8e645ae216da7ull, 0x53fe3ab1e35c59e3ull, 0x8c49833d53bb8085ull, 0x0216d0b17f4e44a5ull}}};
+static const field_t FQ = {
+  {0x3c208c16d87cfd47ull, 0x97816a916871ca8dull, 0xb85045b68181585dull, 0x30644e72e131a029ull},
+  0x87d20782e4866389ull,
+  {{0xd35d438dc58f0d9dull, 0x0a78eb28f5c70b3dull, 0x666ea36f7879462cull, 0x0e0a77c19a07df2full}},
+  {{0xf32cfc5b538afa89ull, 0xb5e71911d44501fbull, 0x47ab1eff0a417ff6ull, 0x06d89f71cab8351full}}};
+
+/* ---- field (halo2curves src/bn256/{fr,fq}.rs via field_arithmetic! macro: mul = schoolbook
+ * 4x4 then montgomery_reduce; add/sub with conditional correction) ---- */
+static inline int fe_is_zero(const fe* a) { return (a->l[0] | a->l[1] | a->l[2] | a->l[3]) == 0; }
+static inline int fe_eq(const fe* a, const fe* b) {
+  return ((a->l[0] ^ b->l[0]) | (a->l[1] ^ b->l[1]) | (a->l[2] ^ b->l[2]) | (a->l[3] ^ b->l[3])) == 0;
+}
+static inline void fe_cond_sub(fe* r, const uint64_t t[4], const field_t* F) {
+  uint64_t u[4];
+  u128 bw = 0;
+  for (int i = 0; i < 4; i++) {
+    u128 d = (u128)t[i] - F->p[i] - (uint64_t)bw;
+    u[i] = (uint64_t)d;
+    bw = (d >> 64) & 1;
+  }
+  const uint64_t* s = bw ? t : u;
+  for (int i = 0; i < 4; i++) r->l[i] = s[i];
+}
+static inline void fe_add(fe* r, const fe* a, const fe* b, const field_t* F) {
+  uint64_t t[4];
+  u128 c = 0;
+  for (int i = 0; i < 4; i++) {
+    c += (u128)a->l[i] + b->l[i];
+    t[i] = (uint64_t)c;
+    c >>= 64;
+  }
+  fe_cond_sub(r, t, F);
+}
+static inline void fe_sub(fe* r, const fe* a, const fe* b, const field_t* F) {
+  uint64_t t[4];
+  u128 bw = 0;
+  for (int i = 0; i < 4; i++) {
+    u128 d = (u128)a->l[i] - b->l[i] - (uint64_t)bw;
+    t[i] = (uint64_t)d;
+    bw = (d >> 64) & 1;
+  }
+  if (bw) {
+    u128 c = 0;
+    for (int i = 0; i < 4; i++) {
+      c += (u128)t[i] + F->p[i];
+      t[i] = (uint64_t)c;
+      c >>= 64;
+    }
+  }
+  for (int i = 0; i < 4; i++) r->l[i] = t[i];
+}
+static inline void fe_neg(fe* r, const fe* a, const field_t* F) {
+  fe z = {{0, 0, 0, 0}};
+  fe_sub(r, &z, a, F);
+}
+static inline void fe_mul(fe* r, const fe* a, const fe* b, const field_t* F) {
+  uint64_t t[8] = {0};
+  for (int i = 0; i < 4; i++) {
+    u128 c = 0;
+    for (int j = 0; j < 4; j++) {
+      c += (u128)a->l[i] * b->l[j] + t[i + j];
+      t[i + j] = (uint64_t)c;
+      c >>= 64;
+    }
+    t[i + 4] = (uint64_t)c;
+  }
+  uint64_t carry2 = 0;
+  for (int i = 0; i < 4; i++) {
+    uint64_t k = t[i] * F->inv;
+    u128 c = 0;
+    for (int j = 0; j < 4; j++) {
+      c += (u128)k * F->p[j] + t[i + j];
+      t[i + j] = (uint64_t)c;
+      c >>= 64;
+    }
+    u128 s = (u128)t[i + 4] + (uint64_t)c + carry2;
+    t[i + 4] = (uint64_t)s;
+    carry2 = (uint64_t)(s >> 64);
+  }
+  fe_cond_sub(r, t + 4, F);
+}
+static inline void fe_sqr(fe* r, const fe* a, const field_t* F) { fe_mul(r, a, a, F); }
+static void fe_pow(fe* r, const fe* a, const uint64_t e[4], const field_t* F) {
+  fe acc = F->r;
+  for (int i = 3; i >= 0; i--)
+    for (int b = 63; b >= 0; b--) {
+      fe_sqr(&acc, &acc, F);
+      if ((e[i] >> b) & 1) fe_mul(&acc, &acc, a, F);
+    }
+  *r = acc;
+}
+static void fe_inv(fe* r, const fe* a, const field_t* F) { /* a^(p-2); 0 -> 0 */
+  uint64_t e[4] = {F->p[0] - 2, F->p[1], F->p[2], F->p[3]};
+  fe_pow(r, a, e, F);
+}
+static inline void fe_from_mont(uint64_t out[4], const fe* a, const field_t* F) { /* to_repr */
+  fe one = {{1, 0, 0, 0}}, t;
+  fe_mul(&t, a, &one, F);
+  memcpy(out, t.l, 32);
+}
+
+/* ---- G1 (halo2curves new_curve_impl!: Jacobian add-2007-bl / dbl-2009-l / madd-2007-bl) ---- */
+static inline int j_is_id(const g1j* p) { return fe_is_zero(&p->z); }
+static inline void j_set_id(g1j* p) { memset(p, 0, sizeof *p); p->y = FQ.r; }
+static void j_double(g1j* r, const g1j* p) {
+  if (j_is_id(p)) { *r = *p; return; }
+  const field_t* F = &FQ;
+  fe a, b, c, d, e, f, t, x3, y3, z3;
+  fe_sqr(&a, &p->x, F);
+  fe_sqr(&b, &p->y, F);
+  fe_sqr(&c, &b, F);
+  fe_add(&d, &p->x, &b, F); fe_sqr(&d, &d, F); fe_sub(&d, &d, &a, F); fe_sub(&d, &d, &c, F); fe_add(&d, &d, &d, F);
+  fe_add(&e, &a, &a, F); fe_add(&e, &e, &a, F);
+  fe_sqr(&f, &e, F);
+  fe_mul(&z3, &p->z, &p->y, F); fe_add(&z3, &z3, &z3, F);
+  fe_sub(&x3, &f, &d, F); fe_sub(&x3, &x3, &d, F);
+  fe_add(&c, &c, &c, F); fe_add(&c, &c, &c, F); fe_add(&c, &c, &c, F);
+  fe_sub(&t, &d, &x3, F); fe_mul(&y3, &e, &t, F); fe_sub(&y3, &y3, &c, F);
+  r->x = x3; r->y = y3; r->z = z3;
+}
+static void j_add(g1j* r, const g1j* p, const g1j* q) {
+  if (j_is_id(p)) { *r = *q; return; }
+  if (j_is_id(q)) { *r = *p; return; }
+  const field_t* F = &FQ;
+  fe z1z1, z2z2, u1, u2, s1, s2, t;
+  fe_sqr(&z1z1, &p->z, F);
+  fe_sqr(&z2z2, &q->z, F);
+  fe_mul(&u1, &p->x, &z2z2, F);
+  fe_mul(&u2, &q->x, &z1z1, F);
+  fe_mul(&t, &q->z, &z2z2, F); fe_mul(&s1, &p->y, &t, F);
+  fe_mul(&t, &p->z, &z1z1, F); fe_mul(&s2, &q->y, &t, F);
+  if (fe_eq(&u1, &u2)) {
+    if (fe_eq(&s1, &s2)) { j_double(r, p); } else { j_set_id(r); }
+    return;
+  }
+  fe h, i, j, rr, v, x3, y3, z3;
+  fe_sub(&h, &u2, &u1, F);
+  fe_add(&i, &h, &h, F); fe_sqr(&i, &i, F);
+  fe_mul(&j, &h, &i, F);
+  fe_sub(&rr, &s2, &s1, F); fe_add(&rr, &rr, &rr, F);
+  fe_mul(&v, &u1, &i, F);
+  fe_sqr(&x3, &rr, F); fe_sub(&x3, &x3, &j, F); fe_sub(&x3, &x3, &v, F); fe_sub(&x3, &x3, &v, F);
+  fe_mul(&s1, &s1, &j, F); fe_add(&s1, &s1, &s1, F);
+  fe_sub(&t, &v, &x3, F); fe_mul(&y3, &rr, &t, F); fe_sub(&y3, &y3, &s1, F);
+  fe_add(&z3, &p->z, &q->z, F); fe_sqr(&z3, &z3, F); fe_sub(&z3, &z3, &z1z1, F); fe_sub(&z3, &z3, &z2z2, F);
+  fe_mul(&z3, &z3, &h, F);
+  r->x = x3; r->y = y3; r->z = z3;
+}
+static inline int a_is_id(const g1a* p) { return fe_is_zero(&p->x) && fe_is_zero(&p->y); }
+static void j_from_affine(g1j* r, const g1a* p) {
+  if (a_is_id(p)) { j_set_id(r); return; }
+  r->x = p->x; r->y = p->y; r->z = FQ.r;
+}
+static void j_add_affine(g1j* r, const g1j* p, const g1a* q) {
+  if (a_is_id(q)) { *r = *p; return; }
+  if (j_is_id(p)) { j_from_affine(r, q); return; }
+  const field_t* F = &FQ;
+  fe z1z1, u2, s2, t;
+  fe_sqr(&z1z1, &p->z, F);
+  fe_mul(&u2, &q->x, &z1z1, F);
+  fe_mul(&t, &p->z, &z1z1, F); fe_mul(&s2, &q->y, &t, F);
+  if (fe_eq(&p->x, &u2)) {
+    if (fe_eq(&p->y, &s2)) { j_double(r, p); } else { j_set_id(r); }
+    return;
+  }
+  fe h, hh, i, j, rr, v, x3, y3, z3;
+  fe_sub(&h, &u2, &p->x, F);
+  fe_sqr(&hh, &h, F);
+  fe_add(&i, &hh, &hh, F); fe_add(&i, &i, &i, F);
+  fe_mul(&j, &h, &i, F);
+  fe_sub(&rr, &s2, &p->y, F); fe_add(&rr, &rr, &rr, F);
+  fe_mul(&v, &p->x, &i, F);
+  fe_sqr(&x3, &rr, F); fe_sub(&x3, &x3, &j, F); fe_sub(&x3, &x3, &v, F); fe_sub(&x3, &x3, &v, F);
+  fe_mul(&j, &p->y, &j, F); fe_add(&j, &j, &j, F);
+  fe_sub(&t, &v, &x3, F); fe_mul(&y3, &rr, &t, F); fe_sub(&y3, &y3, &j, F);
+  fe_add(&z3, &p->z, &h, F); fe_sqr(&z3, &z3, F); fe_sub(&z3, &z3, &z1z1, F); fe_sub(&z3, &z3, &hh, F);
+  r->x = x3; r->y = y3; r->z = z3;
+}
+static void j_to_affine(g1a* r, const g1j* p) {
+  if (j_is_id(p)) { memset(r, 0, sizeof *r); return; }
+  fe zi, zi2, zi3;
+  fe_inv(&zi, &p->z, &FQ);
+  fe_sqr(&zi2, &zi, &FQ);
+  fe_mul(&zi3, &zi2, &zi, &FQ);
+  fe_mul(&r->x, &p->x, &zi2, &FQ);
+  fe_mul(&r->y, &p->y, &zi3, &FQ);
+}
+
+/* ---- best_multiexp (halo2_proofs arithmetic.rs) ---- */
+typedef struct { int kind; g1a a; g1j p; } bucket_t; /* 0 None, 1 Affine, 2 Projective */
+
+static size_t get_at(size_t segment, size_t c, const uint8_t bytes[32]) {
+  size_t skip_bits = segment * c, skip_bytes = skip_bits / 8;
+  if (skip_bytes >= 32) return 0;
+  uint8_t v[8] = {0};
+  for (size_t i = 0; i < 8 && skip_bytes + i < 32; i++) v[i] = bytes[skip_bytes + i];
+  uint64_t tmp;
+  memcpy(&tmp, v, 8);
+  tmp >>= skip_bits - skip_bytes * 8;
+  tmp %= (1ull << c);
+  return (size_t)tmp;
+}
+
+static void multiexp_serial(const fe* coeffs, const g1a* bases, size_t n, g1j* acc) {
+  uint8_t(*repr)[32] = malloc(n * 32);
+  for (size_t i = 0; i < n; i++) fe_from_mont((uint64_t*)repr[i], &coeffs[i], &FR);
+  size_t c;
+  if (n < 4) c = 1; else if (n < 32) c = 3; else c = (size_t)ceil(log((double)n));
+  size_t segments = 256 / c + 1;
+  size_t nb = ((size_t)1 << c) - 1;
+  bucket_t* buckets = malloc(nb * sizeof(bucket_t));
+  for (size_t seg = segments; seg-- > 0;) {
+    for (size_t i = 0; i < c; i++) j_double(acc, acc);
+    for (size_t b = 0; b < nb; b++) buckets[b].kind = 0;
+    for (size_t i = 0; i < n; i++) {
+      size_t co = get_at(seg, c, repr[i]);
+      if (co == 0) continue;
+      bucket_t* b = &buckets[co - 1];
+      if (b->kind == 0) { b->kind = 1; b->a = bases[i]; }
+      else if (b->kind == 1) { g1j t; j_from_affine(&t, &b->a); j_add_affine(&b->p, &t, &bases[i]); b->kind = 2; }
+      else { j_add_affine(&b->p, &b->p, &bases[i]); }
+    }
+    g1j running; j_set_id(&running);
+    for (size_t b = nb; b-- > 0;) {
+      if (buckets[b].kind == 1) j_add_affine(&running, &running, &buckets[b].a);
+      else if (buckets[b].kind == 2) j_add(&running, &running, &buckets[b].p);
+      j_add(acc, acc, &running);
+    }
+  }
+  free(buckets);
+  free(repr);
+}
+
+void zgo_best_multiexp(const fe* coeffs, const g1a* bases, size_t n, int threads, g1j* out) {
+  if (threads < 1) threads = omp_get_max_threads();
+  j_set_id(out);
+  if (n > (size_t)threads) {
+    size_t chunk = n / threads;
+    size_t num_chunks = (n + chunk - 1) / chunk;
+    g1j* results = malloc(num_chunks * sizeof(g1j));
+#pragma omp parallel for num_threads(threads) schedule(dynamic, 1)
+    for (size_t ci = 0; ci < num_chunks; ci++) {
+      size_t b = ci * chunk, e = b + chunk < n ? b + chunk : n;
+      j_set_id(&results[ci]);
+      multiexp_serial(coeffs + b, bases + b, e - b, &results[ci]);
+    }
+    for (size_t ci = 0; ci < num_chunks; ci++) j_add(out, out, &results[ci]);
+    free(results);
+  } else {
+    multiexp_serial(coeffs, bases, n, out);
+  }
+}
+
+void zgo_g1_to_affine(const g1j* in, g1a* out, size_t n) {
+  for (size_t i = 0; i < n; i++) j_to_affine(&out[i], &in[i]);
+}
+/* naive reference: sum of double-and-add scalar multiples (small n only) */
+void zgo_msm_naive(const fe* coeffs, const g1a* bases, size_t n, g1j* out) {
+  j_set_id(out);
+  for (size_t i = 0; i < n; i++) {
+    uint64_t s[4];
+    fe_from_mont(s, &coeffs[i], &FR);
+    g1j acc; j_set_id(&acc);
+    for (int w = 3; w >= 0; w--)
+      for (int b = 63; b >= 0; b--) {
+        j_double(&acc, &acc);
+        if ((s[w] >> b) & 1) j_add_affine(&acc, &acc, &bases[i]);
+      }
+    j_add(out, out, &acc);
+  }
+}
+/* [s^i]G for i < n from a known toy secret (test SRS); g_lagrange via zgo_srs_lagrange */
+void zgo_srs_monomial(const fe* s, const g1a* gen, size_t n, g1a* out) {
+  fe cur = FR.r;
+  fe* pw = malloc(n * sizeof(fe));
+  for (size_t i = 0; i < n; i++) { pw[i] = cur; fe_mul(&cur, &cur, s, &FR); }
+#pragma omp parallel for schedule(dynamic, 64)
+  for (size_t i = 0; i < n; i++) {
+    uint64_t e[4];
+    fe_from_mont(e, &pw[i], &FR);
+    g1j acc; j_set_id(&acc);
+    for (int w = 3; w >= 0; w--)
+      for (int b = 63; b >= 0; b--) {
+        j_double(&acc, &acc);
+        if ((e[w] >> b) & 1) j_add_affine(&acc, &acc, gen);
+      }
+    j_to_affine(&out[i], &acc);
+  }
+  free(pw);
+}
+/* scalar multiples of one generator by arbitrary Fr scalars (used for g_lagrange = [L_i(s)]G) */
+void zgo_g1_mul_many(const fe* scalars, const g1a* gen, size_t n, g1a* out) {
+#pragma omp parallel for schedule(dynamic, 64)
+  for (size_t i = 0; i < n; i++) {
+    uint64_t e[4];
+    fe_from_mont(e, &scalars[i], &FR);
+    g1j acc; j_set_id(&acc);
+    for (int w = 3; w >= 0; w--)
+      for (int b = 63; b >= 0; b--) {
+        j_double(&acc, &acc);
+        if ((e[w] >> b) & 1) j_add_affine(&acc, &acc, gen);
+      }
+    j_to_affine(&out[i], &acc);
+  }
+}
+
+/* ---- best_fft (halo2_proofs arithmetic.rs, v2023_04_20: bit-reverse, serial twiddle scan,
+ * recursive_butterfly_arithmetic with rayon::join -> OpenMP tasks) ---- */
+static size_t bitreverse(size_t n, size_t l) {
+  size_t r = 0;
+  for (size_t i = 0; i < l; i++) { r = (r << 1) | (n & 1); n >>= 1; }
+  return r;
+}
+static void butterflies(fe* a, size_t n, size_t twiddle_chunk, const fe* tw) {
+  if (n == 2) {
+    fe t = a[1];
+    a[1] = a[0];
+    fe_add(&a[0], &a[0], &t, &FR);
+    fe_sub(&a[1], &a[1], &t, &FR);
+    return;
+  }
+  fe* left = a; fe* right = a + n / 2;
+  if (n >= 4096) {
+#pragma omp task
+    butterflies(left, n / 2, twiddle_chunk * 2, tw);
+#pragma omp task
+    butterflies(right, n / 2, twiddle_chunk * 2, tw);
+#pragma omp taskwait
+  } else {
+    butterflies(left, n / 2, twiddle_chunk * 2, tw);
+    butterflies(right, n / 2, twiddle_chunk * 2, tw);
+  }
+  fe t = right[0];
+  right[0] = left[0];
+  fe_add(&left[0], &left[0], &t, &FR);
+  fe_sub(&right[0], &right[0], &t, &FR);
+  for (size_t i = 1; i < n / 2; i++) {
+    fe_mul(&t, &right[i], &tw[i * twiddle_chunk], &FR);
+    right[i] = left[i];
+    fe_add(&left[i], &left[i], &t, &FR);
+    fe_sub(&right[i], &right[i], &t, &FR);
+  }
+}
+void zgo_best_fft(fe* a, const fe* omega, uint32_t log_n, int threads) {
+  if (threads < 1) threads = omp_get_max_threads();
+  size_t n = (size_t)1 << log_n;
+  for (size_t k = 0; k < n; k++) {
+    size_t rk = bitreverse(k, log_n);
+    if (k < rk) { fe t = a[rk]; a[rk] = a[k]; a[k] = t; }
+  }
+  if (n == 1) return;
+  fe* tw = malloc((n / 2) * sizeof(fe));
+  fe w = FR.r;
+  for (size_t i = 0; i < n / 2; i++) { tw[i] = w; fe_mul(&w, &w, omega, &FR); }
+#pragma omp parallel num_threads(threads)
+#pragma omp single
+  butterflies(a, n, 1, tw);
+  free(tw);
+}
+
+/* elementwise helpers used by the Python-side restatement of EvaluationDomain / the prover */
+void zgo_fr_mul_vec(const fe* a, const fe* b, fe* o, size_t n) {
+#pragma omp parallel for
+  for (size_t i = 0; i < n; i++) fe_mul(&o[i], &a[i], &b[i], &FR);
+}
+void zgo_fr_add_vec(const fe* a, const fe* b, fe* o, size_t n) {
+#pragma omp parallel for
+  for (size_t i = 0; i < n; i++) fe_add(&o[i], &a[i], &b[i], &FR);
+}
+void zgo_fr_sub_vec(const fe* a, const fe* b, fe* o, size_t n) {
+#pragma omp parallel for
+  for (size_t i = 0; i < n; i++) fe_sub(&o[i], &a[i], &b[i], &FR);
+}
+void zgo_fr_scale_vec(const fe* a, const fe* s, fe* o, size_t n) {
+#pragma omp parallel for
+  for (size_t i = 0; i < n; i++) fe_mul(&o[i], &a[i], s, &FR);
+}
+/* a[i] *= pw[i % 3]  (distribute_powers_zeta) */
+void zgo_fr_scale_mod3(fe* a, const fe pw[3], size_t n) {
+#pragma omp parallel for
+  for (size_t i = 0; i < n; i++) if (i % 3) fe_mul(&a[i], &a[i], &pw[i % 3], &FR);
+}
+/* Montgomery batch inversion, zeros stay zero (ff::BatchInvert) */
+void zgo_fr_batch_invert(fe* a, size_t n) {
+  fe* pre = malloc(n * sizeof(fe));
+  fe acc = FR.r;
+  for (size_t i = 0; i < n; i++) {
+    pre[i] = acc;
+    if (!fe_is_zero(&a[i])) fe_mul(&acc, &acc, &a[i], &FR);
+  }
+  fe inv;
+  fe_inv(&inv, &acc, &FR);
+  for (size_t i = n; i-- > 0;) {
+    if (fe_is_zero(&a[i])) continue;
+    fe t;
+    fe_mul(&t, &inv, &pre[i], &FR);
+    fe_mul(&inv, &inv, &a[i], &FR);
+    a[i] = t;
+  }
+  free(pre);
+}
+/* eval_polynomial: Horner */
+void zgo_fr_eval_poly(const fe* c, size_t n, const fe* x, fe* out) {
+  fe acc = {{0, 0, 0, 0}};
+  for (size_t i = n; i-- > 0;) {
+    fe_mul(&acc, &acc, x, &FR);
+    fe_add(&acc, &acc, &c[i], &FR);
+  }
+  *out = acc;
+}
+/* to / from canonical little-endian integers */
+void zgo_fr_from_mont_vec(const fe* a, uint64_t* out, size_t n) {
+  for (size_t i = 0; i < n; i++) fe_from_mont(out + 4 * i, &a[i], &FR);
+}
+void zgo_fr_to_mont_vec(const uint64_t* in, fe* out, size_t n) {
+  for (size_t i = 0; i < n; i++) {
+    fe t;
+    memcpy(t.l, in + 4 * i, 32);
+    fe_mul(&out[i], &t, &FR.r2, &FR);
+  }
+}
+void zgo_fq_from_mont_vec(const fe* a, uint64_t* out, size_t n) {
+  for (size_t i = 0; i < n; i++) fe_from_mont(out + 4 * i, &a[i], &FQ);
+}
+void zgo_fq_to_mont_vec(const uint64_t* in, fe* out, size_t n) {
+  for (size_t i = 0; i < n; i++) {
+    fe t;
+    memcpy(t.l, in + 4 * i, 32);
+    fe_mul(&out[i], &t, &FQ.r2, &FQ);
+  }
+}
+int zgo_num_threads(void) { return omp_get_max_threads(); }
+
+/* Synthetic SRS-shaped bases for benchmarks: out[i] = [start + i + 1] * gen, affine.
+ * (A real ParamsKZG basis is [s^i]G; for timing an MSM any distinct curve points do.)
+ * Chunks are seeded by one scalar multiplication each and walked with mixed additions;
+ * the Jacobian points are normalised with one shared inversion per chunk. */
+void zgo_g1_sequence(const g1a* gen, size_t n, g1a* out) {
+  const size_t CH = 4096;
+  size_t nch = (n + CH - 1) / CH;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (size_t c = 0; c < nch; c++) {
+    size_t b = c * CH, e = b + CH < n ? b + CH : n, m = e - b;
+    g1j* jac = malloc(m * sizeof(g1j));
+    fe* pre = malloc(m * sizeof(fe));
+    g1j acc; j_set_id(&acc);
+    uint64_t k = b + 1;
+    for (int bit = 63; bit >= 0; bit--) {
+      j_double(&acc, &acc);
+      if ((k >> bit) & 1) j_add_affine(&acc, &acc, gen);
+    }
+    for (size_t i = 0; i < m; i++) {
+      jac[i] = acc;
+      j_add_affine(&acc, &acc, gen);
+    }
+    fe run = FQ.r;
+    for (size_t i = 0; i < m; i++) { pre[i] = run; fe_mul(&run, &run, &jac[i].z, &FQ); }
+    fe inv; fe_inv(&inv, &run, &FQ);
+    for (size_t i = m; i-- > 0;) {
+      fe zi, zi2, zi3;
+      fe_mul(&zi, &inv, &pre[i], &FQ);
+      fe_mul(&inv, &inv, &jac[i].z, &FQ);
+      fe_sqr(&zi2, &zi, &FQ);
+      fe_mul(&zi3, &zi2, &zi, &FQ);
+      fe_mul(&out[b + i].x, &jac[i].x, &zi2, &FQ);
+      fe_mul(&out[b + i].y, &jac[i].y, &zi3, &FQ);
+    }
+    free(jac); free(pre);
+  }
+}
