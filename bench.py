@@ -170,7 +170,10 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    ctx = zg_b200.Context(local, torch.cuda.current_stream().cuda_stream)
+    # a non-default torch stream: the context enqueues on it, so torch CUDA events time our kernels
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx = zg_b200.Context(local, stream.cuda_stream)
     hbm_peak, peak_src = peaks()
     logn, n = args.logn, 1 << args.logn
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
@@ -261,6 +264,7 @@ def main():
     imad_peak = ctx.bench_int_pipe(0, 4096)
     imad_wide = ctx.bench_int_pipe(1, 4096)
     mulmod_rate = ctx.bench_int_pipe(2, 256)
+    mulmod_ptx_rate = ctx.bench_int_pipe(3, 256)
     if args.workload == "ntt":
         ach = ntt_bytes(logn) / 1e9 / (ms_per_step * 1e-3)
         roof = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
@@ -279,7 +283,8 @@ def main():
         "vs_baseline": None, "dtype": "u256 (8x32-bit Montgomery limbs)", "data": "synthetic",
         "config": {"workload": "%s 2^%d, BN254, uniform scalars" % (args.workload, logn), "l2": "flushed between steps"},
         "roofline": roof,
-        "int_pipe": {"imad_gops": imad_peak, "imad_wide_gops": imad_wide, "fr_mulmod_gops": mulmod_rate},
+        "int_pipe": {"imad_gops": imad_peak, "imad_wide_gops": imad_wide, "fr_mulmod_portable_gops": mulmod_rate,
+                     "fr_mulmod_ptx_gops": mulmod_ptx_rate},
         "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches), "clocks": clocks,
     }

@@ -20,6 +20,8 @@ def ctx():
     import zg_b200
     assert torch.cuda.is_available(), "gpu-marked test running without a CUDA device"
     torch.cuda.set_device(0)
-    c = zg_b200.Context(0, torch.cuda.current_stream().cuda_stream)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    c = zg_b200.Context(0, stream.cuda_stream)
     yield c
     c.close()
