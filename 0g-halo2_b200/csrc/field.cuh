@@ -404,6 +404,19 @@ ZG_HD Fp<P> fp_pow_u64(const Fp<P>& a, uint64_t e) {
   uint32_t limbs[2] = {(uint32_t)e, (uint32_t)(e >> 32)};
   return fp_pow<P>(a, limbs, 2);
 }
+// a^e, square-and-multiply from the highest set bit of e (variable time in e)
+template <class P>
+ZG_HD Fp<P> fp_pow_var(const Fp<P>& a, uint64_t e) {
+  if (e == 0) return fp_one<P>();
+  int top = 63;
+  while (!((e >> top) & 1)) top--;
+  Fp<P> acc = a;
+  for (int b = top - 1; b >= 0; b--) {
+    acc = fp_sqr<P>(acc);
+    if ((e >> b) & 1) acc = fp_mul<P>(acc, a);
+  }
+  return acc;
+}
 // Fermat inverse a^(p-2); maps 0 -> 0 (same convention as ff::Field::invert().unwrap_or(0)
 // inside halo2's batch_invert, which skips zeros).
 template <class P>

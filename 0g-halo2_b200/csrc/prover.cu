@@ -1,0 +1,883 @@
+// Host orchestration of keygen and create_proof on one B200.
+//
+// Restates the stage order, Fiat-Shamir transcript and RNG draw order of halo2_proofs v2023_04_20
+// (un-vendored; /root/reference/Cargo.toml:21-25) `plonk::{keygen_vk, keygen_pk, create_proof}` with
+// `ProverGWC` and snark-verifier's `EvmTranscript`, as instantiated at /root/reference/src/wnn.rs:226-228
+// and :242-259.  All column arithmetic runs in the kernels of ntt.cu,
+// msm.cu, poly.cu, expr.cu and lookup.cu; the host only sequences rounds, hashes (keccak256) and
+// normalises <= 8 commitments per round.  Witness synthesis is the caller's (BASELINE north_star).
+#include <algorithm>
+#include <memory>
+#include "ctx.cuh"
+#include "expr.cuh"
+#include "lookup.cuh"
+#include "poly.cuh"
+
+using namespace zg;
+
+extern "C" int zg_msm_dev(zg_ctx*, int, const zg_fr*, size_t, size_t, size_t, zg_g1*);
+extern "C" int zg_lagrange_to_coeff_dev(zg_ctx*, const zg_fr*, zg_fr*, uint32_t, size_t, size_t);
+extern "C" int zg_coeff_to_extended_dev(zg_ctx*, const zg_fr*, size_t, uint32_t, uint32_t, zg_fr*, size_t, size_t);
+extern "C" int zg_extended_to_coeff_dev(zg_ctx*, const zg_fr*, uint32_t, uint32_t, size_t, zg_fr*);
+
+namespace {
+
+// ---- keccak256 ----------------------------------------------------------------------------------
+static const uint64_t KRC[24] = {
+    0x0000000000000001ull, 0x0000000000008082ull, 0x800000000000808Aull, 0x8000000080008000ull, 0x000000000000808Bull,
+    0x0000000080000001ull, 0x8000000080008081ull, 0x8000000000008009ull, 0x000000000000008Aull, 0x0000000000000088ull,
+    0x0000000080008009ull, 0x000000008000000Aull, 0x000000008000808Bull, 0x800000000000008Bull, 0x8000000000008089ull,
+    0x8000000000008003ull, 0x8000000000008002ull, 0x8000000000000080ull, 0x000000000000800Aull, 0x800000008000000Aull,
+    0x8000000080008081ull, 0x8000000000008080ull, 0x0000000080000001ull, 0x8000000080008008ull};
+static const int KROT[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
+
+static inline uint64_t rotl64(uint64_t v, int r) { return r ? (v << r) | (v >> (64 - r)) : v; }
+
+static void keccak_f(uint64_t a[25]) {  // a[x + 5*y]
+  for (int round = 0; round < 24; round++) {
+    uint64_t c[5], d[5], b[25];
+    for (int x = 0; x < 5; x++) c[x] = a[x] ^ a[x + 5] ^ a[x + 10] ^ a[x + 15] ^ a[x + 20];
+    for (int x = 0; x < 5; x++) d[x] = c[(x + 4) % 5] ^ rotl64(c[(x + 1) % 5], 1);
+    for (int i = 0; i < 25; i++) a[i] ^= d[i % 5];
+    for (int x = 0; x < 5; x++)
+      for (int y = 0; y < 5; y++) b[y + 5 * ((2 * x + 3 * y) % 5)] = rotl64(a[x + 5 * y], KROT[x + 5 * y]);
+    for (int y = 0; y < 5; y++)
+      for (int x = 0; x < 5; x++) a[x + 5 * y] = b[x + 5 * y] ^ ((~b[(x + 1) % 5 + 5 * y]) & b[(x + 2) % 5 + 5 * y]);
+    a[0] ^= KRC[round];
+  }
+}
+static void keccak256(const uint8_t* data, size_t len, uint8_t out[32]) {
+  const size_t rate = 136;
+  uint64_t a[25] = {0};
+  std::vector<uint8_t> p(data, data + len);
+  p.push_back(0x01);
+  while (p.size() % rate) p.push_back(0);
+  p.back() |= 0x80;
+  for (size_t off = 0; off < p.size(); off += rate) {
+    for (size_t i = 0; i < rate / 8; i++) {
+      uint64_t w;
+      memcpy(&w, &p[off + 8 * i], 8);
+      a[i] ^= w;
+    }
+    keccak_f(a);
+  }
+  memcpy(out, a, 32);
+}
+
+// ---- host field helpers ---------------------------------------------------------------------------
+static Fr fr_one() { return fp_one<FrParams>(); }
+static Fr fr_u64(uint64_t x) { return fp_from_u64<FrParams>(x); }
+static Fr fr_delta() {
+  Fr raw;
+  const uint32_t v[8] = {0xe533e9a2u, 0x870e56bbu, 0x5e963f25u, 0x5b5f898eu, 0xd4c86e71u, 0x64ec26aau, 0x22c6f0cau, 0x09226b6eu};
+  for (int i = 0; i < 8; i++) raw.v[i] = v[i];
+  return fp_to_mont(raw);
+}
+template <class P>
+static void to_be32(const Fp<P>& mont, uint8_t out[32]) {
+  Fp<P> c = fp_from_mont(mont);
+  for (int i = 0; i < 8; i++)
+    for (int b = 0; b < 4; b++) out[31 - (4 * i + b)] = (uint8_t)(c.v[i] >> (8 * b));
+}
+static Fr fr_from_be32_mod(const uint8_t h[32]) {
+  // int(h, big endian) mod r -> Montgomery; the raw value can exceed r, so it is the second operand
+  Fr raw;
+  for (int i = 0; i < 8; i++) {
+    uint32_t w = 0;
+    for (int b = 0; b < 4; b++) w |= (uint32_t)h[31 - (4 * i + b)] << (8 * b);
+    raw.v[i] = w;
+  }
+  Fr r2;
+  for (int i = 0; i < 8; i++) r2.v[i] = FrParams::r2(i);
+  return fp_mul(r2, raw);
+}
+static Fr fr_pow(const Fr& a, uint64_t e) { return fp_pow_var(a, e); }
+
+struct Affine {
+  Fq x, y;
+  bool inf;
+};
+// Curve::batch_normalize for a handful of points
+static void batch_normalize(const G1Jac* in, size_t n, Affine* out) {
+  std::vector<Fq> pre(n);
+  Fq acc = fp_one<FqParams>();
+  for (size_t i = 0; i < n; i++) {
+    pre[i] = acc;
+    if (!fp_is_zero(in[i].z)) acc = fp_mul(acc, in[i].z);
+  }
+  Fq inv = fp_inv(acc);
+  for (size_t i = n; i-- > 0;) {
+    if (fp_is_zero(in[i].z)) {
+      out[i].inf = true;
+      out[i].x = out[i].y = fp_zero<FqParams>();
+      continue;
+    }
+    Fq zi = fp_mul(inv, pre[i]);
+    inv = fp_mul(inv, in[i].z);
+    Fq zi2 = fp_sqr(zi);
+    out[i].x = fp_mul(in[i].x, zi2);
+    out[i].y = fp_mul(in[i].y, fp_mul(zi2, zi));
+    out[i].inf = false;
+  }
+}
+
+// snark_verifier EvmTranscript<G1Affine, NativeLoader, _, Vec<u8>>
+struct Transcript {
+  std::vector<uint8_t> buf, out;
+  void common_scalar(const Fr& s) {
+    uint8_t b[32];
+    to_be32(s, b);
+    buf.insert(buf.end(), b, b + 32);
+  }
+  void write_scalar(const Fr& s) {
+    uint8_t b[32];
+    to_be32(s, b);
+    buf.insert(buf.end(), b, b + 32);
+    out.insert(out.end(), b, b + 32);
+  }
+  bool write_point(const Affine& p) {
+    if (p.inf) return false;  // "Cannot write points at infinity to the transcript"
+    uint8_t b[64];
+    to_be32(p.x, b);
+    to_be32(p.y, b + 32);
+    buf.insert(buf.end(), b, b + 64);
+    out.insert(out.end(), b, b + 64);
+    return true;
+  }
+  Fr squeeze() {
+    std::vector<uint8_t> d(buf);
+    if (buf.size() == 32) d.push_back(1);
+    uint8_t h[32];
+    keccak256(d.data(), d.size(), h);
+    buf.assign(h, h + 32);
+    return fr_from_be32_mod(h);
+  }
+};
+
+struct Bump {
+  uint8_t* base = nullptr;
+  size_t off = 0, cap = 0;
+  template <class T>
+  T* take(size_t count) {
+    size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
+    T* p = (T*)(base ? base + off : nullptr);
+    off += bytes;
+    return p;
+  }
+};
+
+}  // namespace
+
+struct zg_pk {
+  uint32_t k = 0, ext_k = 0, rot_scale = 0;
+  size_t n = 0, N = 0;
+  uint32_t A = 0, F = 0, I = 0, degree = 0, bf = 0, usable = 0, qdeg = 0;
+  std::vector<std::pair<uint32_t, int32_t>> q[3];
+  std::vector<std::pair<uint32_t, uint32_t>> perm;  // (kind, index)
+  uint32_t m = 0, chunk = 0, nsets = 0;
+  uint32_t n_progs = 0, n_gate_progs = 0, n_lookups = 0;
+  std::vector<uint32_t> in_first, in_count, tab_first, tab_count;
+  Fr transcript_repr, omega, omega_inv, delta;
+  std::vector<G1Affine> fixed_comm, sigma_comm;
+  uint8_t* arena = nullptr;
+  // resident
+  Fr *fixed_values, *fixed_polys, *fixed_cosets, *sigma_values, *sigma_polys, *sigma_cosets;
+  Fr *l0, *l_last, *l_active, *coset_x, *t_inv, *constants, *omega_pows;
+  uint32_t *ops, *prog_off, *d_in_first, *d_in_count, *d_tab_first, *d_tab_count;
+  uint32_t* d_qcol[3];
+  int32_t* d_qrot[3];
+  const Fr** d_cols_base[3];
+  const Fr** d_cols_ext[3];
+  const Fr** d_perm_cosets;   // m
+  const Fr** d_sigma_cosets;  // m
+  const Fr** d_z_cosets;      // nsets
+  // per-proof workspace
+  Fr *adv_values, *adv_polys, *adv_cosets, *inst_values, *inst_polys, *inst_cosets;
+  Fr *ci, *ct, *pa, *ps, *pa_poly, *ps_poly, *lz, *lz_poly, *lk_cosets;
+  Fr *pz, *pz_poly, *pz_coset, *frac, *rnd, *random_poly, *h, *h_coeff, *h_poly, *fold, *wpoly, *scratch, *evals_dev, *points_dev,
+      *coeff_dev, *one_dev;
+  const Fr** d_polyptrs;
+  uint32_t* d_pidx;
+  uint32_t* d_status;
+  uint8_t* lookup_ws;
+  uint64_t* rnd_words_dev;
+  uint64_t* rnd_words_host = nullptr;  // pinned
+  size_t n_draws = 0;
+  float stage_ms[8] = {0};
+};
+
+namespace {
+
+static int parse_cs(zg_ctx* ctx, zg_pk* pk, const zg_pk_desc* d, std::vector<uint32_t>& ops, std::vector<uint32_t>& prog_off) {
+  const uint32_t* w = d->cs_words;
+  size_t nw = d->cs_nwords, p = 0;
+  auto need = [&](size_t c) { return p + c <= nw; };
+  if (!need(6) || w[0] != 0x5A473031u) return ctx->fail(ZG_E_INVALID, "pk_load: bad constraint-system blob");
+  pk->A = w[1]; pk->F = w[2]; pk->I = w[3]; pk->degree = w[4]; pk->bf = w[5];
+  p = 6;
+  for (int kind = 0; kind < 3; kind++) {
+    if (!need(1)) return ctx->fail(ZG_E_INVALID, "pk_load: truncated blob");
+    uint32_t c = w[p++];
+    if (!need(2 * (size_t)c)) return ctx->fail(ZG_E_INVALID, "pk_load: truncated blob");
+    for (uint32_t i = 0; i < c; i++, p += 2) pk->q[kind].push_back({w[p], (int32_t)w[p + 1]});
+  }
+  if (!need(1)) return ctx->fail(ZG_E_INVALID, "pk_load: truncated blob");
+  pk->m = w[p++];
+  if (!need(2 * (size_t)pk->m)) return ctx->fail(ZG_E_INVALID, "pk_load: truncated blob");
+  for (uint32_t i = 0; i < pk->m; i++, p += 2) pk->perm.push_back({w[p], w[p + 1]});
+  if (!need(1)) return ctx->fail(ZG_E_INVALID, "pk_load: truncated blob");
+  pk->n_progs = w[p++];
+  if (!need(pk->n_progs + 3)) return ctx->fail(ZG_E_INVALID, "pk_load: truncated blob");
+  prog_off.assign(w + p, w + p + pk->n_progs + 1);
+  p += pk->n_progs + 1;
+  pk->n_gate_progs = w[p++];
+  pk->n_lookups = w[p++];
+  if (!need(4 * (size_t)pk->n_lookups + 1)) return ctx->fail(ZG_E_INVALID, "pk_load: truncated blob");
+  for (uint32_t l = 0; l < pk->n_lookups; l++, p += 4) {
+    pk->in_first.push_back(w[p]); pk->in_count.push_back(w[p + 1]);
+    pk->tab_first.push_back(w[p + 2]); pk->tab_count.push_back(w[p + 3]);
+  }
+  uint32_t nops = w[p++];
+  if (!need(nops)) return ctx->fail(ZG_E_INVALID, "pk_load: truncated blob");
+  ops.assign(w + p, w + p + nops);
+  if (pk->degree < 3) return ctx->fail(ZG_E_INVALID, "pk_load: constraint degree < 3");
+  return ZG_OK;
+}
+
+template <class T>
+static cudaError_t upload(T* dst, const std::vector<T>& v, cudaStream_t st) {
+  if (v.empty()) return cudaSuccess;
+  return cudaMemcpyAsync(dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st);
+}
+
+// commit `count` columns (stride n) on `basis`, normalise on the host
+static int commit_batch(zg_ctx* ctx, int basis, const Fr* cols, size_t stride, size_t n, size_t count, Affine* out) {
+  int rc = zg_msm_dev(ctx, basis, (const zg_fr*)cols, stride, n, count, (zg_g1*)ctx->d_msm_out);
+  if (rc) return rc;
+  std::vector<G1Jac> jac(count);
+  ZG_CUDA(cudaMemcpyAsync(jac.data(), ctx->d_msm_out, sizeof(G1Jac) * count, cudaMemcpyDeviceToHost, ctx->stream));
+  ZG_CUDA(cudaStreamSynchronize(ctx->stream));
+  batch_normalize(jac.data(), count, out);
+  return ZG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void zg_xorshift_seed(zg_xorshift* r, const uint8_t seed[16]) {
+  uint32_t s[4];
+  memcpy(s, seed, 16);
+  if ((s[0] | s[1] | s[2] | s[3]) == 0) s[0] = s[1] = s[2] = s[3] = 0x0BAD5EEDu;
+  r->x = s[0]; r->y = s[1]; r->z = s[2]; r->w = s[3];
+}
+void zg_xorshift_fill(void* state, uint64_t* out, size_t n) {
+  zg_xorshift* r = (zg_xorshift*)state;
+  uint32_t x = r->x, y = r->y, z = r->z, w = r->w;
+  for (size_t i = 0; i < n; i++) {
+    uint32_t t = x ^ (x << 11);
+    x = y; y = z; z = w;
+    w = w ^ (w >> 19) ^ (t ^ (t >> 8));
+    uint64_t lo = w;
+    t = x ^ (x << 11);
+    x = y; y = z; z = w;
+    w = w ^ (w >> 19) ^ (t ^ (t >> 8));
+    out[i] = lo | ((uint64_t)w << 32);
+  }
+  r->x = x; r->y = y; r->z = z; r->w = w;
+}
+
+void zg_pk_free(zg_ctx* ctx, zg_pk* pk) {
+  if (!pk) return;
+  cudaStreamSynchronize(ctx->stream);
+  if (pk->arena) cudaFree(pk->arena);
+  if (pk->rnd_words_host) cudaFreeHost(pk->rnd_words_host);
+  delete pk;
+}
+
+int zg_pk_last_stage_ms(const zg_pk* pk, float out[8]) {
+  if (!pk) return ZG_E_INVALID;
+  memcpy(out, pk->stage_ms, sizeof(float) * 8);
+  return ZG_OK;
+}
+
+int zg_pk_commitments(zg_ctx* ctx, const zg_pk* pk, zg_g1_affine* fixed_out, zg_g1_affine* sigma_out) {
+  if (!pk) return ctx->fail(ZG_E_INVALID, "pk_commitments: null pk");
+  if (fixed_out) memcpy(fixed_out, pk->fixed_comm.data(), sizeof(G1Affine) * pk->F);
+  if (sigma_out) memcpy(sigma_out, pk->sigma_comm.data(), sizeof(G1Affine) * pk->m);
+  return ZG_OK;
+}
+
+int zg_pk_load(zg_ctx* ctx, const zg_pk_desc* d, zg_pk** out) {
+  if (!d || !out) return ctx->fail(ZG_E_INVALID, "pk_load: null argument");
+  *out = nullptr;
+  if (!ctx->srs_loaded || ctx->srs_k != d->k || !ctx->table[0].pts || !ctx->table[1].pts)
+    return ctx->fail(ZG_E_STATE, "pk_load: load an SRS with both bases for the same k first");
+  std::unique_ptr<zg_pk> pk(new zg_pk());
+  std::vector<uint32_t> ops, prog_off;
+  int rc = parse_cs(ctx, pk.get(), d, ops, prog_off);
+  if (rc) return rc;
+  pk->k = d->k;
+  pk->n = (size_t)1 << d->k;
+  pk->qdeg = pk->degree - 1;
+  pk->ext_k = pk->k;
+  while (((size_t)1 << pk->ext_k) < pk->n * pk->qdeg) pk->ext_k++;
+  pk->N = (size_t)1 << pk->ext_k;
+  pk->rot_scale = 1u << (pk->ext_k - pk->k);
+  pk->usable = (uint32_t)pk->n - (pk->bf + 1);
+  pk->chunk = pk->degree - 2;
+  pk->nsets = (pk->m + pk->chunk - 1) / pk->chunk;
+  pk->omega = host_omega(pk->k);
+  pk->omega_inv = fp_inv(pk->omega);
+  pk->delta = fr_delta();
+  memcpy(pk->transcript_repr.v, &d->transcript_repr, 32);
+  if (pk->n < pk->bf + 3) return ctx->fail(ZG_E_INVALID, "pk_load: not enough rows");
+  const size_t n = pk->n, N = pk->N;
+  const uint32_t A = pk->A, F = pk->F, I = pk->I, m = pk->m, Lk = pk->n_lookups, S = pk->nsets;
+  if (A + I + F > 60 || m > 60) return ctx->fail(ZG_E_INVALID, "pk_load: too many columns for one commitment batch");
+  // RNG draws of one proof, in order
+  pk->n_draws = (size_t)A * (pk->bf + 1) + A + (size_t)Lk * (2 * (pk->bf + 1) + 2) + (size_t)S * (pk->bf + 1) +
+                (size_t)Lk * (pk->bf + 1) + (n + 1) + pk->qdeg;
+  const uint32_t n_queries = (uint32_t)(pk->q[0].size() + pk->q[1].size() + m + 3 * S + 5 * Lk + 2);
+
+  // one arena: first pass sizes, second pass carves
+  for (int pass = 0; pass < 2; pass++) {
+    Bump b;
+    b.base = pass ? pk->arena : nullptr;
+    pk->fixed_values = b.take<Fr>(F * n); pk->fixed_polys = b.take<Fr>(F * n); pk->fixed_cosets = b.take<Fr>(F * N);
+    pk->sigma_values = b.take<Fr>(m * n); pk->sigma_polys = b.take<Fr>(m * n); pk->sigma_cosets = b.take<Fr>(m * N);
+    pk->l0 = b.take<Fr>(N); pk->l_last = b.take<Fr>(N); pk->l_active = b.take<Fr>(N); pk->coset_x = b.take<Fr>(N);
+    pk->t_inv = b.take<Fr>(pk->rot_scale); pk->constants = b.take<Fr>(d->n_constants + 1); pk->omega_pows = b.take<Fr>(n);
+    pk->ops = b.take<uint32_t>(ops.size() + 1); pk->prog_off = b.take<uint32_t>(prog_off.size());
+    pk->d_in_first = b.take<uint32_t>(Lk + 1); pk->d_in_count = b.take<uint32_t>(Lk + 1);
+    pk->d_tab_first = b.take<uint32_t>(Lk + 1); pk->d_tab_count = b.take<uint32_t>(Lk + 1);
+    for (int kind = 0; kind < 3; kind++) {
+      pk->d_qcol[kind] = b.take<uint32_t>(pk->q[kind].size() + 1);
+      pk->d_qrot[kind] = b.take<int32_t>(pk->q[kind].size() + 1);
+    }
+    const uint32_t ncols[3] = {A, F, I};
+    for (int kind = 0; kind < 3; kind++) {
+      pk->d_cols_base[kind] = b.take<const Fr*>(ncols[kind] + 1);
+      pk->d_cols_ext[kind] = b.take<const Fr*>(ncols[kind] + 1);
+    }
+    pk->d_perm_cosets = b.take<const Fr*>(m + 1); pk->d_sigma_cosets = b.take<const Fr*>(m + 1);
+    pk->d_z_cosets = b.take<const Fr*>(S + 1);
+    pk->adv_values = b.take<Fr>(A * n); pk->adv_polys = b.take<Fr>(A * n); pk->adv_cosets = b.take<Fr>(A * N);
+    pk->inst_values = b.take<Fr>(I * n); pk->inst_polys = b.take<Fr>(I * n); pk->inst_cosets = b.take<Fr>(I * N);
+    pk->ci = b.take<Fr>(Lk * n); pk->ct = b.take<Fr>(Lk * n);
+    pk->pa = b.take<Fr>(2 * Lk * n); pk->ps = pk->pa ? pk->pa + (size_t)Lk * n : nullptr;   // pa | ps contiguous: one MSM batch
+    pk->pa_poly = b.take<Fr>(2 * Lk * n); pk->ps_poly = pk->pa_poly ? pk->pa_poly + (size_t)Lk * n : nullptr;
+    pk->pz = b.take<Fr>((S + Lk) * n); pk->lz = pk->pz ? pk->pz + (size_t)S * n : nullptr;     // pz | lz contiguous
+    pk->pz_poly = b.take<Fr>((S + Lk) * n); pk->lz_poly = pk->pz_poly ? pk->pz_poly + (size_t)S * n : nullptr;
+    pk->pz_coset = b.take<Fr>(S * N); pk->lk_cosets = b.take<Fr>(3 * N);
+    pk->frac = b.take<Fr>(n); pk->rnd = b.take<Fr>(pk->n_draws); pk->random_poly = pk->rnd;  // set per proof
+    pk->h = b.take<Fr>(N); pk->h_coeff = b.take<Fr>(N); pk->h_poly = b.take<Fr>(n);
+    pk->fold = b.take<Fr>(n); pk->wpoly = b.take<Fr>(8 * n);
+    pk->scratch = b.take<Fr>(8192 + 64 * (size_t)n_queries);
+    pk->evals_dev = b.take<Fr>(n_queries + 8); pk->points_dev = b.take<Fr>(16); pk->coeff_dev = b.take<Fr>(n_queries + 8);
+    pk->one_dev = b.take<Fr>(8);
+    pk->d_polyptrs = b.take<const Fr*>(n_queries + 8); pk->d_pidx = b.take<uint32_t>(n_queries + 8);
+    pk->d_status = b.take<uint32_t>(64);
+    pk->lookup_ws = b.take<uint8_t>(lookup_workspace_bytes(pk->usable));
+    pk->rnd_words_dev = b.take<uint64_t>(8 * pk->n_draws);
+    if (!pass) {
+      cudaError_t e = cudaMalloc(&pk->arena, b.off);
+      if (e != cudaSuccess) return ctx->fail(ZG_E_NOMEM, "pk_load: device arena allocation failed");
+    }
+  }
+  ZG_CUDA(cudaMallocHost(&pk->rnd_words_host, 8 * pk->n_draws * sizeof(uint64_t)));
+  cudaStream_t st = ctx->stream;
+  LaunchCounter lc{&ctx->launches};
+
+  // constraint system tables
+  ZG_CUDA(upload(pk->ops, ops, st));
+  ZG_CUDA(upload(pk->prog_off, prog_off, st));
+  ZG_CUDA(upload(pk->d_in_first, pk->in_first, st)); ZG_CUDA(upload(pk->d_in_count, pk->in_count, st));
+  ZG_CUDA(upload(pk->d_tab_first, pk->tab_first, st)); ZG_CUDA(upload(pk->d_tab_count, pk->tab_count, st));
+  if (d->n_constants)
+    ZG_CUDA(cudaMemcpyAsync(pk->constants, d->constants, sizeof(Fr) * d->n_constants, cudaMemcpyHostToDevice, st));
+  std::vector<uint32_t> qc[3];
+  std::vector<int32_t> qr[3];
+  for (int kind = 0; kind < 3; kind++) {
+    for (auto& pr : pk->q[kind]) { qc[kind].push_back(pr.first); qr[kind].push_back(pr.second); }
+    ZG_CUDA(upload(pk->d_qcol[kind], qc[kind], st));
+    ZG_CUDA(upload(pk->d_qrot[kind], qr[kind], st));
+  }
+  // column pointer tables
+  std::vector<const Fr*> pb[3], pe[3];
+  for (uint32_t c = 0; c < A; c++) { pb[0].push_back(pk->adv_values + c * n); pe[0].push_back(pk->adv_cosets + c * N); }
+  for (uint32_t c = 0; c < F; c++) { pb[1].push_back(pk->fixed_values + c * n); pe[1].push_back(pk->fixed_cosets + c * N); }
+  for (uint32_t c = 0; c < I; c++) { pb[2].push_back(pk->inst_values + c * n); pe[2].push_back(pk->inst_cosets + c * N); }
+  for (int kind = 0; kind < 3; kind++) {
+    ZG_CUDA(upload(pk->d_cols_base[kind], pb[kind], st));
+    ZG_CUDA(upload(pk->d_cols_ext[kind], pe[kind], st));
+  }
+  std::vector<const Fr*> pcos, scos, zcos;
+  for (uint32_t c = 0; c < m; c++) {
+    uint32_t kind = pk->perm[c].first, idx = pk->perm[c].second;
+    if (kind > 2 || idx >= (kind == 0 ? A : kind == 1 ? F : I)) return ctx->fail(ZG_E_INVALID, "pk_load: bad permutation column");
+    pcos.push_back(pe[kind][idx]);
+    scos.push_back(pk->sigma_cosets + c * N);
+  }
+  for (uint32_t s = 0; s < S; s++) zcos.push_back(pk->pz_coset + s * N);
+  ZG_CUDA(upload(pk->d_perm_cosets, pcos, st));
+  ZG_CUDA(upload(pk->d_sigma_cosets, scos, st));
+  ZG_CUDA(upload(pk->d_z_cosets, zcos, st));
+  Fr onev = fr_one();
+  ZG_CUDA(cudaMemcpyAsync(pk->one_dev, &onev, sizeof(Fr), cudaMemcpyHostToDevice, st));
+
+  // fixed columns: values -> coeff -> extended; commitments (keygen_vk)
+  for (uint32_t c = 0; c < F; c++)
+    ZG_CUDA(cudaMemcpyAsync(pk->fixed_values + c * n, d->fixed[c], sizeof(Fr) * n, cudaMemcpyHostToDevice, st));
+  if (F) {
+    rc = zg_lagrange_to_coeff_dev(ctx, (const zg_fr*)pk->fixed_values, (zg_fr*)pk->fixed_polys, pk->k, F, n);
+    if (rc) return rc;
+    rc = zg_coeff_to_extended_dev(ctx, (const zg_fr*)pk->fixed_polys, n, pk->k, pk->ext_k, (zg_fr*)pk->fixed_cosets, N, F);
+    if (rc) return rc;
+    std::vector<Affine> aff(F);
+    rc = commit_batch(ctx, ZG_BASIS_LAGRANGE, pk->fixed_values, n, n, F, aff.data());
+    if (rc) return rc;
+    pk->fixed_comm.resize(F);
+    for (uint32_t c = 0; c < F; c++) { pk->fixed_comm[c].x = aff[c].x; pk->fixed_comm[c].y = aff[c].y; }
+  }
+  // permutation: sigma values from the mapping
+  if (m) {
+    uint32_t* map_dev = (uint32_t*)pk->h;  // scratch: 2*m*n words fit in N Fr when 8*m*n <= 32*N
+    if ((size_t)8 * m * n > sizeof(Fr) * N) return ctx->fail(ZG_E_INVALID, "pk_load: permutation too wide for scratch");
+    ZG_CUDA(cudaMemcpyAsync(map_dev, d->perm_mapping, (size_t)8 * m * n, cudaMemcpyHostToDevice, st));
+    std::vector<Fr> dp(m);
+    Fr cur = fr_one();
+    for (uint32_t c = 0; c < m; c++) { dp[c] = cur; cur = fp_mul(cur, pk->delta); }
+    ZG_CUDA(cudaMemcpyAsync(pk->coeff_dev, dp.data(), sizeof(Fr) * m, cudaMemcpyHostToDevice, st));
+    fr_sigma_values(map_dev, pk->coeff_dev, pk->omega, m, n, pk->sigma_values, st, lc);
+    rc = zg_lagrange_to_coeff_dev(ctx, (const zg_fr*)pk->sigma_values, (zg_fr*)pk->sigma_polys, pk->k, m, n);
+    if (rc) return rc;
+    rc = zg_coeff_to_extended_dev(ctx, (const zg_fr*)pk->sigma_polys, n, pk->k, pk->ext_k, (zg_fr*)pk->sigma_cosets, N, m);
+    if (rc) return rc;
+    std::vector<Affine> aff(m);
+    rc = commit_batch(ctx, ZG_BASIS_LAGRANGE, pk->sigma_values, n, n, m, aff.data());
+    if (rc) return rc;
+    pk->sigma_comm.resize(m);
+    for (uint32_t c = 0; c < m; c++) { pk->sigma_comm[c].x = aff[c].x; pk->sigma_comm[c].y = aff[c].y; }
+  }
+  // l_0, l_last, l_blind -> l_active, on the extended coset (use pz / pz_poly / h as scratch)
+  {
+    Fr* lag = pk->wpoly;  // 3 columns of n
+    Fr* coef = pk->wpoly + 3 * n;
+    ZG_CUDA(cudaMemsetAsync(lag, 0, sizeof(Fr) * 3 * n, st));
+    std::vector<uint32_t> rows;
+    rows.push_back(0);
+    rows.push_back((uint32_t)(n + (n - pk->bf - 1)));
+    for (uint32_t r = 0; r < pk->bf; r++) rows.push_back((uint32_t)(2 * n + (n - pk->bf + r)));
+    std::vector<Fr> ones(rows.size(), fr_one());
+    ZG_CUDA(cudaMemcpyAsync(pk->d_pidx, rows.data(), rows.size() * 4, cudaMemcpyHostToDevice, st));
+    ZG_CUDA(cudaMemcpyAsync(pk->evals_dev, ones.data(), ones.size() * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    fr_scatter_rows(lag, pk->d_pidx, pk->evals_dev, (uint32_t)rows.size(), st, lc);
+    rc = zg_lagrange_to_coeff_dev(ctx, (const zg_fr*)lag, (zg_fr*)coef, pk->k, 3, n);
+    if (rc) return rc;
+    rc = zg_coeff_to_extended_dev(ctx, (const zg_fr*)coef, n, pk->k, pk->ext_k, (zg_fr*)pk->l0, N, 1);
+    if (rc) return rc;
+    rc = zg_coeff_to_extended_dev(ctx, (const zg_fr*)(coef + n), n, pk->k, pk->ext_k, (zg_fr*)pk->l_last, N, 1);
+    if (rc) return rc;
+    rc = zg_coeff_to_extended_dev(ctx, (const zg_fr*)(coef + 2 * n), n, pk->k, pk->ext_k, (zg_fr*)pk->h, N, 1);
+    if (rc) return rc;
+    fr_one_minus_sum(pk->l_last, pk->h, pk->l_active, N, st, lc);
+  }
+  // coset points X_i = zeta * ext_omega^i : extended form of the polynomial X
+  {
+    Fr* coef = pk->wpoly;
+    ZG_CUDA(cudaMemsetAsync(coef, 0, sizeof(Fr) * n, st));
+    ZG_CUDA(cudaMemcpyAsync(coef + 1, &onev, sizeof(Fr), cudaMemcpyHostToDevice, st));
+    rc = zg_coeff_to_extended_dev(ctx, (const zg_fr*)coef, n, pk->k, pk->ext_k, (zg_fr*)pk->coset_x, N, 1);
+    if (rc) return rc;
+  }
+  // t_inv[i] = 1 / ((zeta * ext_omega^i)^n - 1), period 2^(ext_k - k)
+  {
+    std::vector<Fr> t(pk->rot_scale);
+    Fr zn = fr_pow(host_fr_zeta(), n);
+    Fr wn = fr_pow(host_omega(pk->ext_k), n);
+    Fr cur = zn;
+    for (uint32_t i = 0; i < pk->rot_scale; i++) {
+      t[i] = fp_inv(fp_sub(cur, fr_one()));
+      cur = fp_mul(cur, wn);
+    }
+    ZG_CUDA(cudaMemcpyAsync(pk->t_inv, t.data(), sizeof(Fr) * t.size(), cudaMemcpyHostToDevice, st));
+  }
+  // omega^i column for the permutation numerators
+  fr_fill(pk->frac, pk->omega, n, st, lc);
+  fr_running_product(pk->frac, pk->one_dev, pk->omega_pows, n, pk->scratch, st, lc);
+  ZG_CUDA(cudaStreamSynchronize(st));
+  *out = pk.release();
+  return ZG_OK;
+}
+
+int zg_create_proof(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice, const zg_fr* const* instances, const size_t* instance_lens,
+                    zg_rng_fill_fn rng, void* rng_state, uint8_t* proof_out, size_t proof_cap, size_t* proof_len) {
+  if (!pk || !advice || !rng || !proof_out || !proof_len) return ctx->fail(ZG_E_INVALID, "create_proof: null argument");
+  const size_t n = pk->n, N = pk->N;
+  const uint32_t A = pk->A, I = pk->I, Lk = pk->n_lookups, S = pk->nsets, bf = pk->bf, usable = pk->usable, m = pk->m;
+  cudaStream_t st = ctx->stream;
+  LaunchCounter lc{&ctx->launches};
+  int rc;
+  cudaEvent_t ev[9];
+  for (auto& e : ev) ZG_CUDA(cudaEventCreate(&e));
+  ZG_CUDA(cudaEventRecord(ev[0], st));
+  Transcript tr;
+  tr.common_scalar(pk->transcript_repr);
+
+  // ---- RNG: every draw of this proof, in upstream order; the small leading draws first -----------------
+  const size_t small_draws = (size_t)A * (bf + 1) + A + (size_t)Lk * (2 * (bf + 1) + 2) + (size_t)S * (bf + 1) + (size_t)Lk * (bf + 1);
+  rng(rng_state, pk->rnd_words_host, 8 * small_draws);
+  ZG_CUDA(cudaMemcpyAsync(pk->rnd_words_dev, pk->rnd_words_host, 64 * small_draws, cudaMemcpyHostToDevice, st));
+  fr_from_u512(pk->rnd_words_dev, pk->rnd, small_draws, st, lc);
+  size_t draw = 0;  // next unused draw index
+  auto blind_rows = [&](Fr* col, size_t first_row, size_t count) -> cudaError_t {
+    cudaError_t e = cudaMemcpyAsync(col + first_row, pk->rnd + draw, sizeof(Fr) * count, cudaMemcpyDeviceToDevice, st);
+    draw += count;
+    return e;
+  };
+
+  // ---- 1. instance columns ------------------------------------------------------------------------------
+  ZG_CUDA(cudaMemsetAsync(pk->inst_values, 0, sizeof(Fr) * I * n, st));
+  for (uint32_t c = 0; c < I; c++) {
+    size_t len = instance_lens ? instance_lens[c] : 0;
+    if (len > usable) return ctx->fail(ZG_E_INVALID, "create_proof: instance too large");
+    for (size_t i = 0; i < len; i++) {
+      Fr v;
+      memcpy(v.v, &instances[c][i], 32);
+      tr.common_scalar(v);
+    }
+    if (len) ZG_CUDA(cudaMemcpyAsync(pk->inst_values + c * n, instances[c], sizeof(Fr) * len, cudaMemcpyHostToDevice, st));
+  }
+  if (I) {
+    rc = zg_lagrange_to_coeff_dev(ctx, (const zg_fr*)pk->inst_values, (zg_fr*)pk->inst_polys, pk->k, I, n);
+    if (rc) return rc;
+  }
+  // ---- 2. advice: upload, blind, commit ----------------------------------------------------------------------
+  for (uint32_t c = 0; c < A; c++)
+    ZG_CUDA(cudaMemcpyAsync(pk->adv_values + c * n, advice[c], sizeof(Fr) * usable, cudaMemcpyHostToDevice, st));
+  for (uint32_t c = 0; c < A; c++) ZG_CUDA(blind_rows(pk->adv_values + c * n, usable, bf + 1));
+  draw += A;  // one Blind(Fr::random) per column, unused by KZG
+  {
+    std::vector<Affine> aff(A);
+    rc = zg_msm_dev(ctx, ZG_BASIS_LAGRANGE, (const zg_fr*)pk->adv_values, n, n, A, (zg_g1*)ctx->d_msm_out);
+    if (rc) return rc;
+    // the big random polynomial is drawn on the host while the GPU commits
+    const size_t rest = pk->n_draws - small_draws;
+    rng(rng_state, pk->rnd_words_host + 8 * small_draws, 8 * rest);
+    std::vector<G1Jac> jac(A);
+    ZG_CUDA(cudaMemcpyAsync(jac.data(), ctx->d_msm_out, sizeof(G1Jac) * A, cudaMemcpyDeviceToHost, st));
+    ZG_CUDA(cudaMemcpyAsync(pk->rnd_words_dev + 8 * small_draws, pk->rnd_words_host + 8 * small_draws, 64 * rest,
+                            cudaMemcpyHostToDevice, st));
+    fr_from_u512(pk->rnd_words_dev + 8 * small_draws, pk->rnd + small_draws, rest, st, lc);
+    rc = zg_lagrange_to_coeff_dev(ctx, (const zg_fr*)pk->adv_values, (zg_fr*)pk->adv_polys, pk->k, A, n);
+    if (rc) return rc;
+    ZG_CUDA(cudaEventRecord(ev[1], st));
+    ZG_CUDA(cudaStreamSynchronize(st));
+    batch_normalize(jac.data(), A, aff.data());
+    for (uint32_t c = 0; c < A; c++)
+      if (!tr.write_point(aff[c])) return ctx->fail(ZG_E_SYNTH, "create_proof: advice commitment is the identity");
+  }
+  const Fr theta = tr.squeeze();
+
+  // ---- 3. lookups: compress, permute, commit --------------------------------------------------------------------
+  ExprEnv base_env;
+  for (int kind = 0; kind < 3; kind++) {
+    base_env.cols[kind] = pk->d_cols_base[kind];
+    base_env.qcol[kind] = pk->d_qcol[kind];
+    base_env.qrot[kind] = pk->d_qrot[kind];
+  }
+  base_env.constants = pk->constants;
+  base_env.ops = pk->ops;
+  base_env.size = (uint32_t)n;
+  base_env.rot_scale = 1;
+  LookupProgs lp{pk->prog_off, pk->d_in_first, pk->d_in_count, pk->d_tab_first, pk->d_tab_count};
+  if (Lk) {
+    expr_compress_lookups(base_env, lp, Lk, theta, pk->ci, pk->ct, n, st, lc);
+    ZG_CUDA(cudaMemsetAsync(pk->d_status, 0, 4 * 2 * Lk, st));
+    for (uint32_t l = 0; l < Lk; l++)
+      if (lookup_permute(pk->ci + l * n, pk->ct + l * n, usable, pk->pa + l * n, pk->ps + l * n, pk->lookup_ws, pk->d_status + 2 * l,
+                         false, st, lc))
+        return ctx->cuda_fail(cudaGetLastError(), "lookup_permute");
+    std::vector<uint32_t> status(2 * Lk);
+    ZG_CUDA(cudaMemcpyAsync(status.data(), pk->d_status, 4 * 2 * Lk, cudaMemcpyDeviceToHost, st));
+    ZG_CUDA(cudaStreamSynchronize(st));
+    for (uint32_t l = 0; l < Lk; l++) {
+      if (status[2 * l]) {  // top-64-bit sort left ties out of order: redo this lookup with the full 256-bit sort
+        ZG_CUDA(cudaMemsetAsync(pk->d_status + 2 * l, 0, 8, st));
+        if (lookup_permute(pk->ci + l * n, pk->ct + l * n, usable, pk->pa + l * n, pk->ps + l * n, pk->lookup_ws,
+                           pk->d_status + 2 * l, true, st, lc))
+          return ctx->cuda_fail(cudaGetLastError(), "lookup_permute");
+        ZG_CUDA(cudaMemcpyAsync(status.data() + 2 * l, pk->d_status + 2 * l, 8, cudaMemcpyDeviceToHost, st));
+        ZG_CUDA(cudaStreamSynchronize(st));
+      }
+      if (status[2 * l + 1]) return ctx->fail(ZG_E_SYNTH, "create_proof: lookup input not in table (ConstraintSystemFailure)");
+    }
+    // blinding rows: per lookup input rows, table rows, then two blinds
+    for (uint32_t l = 0; l < Lk; l++) {
+      ZG_CUDA(blind_rows(pk->pa + l * n, usable, bf + 1));
+      ZG_CUDA(blind_rows(pk->ps + l * n, usable, bf + 1));
+      draw += 2;
+    }
+    // commitments: write order is (input_l, table_l) per lookup
+    std::vector<Affine> aff(2 * Lk);
+    rc = zg_msm_dev(ctx, ZG_BASIS_LAGRANGE, (const zg_fr*)pk->pa, n, n, 2 * Lk, (zg_g1*)ctx->d_msm_out);
+    if (rc) return rc;
+    std::vector<G1Jac> jac(2 * Lk);
+    ZG_CUDA(cudaMemcpyAsync(jac.data(), ctx->d_msm_out, sizeof(G1Jac) * 2 * Lk, cudaMemcpyDeviceToHost, st));
+    rc = zg_lagrange_to_coeff_dev(ctx, (const zg_fr*)pk->pa, (zg_fr*)pk->pa_poly, pk->k, 2 * Lk, n);
+    if (rc) return rc;
+    ZG_CUDA(cudaEventRecord(ev[2], st));
+    ZG_CUDA(cudaStreamSynchronize(st));
+    batch_normalize(jac.data(), 2 * Lk, aff.data());
+    for (uint32_t l = 0; l < Lk; l++) {
+      if (!tr.write_point(aff[l]) || !tr.write_point(aff[Lk + l]))
+        return ctx->fail(ZG_E_SYNTH, "create_proof: lookup commitment is the identity");
+    }
+  } else {
+    ZG_CUDA(cudaEventRecord(ev[2], st));
+  }
+  const Fr beta = tr.squeeze();
+  const Fr gamma = tr.squeeze();
+
+  // ---- 4. permutation grand products ------------------------------------------------------------------------------
+  // frac[i] = prod_j (v_j + delta^j w^i beta + gamma) / (v_j + beta sigma_j + gamma), via expr-free kernels:
+  // numerator and denominator are accumulated with fr_mul_add_scalar-style passes on the host-selected columns.
+  auto col_values = [&](uint32_t c) -> const Fr* {
+    uint32_t kind = pk->perm[c].first, idx = pk->perm[c].second;
+    return kind == 0 ? pk->adv_values + idx * n : kind == 1 ? pk->fixed_values + idx * n : pk->inst_values + idx * n;
+  };
+  Fr deltaomega = fr_one();
+  for (uint32_t s = 0; s < S; s++) {
+    uint32_t c0 = s * pk->chunk, c1 = std::min(c0 + pk->chunk, m);
+    std::vector<const Fr*> vals, sigs;
+    for (uint32_t c = c0; c < c1; c++) { vals.push_back(col_values(c)); sigs.push_back(pk->sigma_values + c * n); }
+    const Fr** dv = pk->d_polyptrs;
+    const Fr** ds = pk->d_polyptrs + vals.size();
+    ZG_CUDA(cudaMemcpyAsync(dv, vals.data(), vals.size() * sizeof(Fr*), cudaMemcpyHostToDevice, st));
+    ZG_CUDA(cudaMemcpyAsync(ds, sigs.data(), sigs.size() * sizeof(Fr*), cudaMemcpyHostToDevice, st));
+    Fr* num = pk->h_poly;   // scratch columns of n
+    Fr* den = pk->frac;
+    perm_fraction(dv, ds, (uint32_t)vals.size(), pk->omega_pows, beta, gamma, deltaomega, pk->delta, num, den, n, st, lc);
+    for (uint32_t c = c0; c < c1; c++) deltaomega = fp_mul(deltaomega, pk->delta);
+    fr_batch_invert(den, n, st, lc);
+    fr_mul_vec(num, den, den, n, st, lc);
+    Fr* z = pk->pz + s * n;
+    const Fr* start = s == 0 ? pk->one_dev : pk->pz + (s - 1) * n + (n - (bf + 1));
+    fr_running_product(den, start, z, n, pk->scratch, st, lc);
+    ZG_CUDA(blind_rows(z, n - bf, bf));
+    draw += 1;
+  }
+  // ---- 5. lookup grand products ---------------------------------------------------------------------------------------
+  for (uint32_t l = 0; l < Lk; l++) {
+    Fr* num = pk->h_poly;
+    Fr* den = pk->frac;
+    lookup_fraction(pk->ci + l * n, pk->ct + l * n, pk->pa + l * n, pk->ps + l * n, beta, gamma, num, den, n, st, lc);
+    fr_batch_invert(den, n, st, lc);
+    fr_mul_vec(num, den, den, n, st, lc);
+    Fr* z = pk->lz + l * n;
+    fr_running_product(den, pk->one_dev, z, n - bf, pk->scratch, st, lc);
+    ZG_CUDA(blind_rows(z, n - bf, bf));
+    draw += 1;
+  }
+  // ---- 6. vanishing random polynomial; commit round ------------------------------------------------------------------
+  pk->random_poly = pk->rnd + draw;
+  draw += n + 1;
+  {
+    const uint32_t cnt = S + Lk;
+    std::vector<G1Jac> jac(cnt + 1);
+    if (cnt) {
+      rc = zg_msm_dev(ctx, ZG_BASIS_LAGRANGE, (const zg_fr*)pk->pz, n, n, cnt, (zg_g1*)ctx->d_msm_out);
+      if (rc) return rc;
+    }
+    rc = zg_msm_dev(ctx, ZG_BASIS_MONOMIAL, (const zg_fr*)pk->random_poly, n, n, 1, (zg_g1*)(ctx->d_msm_out + cnt));
+    if (rc) return rc;
+    ZG_CUDA(cudaMemcpyAsync(jac.data(), ctx->d_msm_out, sizeof(G1Jac) * (cnt + 1), cudaMemcpyDeviceToHost, st));
+    if (cnt) {
+      rc = zg_lagrange_to_coeff_dev(ctx, (const zg_fr*)pk->pz, (zg_fr*)pk->pz_poly, pk->k, cnt, n);
+      if (rc) return rc;
+    }
+    ZG_CUDA(cudaEventRecord(ev[3], st));
+    ZG_CUDA(cudaStreamSynchronize(st));
+    std::vector<Affine> aff(cnt + 1);
+    batch_normalize(jac.data(), cnt + 1, aff.data());
+    for (uint32_t i = 0; i < cnt + 1; i++)
+      if (!tr.write_point(aff[i])) return ctx->fail(ZG_E_SYNTH, "create_proof: product commitment is the identity");
+  }
+  const Fr y = tr.squeeze();
+
+  // ---- 7. quotient numerator on the extended coset ----------------------------------------------------------------------
+  rc = zg_coeff_to_extended_dev(ctx, (const zg_fr*)pk->adv_polys, n, pk->k, pk->ext_k, (zg_fr*)pk->adv_cosets, N, A);
+  if (rc) return rc;
+  if (I) {
+    rc = zg_coeff_to_extended_dev(ctx, (const zg_fr*)pk->inst_polys, n, pk->k, pk->ext_k, (zg_fr*)pk->inst_cosets, N, I);
+    if (rc) return rc;
+  }
+  if (S) {
+    rc = zg_coeff_to_extended_dev(ctx, (const zg_fr*)pk->pz_poly, n, pk->k, pk->ext_k, (zg_fr*)pk->pz_coset, N, S);
+    if (rc) return rc;
+  }
+  ExprEnv ext_env = base_env;
+  for (int kind = 0; kind < 3; kind++) ext_env.cols[kind] = pk->d_cols_ext[kind];
+  ext_env.size = (uint32_t)N;
+  ext_env.rot_scale = pk->rot_scale;
+  expr_h_gates(ext_env, pk->prog_off, pk->n_gate_progs, y, pk->h, st, lc);
+  if (S) {
+    PermEnv pe;
+    pe.z_cosets = pk->d_z_cosets; pe.col_cosets = pk->d_perm_cosets; pe.sigma_cosets = pk->d_sigma_cosets;
+    pe.l0 = pk->l0; pe.l_last = pk->l_last; pe.l_active = pk->l_active; pe.coset_x = pk->coset_x;
+    pe.nsets = S; pe.m = m; pe.chunk = pk->chunk; pe.size = (uint32_t)N; pe.rot_scale = pk->rot_scale;
+    pe.last_rot = -(int32_t)(bf + 1);
+    expr_h_permutation(pe, beta, gamma, y, pk->delta, pk->h, st, lc);
+  }
+  for (uint32_t l = 0; l < Lk; l++) {
+    Fr* zc = pk->lk_cosets;
+    Fr* ac = pk->lk_cosets + N;
+    Fr* sc = pk->lk_cosets + 2 * N;
+    rc = zg_coeff_to_extended_dev(ctx, (const zg_fr*)(pk->lz_poly + l * n), n, pk->k, pk->ext_k, (zg_fr*)zc, N, 1);
+    if (rc) return rc;
+    rc = zg_coeff_to_extended_dev(ctx, (const zg_fr*)(pk->pa_poly + l * n), n, pk->k, pk->ext_k, (zg_fr*)ac, N, 1);
+    if (rc) return rc;
+    rc = zg_coeff_to_extended_dev(ctx, (const zg_fr*)(pk->ps_poly + l * n), n, pk->k, pk->ext_k, (zg_fr*)sc, N, 1);
+    if (rc) return rc;
+    LookupHEnv le{zc, ac, sc, pk->l0, pk->l_last, pk->l_active};
+    expr_h_lookup(ext_env, lp, l, le, theta, beta, gamma, y, pk->h, st, lc);
+  }
+  ZG_CUDA(cudaEventRecord(ev[4], st));
+  // ---- 8. vanishing::construct: divide, back to coefficients, commit the pieces ---------------------------------------------
+  fr_mul_periodic(pk->h, pk->t_inv, pk->rot_scale, N, st, lc);
+  rc = zg_extended_to_coeff_dev(ctx, (const zg_fr*)pk->h, pk->k, pk->ext_k, n * pk->qdeg, (zg_fr*)pk->h_coeff);
+  if (rc) return rc;
+  draw += pk->qdeg;  // h piece blinds
+  {
+    std::vector<Affine> aff(pk->qdeg);
+    rc = commit_batch(ctx, ZG_BASIS_MONOMIAL, pk->h_coeff, n, n, pk->qdeg, aff.data());
+    if (rc) return rc;
+    for (uint32_t i = 0; i < pk->qdeg; i++)
+      if (!tr.write_point(aff[i])) return ctx->fail(ZG_E_SYNTH, "create_proof: h commitment is the identity");
+  }
+  ZG_CUDA(cudaEventRecord(ev[5], st));
+  const Fr x = tr.squeeze();
+  const Fr xn = fr_pow(x, n);
+
+  // ---- 9. evaluations ------------------------------------------------------------------------------------------------------------
+  // h_poly = sum_i xn^i piece_i
+  {
+    std::vector<const Fr*> pp(pk->qdeg);
+    std::vector<Fr> cf(pk->qdeg);
+    Fr cur = fr_one();
+    for (uint32_t i = 0; i < pk->qdeg; i++) { pp[i] = pk->h_coeff + i * n; cf[i] = cur; cur = fp_mul(cur, xn); }
+    ZG_CUDA(cudaMemcpyAsync(pk->d_polyptrs, pp.data(), pp.size() * sizeof(Fr*), cudaMemcpyHostToDevice, st));
+    ZG_CUDA(cudaMemcpyAsync(pk->coeff_dev, cf.data(), cf.size() * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    fr_linear_combination(pk->d_polyptrs, pk->coeff_dev, pk->qdeg, n, fp_zero<FrParams>(), pk->h_poly, st, lc);
+  }
+  // queries in create_proof's ProverQuery order
+  struct Query { const Fr* poly; int32_t rot; };
+  std::vector<Query> Q;
+  for (auto& qa : pk->q[0]) Q.push_back({pk->adv_polys + qa.first * n, qa.second});
+  const size_t q_perm = Q.size();
+  for (uint32_t s = 0; s < S; s++) { Q.push_back({pk->pz_poly + s * n, 0}); Q.push_back({pk->pz_poly + s * n, 1}); }
+  for (int s = (int)S - 2; s >= 0; s--) Q.push_back({pk->pz_poly + s * n, -(int32_t)(bf + 1)});
+  const size_t q_lk = Q.size();
+  for (uint32_t l = 0; l < Lk; l++) {
+    Q.push_back({pk->lz_poly + l * n, 0});
+    Q.push_back({pk->pa_poly + l * n, 0});
+    Q.push_back({pk->ps_poly + l * n, 0});
+    Q.push_back({pk->pa_poly + l * n, -1});
+    Q.push_back({pk->lz_poly + l * n, 1});
+  }
+  const size_t q_fixed = Q.size();
+  for (auto& qf : pk->q[1]) Q.push_back({pk->fixed_polys + qf.first * n, qf.second});
+  const size_t q_sigma = Q.size();
+  for (uint32_t c = 0; c < m; c++) Q.push_back({pk->sigma_polys + c * n, 0});
+  const size_t q_h = Q.size();
+  Q.push_back({pk->h_poly, 0});
+  Q.push_back({pk->random_poly, 0});
+  // distinct rotations in first-appearance order (construct_intermediate_sets)
+  std::vector<int32_t> rots;
+  std::vector<uint32_t> pidx(Q.size());
+  for (size_t i = 0; i < Q.size(); i++) {
+    auto it = std::find(rots.begin(), rots.end(), Q[i].rot);
+    if (it == rots.end()) { rots.push_back(Q[i].rot); pidx[i] = (uint32_t)rots.size() - 1; }
+    else pidx[i] = (uint32_t)(it - rots.begin());
+  }
+  if (rots.size() > 16) return ctx->fail(ZG_E_INVALID, "create_proof: more than 16 opening points");
+  std::vector<Fr> points(rots.size());
+  for (size_t i = 0; i < rots.size(); i++)
+    points[i] = fp_mul(x, fr_pow(rots[i] >= 0 ? pk->omega : pk->omega_inv, (uint64_t)(rots[i] >= 0 ? rots[i] : -rots[i])));
+  std::vector<const Fr*> qptr(Q.size());
+  for (size_t i = 0; i < Q.size(); i++) qptr[i] = Q[i].poly;
+  ZG_CUDA(cudaMemcpyAsync(pk->d_polyptrs, qptr.data(), qptr.size() * sizeof(Fr*), cudaMemcpyHostToDevice, st));
+  ZG_CUDA(cudaMemcpyAsync(pk->d_pidx, pidx.data(), pidx.size() * 4, cudaMemcpyHostToDevice, st));
+  ZG_CUDA(cudaMemcpyAsync(pk->points_dev, points.data(), points.size() * sizeof(Fr), cudaMemcpyHostToDevice, st));
+  fr_eval_many(pk->d_polyptrs, pk->d_pidx, pk->points_dev, (uint32_t)Q.size(), n, pk->evals_dev, pk->scratch + 8192, st, lc);
+  std::vector<Fr> evals(Q.size());
+  ZG_CUDA(cudaMemcpyAsync(evals.data(), pk->evals_dev, sizeof(Fr) * Q.size(), cudaMemcpyDeviceToHost, st));
+  ZG_CUDA(cudaEventRecord(ev[6], st));
+  ZG_CUDA(cudaStreamSynchronize(st));
+  // transcript order: advice, fixed, random, sigma, permutation sets, lookups
+  for (size_t i = 0; i < q_perm; i++) tr.write_scalar(evals[i]);
+  for (size_t i = q_fixed; i < q_sigma; i++) tr.write_scalar(evals[i]);
+  tr.write_scalar(evals[q_h + 1]);
+  for (size_t i = q_sigma; i < q_h; i++) tr.write_scalar(evals[i]);
+  for (uint32_t s = 0; s < S; s++) {
+    tr.write_scalar(evals[q_perm + 2 * s]);
+    tr.write_scalar(evals[q_perm + 2 * s + 1]);
+    if (s + 1 < S) tr.write_scalar(evals[q_perm + 2 * S + (S - 2 - s)]);
+  }
+  for (uint32_t l = 0; l < Lk; l++) {
+    const size_t b = q_lk + 5 * l;
+    tr.write_scalar(evals[b + 0]);   // product
+    tr.write_scalar(evals[b + 4]);   // product at omega x
+    tr.write_scalar(evals[b + 1]);   // permuted input
+    tr.write_scalar(evals[b + 3]);   // permuted input at omega^-1 x
+    tr.write_scalar(evals[b + 2]);   // permuted table
+  }
+  // ---- 10. GWC multi-open -------------------------------------------------------------------------------------------------------------
+  const Fr v = tr.squeeze();
+  const uint32_t nsetsQ = (uint32_t)rots.size();
+  if (nsetsQ > 8) return ctx->fail(ZG_E_INVALID, "create_proof: more than 8 opening sets");
+  ZG_CUDA(cudaMemsetAsync(pk->wpoly, 0, sizeof(Fr) * nsetsQ * n, st));
+  std::vector<const Fr*> gp;
+  std::vector<Fr> gc;
+  std::vector<Fr> eaccs(nsetsQ);
+  std::vector<size_t> goff(nsetsQ + 1, 0);
+  for (uint32_t g = 0; g < nsetsQ; g++) {
+    Fr pw = fr_one(), eacc = fp_zero<FrParams>();
+    for (size_t i = 0; i < Q.size(); i++) {
+      if (pidx[i] != g) continue;
+      gp.push_back(Q[i].poly);
+      gc.push_back(pw);
+      eacc = fp_add(eacc, fp_mul(evals[i], pw));
+      pw = fp_mul(pw, v);
+    }
+    eaccs[g] = eacc;
+    goff[g + 1] = gp.size();
+  }
+  ZG_CUDA(cudaMemcpyAsync(pk->d_polyptrs, gp.data(), gp.size() * sizeof(Fr*), cudaMemcpyHostToDevice, st));
+  ZG_CUDA(cudaMemcpyAsync(pk->coeff_dev, gc.data(), gc.size() * sizeof(Fr), cudaMemcpyHostToDevice, st));
+  for (uint32_t g = 0; g < nsetsQ; g++) {
+    fr_linear_combination(pk->d_polyptrs + goff[g], pk->coeff_dev + goff[g], (uint32_t)(goff[g + 1] - goff[g]), n, eaccs[g], pk->fold,
+                          st, lc);
+    fr_kate_division(pk->fold, n, points[g], pk->wpoly + g * n, pk->scratch, st, lc);
+  }
+  {
+    std::vector<Affine> aff(nsetsQ);
+    rc = commit_batch(ctx, ZG_BASIS_MONOMIAL, pk->wpoly, n, n, nsetsQ, aff.data());
+    if (rc) return rc;
+    for (uint32_t g = 0; g < nsetsQ; g++)
+      if (!tr.write_point(aff[g])) return ctx->fail(ZG_E_SYNTH, "create_proof: opening witness is the identity");
+  }
+  ZG_CUDA(cudaEventRecord(ev[7], st));
+  ZG_CUDA(cudaEventSynchronize(ev[7]));
+  for (int i = 0; i < 7; i++) cudaEventElapsedTime(&pk->stage_ms[i], ev[i], ev[i + 1]);
+  cudaEventElapsedTime(&pk->stage_ms[7], ev[0], ev[7]);
+  for (auto& e : ev) cudaEventDestroy(e);
+  if (draw != pk->n_draws) return ctx->fail(ZG_E_STATE, "create_proof: RNG draw accounting mismatch");
+  if (tr.out.size() > proof_cap) return ctx->fail(ZG_E_INVALID, "create_proof: proof buffer too small");
+  memcpy(proof_out, tr.out.data(), tr.out.size());
+  *proof_len = tr.out.size();
+  return ZG_OK;
+}
+
+}  // extern "C"

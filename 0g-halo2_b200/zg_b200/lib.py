@@ -29,6 +29,8 @@ EXPORTS = [
     "zg_ntt", "zg_ntt_dev", "zg_lagrange_to_coeff", "zg_lagrange_to_coeff_dev",
     "zg_coeff_to_extended", "zg_coeff_to_extended_dev", "zg_extended_to_coeff", "zg_extended_to_coeff_dev",
     "zg_bench_int_pipe", "zg_debug_field_op",
+    "zg_xorshift_seed", "zg_xorshift_fill", "zg_pk_load", "zg_pk_free", "zg_pk_commitments", "zg_create_proof",
+    "zg_pk_last_stage_ms",
 ]
 
 
@@ -79,6 +81,16 @@ def load_library() -> ctypes.CDLL:
     L.zg_extended_to_coeff_dev.argtypes = [vp, vp, u32, u32, sz, vp]
     L.zg_bench_int_pipe.argtypes = [vp, ci, u32, ctypes.POINTER(ctypes.c_double)]
     L.zg_debug_field_op.argtypes = [vp, ci, ci, vp, vp, vp, sz]
+    L.zg_xorshift_seed.argtypes = [vp, vp]
+    L.zg_xorshift_seed.restype = None
+    L.zg_xorshift_fill.argtypes = [vp, vp, sz]
+    L.zg_xorshift_fill.restype = None
+    L.zg_pk_load.argtypes = [vp, vp, ctypes.POINTER(vp)]
+    L.zg_pk_free.argtypes = [vp, vp]
+    L.zg_pk_free.restype = None
+    L.zg_pk_commitments.argtypes = [vp, vp, vp, vp]
+    L.zg_create_proof.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, sz, ctypes.POINTER(sz)]
+    L.zg_pk_last_stage_ms.argtypes = [vp, vp]
     _lib = L
     return L
 
@@ -206,3 +218,22 @@ class Context:
         out = np.zeros_like(a)
         self._ck(self._L.zg_debug_field_op(self._h, field, op, _ptr(a), _ptr(b), _ptr(out), a.shape[0]))
         return out
+
+
+class PkDesc(ctypes.Structure):
+    """zg_pk_desc (include/zg_b200.h)."""
+    _fields_ = [("k", ctypes.c_uint32), ("cs_words", ctypes.c_void_p), ("cs_nwords", ctypes.c_size_t),
+                ("constants", ctypes.c_void_p), ("n_constants", ctypes.c_size_t), ("fixed", ctypes.c_void_p),
+                ("perm_mapping", ctypes.c_void_p), ("transcript_repr", ctypes.c_uint64 * 4)]
+
+
+class XorShift(ctypes.Structure):
+    """zg_xorshift: rand_xorshift::XorShiftRng state; `fill_fn` is the zg_rng_fill_fn to pass with it."""
+    _fields_ = [("x", ctypes.c_uint32), ("y", ctypes.c_uint32), ("z", ctypes.c_uint32), ("w", ctypes.c_uint32)]
+
+    @classmethod
+    def from_seed(cls, seed: bytes):
+        assert len(seed) == 16
+        r = cls()
+        load_library().zg_xorshift_seed(ctypes.byref(r), seed)
+        return r

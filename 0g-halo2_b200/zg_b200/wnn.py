@@ -84,12 +84,12 @@ class Wnn:
         assert_satisfied(circuit.cs, asm, [outputs])
 
     # ---- src/wnn.rs:222-281: proving through the B200 backend ------------------------------------
-    def generate_proving_key(self, params, k: int = None):
+    def generate_proving_key(self, ctx, params, k: int = None):
         """keygen_vk + keygen_pk on a dummy (all-zero) image: keys do not depend on the input."""
         from .prover import keygen
         k = params.k if k is None else k
         circuit, asm = self.synthesize(np.zeros(self.img_shape(), dtype=np.uint8), k)
-        return keygen(params, circuit.cs, asm)
+        return keygen(ctx, params, circuit.cs, asm)
 
     def proof(self, pk, params, image, rng):
         """create_proof::<KZG<Bn256>, ProverGWC, _, _, EvmTranscript, _>; returns (proof bytes, outputs)."""

@@ -104,6 +104,46 @@ int zg_extended_to_coeff(zg_ctx* ctx, const zg_fr* ext, uint32_t k, uint32_t ext
 int zg_extended_to_coeff_dev(zg_ctx* ctx, const zg_fr* ext_dev, uint32_t k, uint32_t ext_k,
                              size_t keep, zg_fr* out_dev);
 
+/* ---- keygen + create_proof ----------------------------------------------------------------
+ * plonk::{keygen_vk, keygen_pk} (src/wnn.rs:226-228) and plonk::create_proof::<KZGCommitmentScheme<Bn256>,
+ * ProverGWC, _, _, EvmTranscript, _> (src/wnn.rs:242-259) for ONE circuit.  Witness synthesis stays on
+ * the host: the caller passes the synthesized columns.  The transcript (keccak256 EvmTranscript) and the
+ * RNG draw order are those of halo2_proofs v2023_04_20. */
+typedef struct zg_pk zg_pk;
+
+/* RngCore::next_u64 in bulk: fill out[0..n) with the next n u64 draws of the caller's RNG */
+typedef void (*zg_rng_fill_fn)(void* state, uint64_t* out, size_t n);
+/* rand_xorshift::XorShiftRng restated (seedable RNG for tests / benches; the reference uses OsRng) */
+typedef struct { uint32_t x, y, z, w; } zg_xorshift;
+void zg_xorshift_seed(zg_xorshift* rng, const uint8_t seed[16]);
+void zg_xorshift_fill(void* state /* zg_xorshift* */, uint64_t* out, size_t n);
+
+typedef struct {
+  uint32_t k;
+  /* constraint system after selector compression, serialised by the host front-end
+   * (0g-halo2_b200/zg_b200/plonk/serialize.py documents the word stream) */
+  const uint32_t* cs_words; size_t cs_nwords;
+  const zg_fr* constants; size_t n_constants;    /* constant pool of the expression programs */
+  const zg_fr* const* fixed;                     /* num_fixed columns of 2^k Lagrange values */
+  const uint32_t* perm_mapping;                  /* [m][2^k][2]: (column, row) -> (column', row') of sigma */
+  zg_fr transcript_repr;                         /* VerifyingKey::transcript_repr, hashed first */
+} zg_pk_desc;
+
+/* keygen: commits fixed and sigma columns, builds coefficient + extended-coset forms, l_0/l_last/
+ * l_active; everything stays resident on the context's device.  Needs the SRS (zg_srs_load, same k). */
+int zg_pk_load(zg_ctx* ctx, const zg_pk_desc* desc, zg_pk** out);
+void zg_pk_free(zg_ctx* ctx, zg_pk* pk);
+/* VerifyingKey: fixed_commitments (num_fixed) and permutation commitments (m), affine */
+int zg_pk_commitments(zg_ctx* ctx, const zg_pk* pk, zg_g1_affine* fixed_out, zg_g1_affine* sigma_out);
+/* advice: num_advice host columns of 2^k values (rows >= 2^k - blinding_factors - 1 are overwritten with
+ * blinding scalars); instances: num_instance host columns with their lengths.  Writes the proof bytes. */
+int zg_create_proof(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice, const zg_fr* const* instances,
+                    const size_t* instance_lens, zg_rng_fill_fn rng, void* rng_state, uint8_t* proof_out,
+                    size_t proof_cap, size_t* proof_len);
+/* device time (ms) of the stages of the last zg_create_proof on this pk, for profiling:
+ * out[0..8) = advice, lookups, products, quotient, h-commit, evals, gwc, total */
+int zg_pk_last_stage_ms(const zg_pk* pk, float out[8]);
+
 /* ---- micro-benchmarks used for the integer-pipe roofline (bench.py) ---------------------- */
 /* runs `iters` dependent-free IMAD-class instructions per thread on every SM and returns the
  * achieved rate in 1e9 thread-instructions per second; kind 0 = IMAD (32-bit), 1 = IMAD.WIDE,

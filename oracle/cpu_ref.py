@@ -180,3 +180,31 @@ def g1_sequence(gen_affine: np.ndarray, n: int) -> np.ndarray:
     out = np.zeros((n, 8), dtype=np.uint64)
     lib().zgo_g1_sequence(_p(np.ascontiguousarray(gen_affine, dtype=np.uint64)), ctypes.c_size_t(n), _p(out))
     return out
+
+
+def fr_running_product(f, start, n_out):
+    f = _fr(f)
+    z = np.zeros((n_out, 4), dtype=np.uint64)
+    lib().zgo_fr_running_product(_p(f), _p(_fr(start)), _p(z), ctypes.c_size_t(n_out))
+    return z
+
+
+def fr_kate_division(a, z):
+    a = _fr(a)
+    q = np.zeros((a.shape[0] - 1, 4), dtype=np.uint64)
+    lib().zgo_fr_kate_division(_p(a), ctypes.c_size_t(a.shape[0]), _p(_fr(z)), _p(q))
+    return q
+
+
+def fr_mul_add_scalar(a, s, b):
+    a, b = _fr(a), _fr(b)
+    o = np.empty_like(a)
+    lib().zgo_fr_mul_add_scalar(_p(a), _p(_fr(s)), _p(b), _p(o), ctypes.c_size_t(a.shape[0]))
+    return o
+
+
+def fr_from_u512(words):
+    w = np.ascontiguousarray(words, dtype=np.uint64).reshape(-1, 8)
+    o = np.zeros((w.shape[0], 4), dtype=np.uint64)
+    lib().zgo_fr_from_u512(_p(w), _p(o), ctypes.c_size_t(w.shape[0]))
+    return o

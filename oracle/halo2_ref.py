@@ -1,0 +1,779 @@
+"""CPU restatement of halo2_proofs' KZG/GWC prover and verifier.  TEST INFRASTRUCTURE ONLY.
+
+Restates, from the published algorithm of halo2_proofs tag v2023_04_20 (git
+privacy-scaling-explorations/halo2, pinned at /root/reference/Cargo.toml:21-25 and NOT vendored
+under /root/reference), halo2curves 0.3.3 and snark-verifier v2023_04_20 (EvmTranscript):
+  plonk::{keygen_vk, keygen_pk, create_proof, verify_proof}, plonk::{lookup, permutation,
+  vanishing}::prover, plonk::evaluation::Evaluator::evaluate_h, poly::EvaluationDomain,
+  poly::kzg::multiopen::gwc::{ProverGWC, VerifierGWC}
+as instantiated at /root/reference/src/wnn.rs:226-228, 242-259, 272-279 (KZG<Bn256>, GWC,
+EvmTranscript, one circuit, one instance column).
+
+PARITY UNPINNED against the real crates: the reference has no golden proof / commitment /
+evaluation vectors and no Rust toolchain exists here.  What pins this file:
+(i) the verifier below accepts the proofs (a KZG opening check with the test SRS's known trapdoor,
+equivalent to the pairing check), (ii) h(X) * (X^n - 1) == numerator(X) implied by (i),
+(iii) the reference's own snapshot vectors pin the public instance.  `vk.transcript_repr` (Rust
+Debug-format dependent) is an INPUT here, derived from a documented stand-in hash.
+
+Heavy vector arithmetic runs in the C oracle (oracle/zg_oracle.c via cpu_ref); with
+`real_msm=True` commitments use the restated best_multiexp (the CPU baseline), otherwise the
+known SRS trapdoor s gives the same group element as [p(s)]G with one scalar multiplication."""
+from __future__ import annotations
+
+import hashlib
+
+import numpy as np
+
+import bn254
+import cpu_ref
+from bn254 import R_MOD, Q_MOD
+
+ADVICE, FIXED, INSTANCE = "advice", "fixed", "instance"
+
+
+def L(x: int) -> np.ndarray:
+    return bn254.fr_to_limbs([x])[0]
+
+
+def I(limbs) -> int:
+    return bn254.fr_from_limbs(np.asarray(limbs).reshape(1, 4))[0]
+
+
+# ---- keccak256 (EvmTranscript) ---------------------------------------------------------------
+_RC = [0x0000000000000001, 0x0000000000008082, 0x800000000000808A, 0x8000000080008000, 0x000000000000808B,
+       0x0000000080000001, 0x8000000080008081, 0x8000000000008009, 0x000000000000008A, 0x0000000000000088,
+       0x0000000080008009, 0x000000008000000A, 0x000000008000808B, 0x800000000000008B, 0x8000000000008089,
+       0x8000000000008003, 0x8000000000008002, 0x8000000000000080, 0x000000000000800A, 0x800000008000000A,
+       0x8000000080008081, 0x8000000000008080, 0x0000000080000001, 0x8000000080008008]
+_ROT = [[0, 36, 3, 41, 18], [1, 44, 10, 45, 2], [62, 6, 43, 15, 61], [28, 55, 25, 21, 56], [27, 20, 39, 8, 14]]
+_M64 = (1 << 64) - 1
+
+
+def _keccak_f(a):
+    for rc in _RC:
+        c = [a[x][0] ^ a[x][1] ^ a[x][2] ^ a[x][3] ^ a[x][4] for x in range(5)]
+        d = [c[(x - 1) % 5] ^ (((c[(x + 1) % 5] << 1) | (c[(x + 1) % 5] >> 63)) & _M64) for x in range(5)]
+        a = [[a[x][y] ^ d[x] for y in range(5)] for x in range(5)]
+        b = [[0] * 5 for _ in range(5)]
+        for x in range(5):
+            for y in range(5):
+                r = _ROT[x][y]
+                v = a[x][y]
+                b[y][(2 * x + 3 * y) % 5] = ((v << r) | (v >> (64 - r))) & _M64 if r else v
+        a = [[b[x][y] ^ ((~b[(x + 1) % 5][y]) & b[(x + 2) % 5][y]) for y in range(5)] for x in range(5)]
+        a[0][0] ^= rc
+    return a
+
+
+def keccak256(data: bytes) -> bytes:
+    rate = 136
+    p = bytearray(data)
+    p.append(0x01)
+    while len(p) % rate:
+        p.append(0)
+    p[-1] |= 0x80
+    a = [[0] * 5 for _ in range(5)]
+    for off in range(0, len(p), rate):
+        for i in range(rate // 8):
+            a[i % 5][i // 5] ^= int.from_bytes(p[off + 8 * i: off + 8 * i + 8], "little")
+        a = _keccak_f(a)
+    out = b"".join(a[i % 5][i // 5].to_bytes(8, "little") for i in range(4))
+    return out
+
+
+assert keccak256(b"").hex() == "c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470"
+
+
+class EvmTranscript:
+    """snark_verifier::system::halo2::transcript::evm::EvmTranscript<G1Affine, NativeLoader, ..>."""
+
+    def __init__(self, proof: bytes = None):
+        self.buf = bytearray()
+        self.out = bytearray()
+        self.inp, self.pos = proof, 0
+
+    def common_scalar(self, x: int):
+        self.buf += int(x % R_MOD).to_bytes(32, "big")
+
+    def common_point(self, p):
+        if p is None:
+            raise ValueError("Cannot write points at infinity to the transcript")
+        self.buf += p[0].to_bytes(32, "big") + p[1].to_bytes(32, "big")
+
+    def write_scalar(self, x: int):
+        self.common_scalar(x)
+        self.out += int(x % R_MOD).to_bytes(32, "big")
+
+    def write_point(self, p):
+        self.common_point(p)
+        self.out += p[0].to_bytes(32, "big") + p[1].to_bytes(32, "big")
+
+    def read_scalar(self) -> int:
+        v = int.from_bytes(self.inp[self.pos:self.pos + 32], "big")
+        self.pos += 32
+        if v >= R_MOD:
+            raise ValueError("non-canonical scalar")
+        self.common_scalar(v)
+        return v
+
+    def read_point(self):
+        x = int.from_bytes(self.inp[self.pos:self.pos + 32], "big")
+        y = int.from_bytes(self.inp[self.pos + 32:self.pos + 64], "big")
+        self.pos += 64
+        p = (x, y)
+        if x >= Q_MOD or y >= Q_MOD or not bn254.g1_is_on_curve(p):
+            raise ValueError("invalid point in proof")
+        self.common_point(p)
+        return p
+
+    def squeeze(self) -> int:
+        data = bytes(self.buf) + (b"\x01" if len(self.buf) == 32 else b"")
+        h = keccak256(data)
+        self.buf = bytearray(h)
+        return int.from_bytes(h, "big") % R_MOD
+
+
+class XorShiftRng:
+    """rand_xorshift::XorShiftRng (16-byte seed); next_u64 = lo | hi << 32 of two next_u32."""
+
+    def __init__(self, seed: bytes):
+        assert len(seed) == 16
+        self.x, self.y, self.z, self.w = (int.from_bytes(seed[4 * i:4 * i + 4], "little") for i in range(4))
+        if self.x | self.y | self.z | self.w == 0:
+            self.x, self.y, self.z, self.w = 0x0BAD5EED, 0x0BAD5EED, 0x0BAD5EED, 0x0BAD5EED
+
+    def next_u32(self) -> int:
+        t = (self.x ^ (self.x << 11)) & 0xFFFFFFFF
+        self.x, self.y, self.z = self.y, self.z, self.w
+        self.w = (self.w ^ (self.w >> 19) ^ (t ^ (t >> 8))) & 0xFFFFFFFF
+        return self.w
+
+    def words(self, n_u64: int) -> np.ndarray:
+        out = np.empty(n_u64, dtype=np.uint64)
+        for i in range(n_u64):
+            lo = self.next_u32()
+            hi = self.next_u32()
+            out[i] = lo | (hi << 32)
+        return out
+
+    def fr(self, count: int = 1) -> np.ndarray:
+        """`count` draws of Fr::random = from_u512 of eight next_u64 -> (count,4) Montgomery limbs."""
+        return cpu_ref.fr_from_u512(self.words(8 * count))
+
+    def fr_int(self) -> int:
+        return I(self.fr(1)[0])
+
+
+# ---- SRS with a known trapdoor (test-only; ParamsKZG::new uses OsRng, src/main.rs:232) ----------
+class Srs:
+    def __init__(self, k: int, s: int):
+        self.k, self.n, self.s = k, 1 << k, s % R_MOD
+        gen = bn254.g1_affine_to_limbs([bn254.G1_GEN])[0]
+        self.g = cpu_ref.srs_monomial(L(self.s), gen, self.n)
+        # g_lagrange[i] = [L_i(s)]G,  L_i(s) = w^i (s^n - 1) / (n (s - w^i))
+        w = bn254.omega(k)
+        wi = [pow(w, i, R_MOD) for i in range(self.n)]
+        num = (pow(self.s, self.n, R_MOD) - 1) * pow(self.n, -1, R_MOD) % R_MOD
+        den = cpu_ref.fr_batch_invert(bn254.fr_to_limbs([(self.s - x) % R_MOD for x in wi]))
+        li = cpu_ref.fr_mul_vec(den, bn254.fr_to_limbs([x * num % R_MOD for x in wi]))
+        self.g_lagrange = cpu_ref.g1_mul_many(li, gen)
+
+
+class Domain:
+    """poly::EvaluationDomain::new(j = cs.degree(), k)."""
+
+    def __init__(self, k: int, degree: int):
+        self.k, self.n = k, 1 << k
+        self.quotient_poly_degree = degree - 1
+        ek = k
+        while (1 << ek) < self.n * self.quotient_poly_degree:
+            ek += 1
+        self.ext_k, self.ext_n = ek, 1 << ek
+        self.omega, self.ext_omega = bn254.omega(k), bn254.omega(ek)
+        self.omega_inv, self.ext_omega_inv = pow(self.omega, -1, R_MOD), pow(self.ext_omega, -1, R_MOD)
+        self.zeta = bn254.FR_ZETA
+        self.zeta_inv = self.zeta * self.zeta % R_MOD
+        # t_evaluations: (zeta * ext_omega^i)^n - 1 has period 2^(ext_k - k)
+        per = 1 << (ek - k)
+        zn = pow(self.zeta, self.n, R_MOD)
+        wn = pow(self.ext_omega, self.n, R_MOD)
+        self.t_inv = [pow((zn * pow(wn, i, R_MOD) - 1) % R_MOD, -1, R_MOD) for i in range(per)]
+
+    def lagrange_to_coeff(self, a):
+        c = cpu_ref.best_fft(a, L(self.omega_inv), self.k)
+        return cpu_ref.fr_scale_vec(c, L(pow(self.n, -1, R_MOD)))
+
+    def coeff_to_extended(self, c):
+        ext = np.zeros((self.ext_n, 4), dtype=np.uint64)
+        ext[:self.n] = cpu_ref.fr_scale_mod3(c, bn254.fr_to_limbs([1, self.zeta, self.zeta_inv]))
+        return cpu_ref.best_fft(ext, L(self.ext_omega), self.ext_k)
+
+    def extended_to_coeff(self, e):
+        c = cpu_ref.best_fft(e, L(self.ext_omega_inv), self.ext_k)
+        c = cpu_ref.fr_scale_vec(c, L(pow(self.ext_n, -1, R_MOD)))
+        c = cpu_ref.fr_scale_mod3(c, bn254.fr_to_limbs([1, self.zeta_inv, self.zeta]))
+        return c[: self.n * self.quotient_poly_degree]
+
+    def divide_by_vanishing(self, e):
+        per = len(self.t_inv)
+        t = np.tile(bn254.fr_to_limbs(self.t_inv), (self.ext_n // per, 1))
+        return cpu_ref.fr_mul_vec(e, t)
+
+    def rotate_omega(self, x: int, rot: int) -> int:
+        return x * pow(self.omega if rot >= 0 else self.omega_inv, abs(rot), R_MOD) % R_MOD
+
+    def l_i_range(self, x: int, xn: int, rots) -> list:
+        """l_i(x) for rotation i (Lagrange basis polynomial of row i mod n)."""
+        out = []
+        for r in rots:
+            wi = self.rotate_omega(1, r)
+            out.append(wi * (xn - 1) % R_MOD * pow(self.n * (x - wi) % R_MOD, -1, R_MOD) % R_MOD)
+        return out
+
+
+# ---- expression evaluation over whole columns ----------------------------------------------------
+def eval_expr_vec(expr, cs, cols, size, rot_scale, memo):
+    key = id(expr)
+    if key in memo:
+        return memo[key]
+    k = expr.kind
+    if k == "const":
+        r = np.tile(L(expr.v), (size, 1))
+    elif k in (ADVICE, FIXED, INSTANCE):
+        col, rot = cs.queries[k][expr.v[0]]
+        r = np.roll(cols[k][col], -rot * rot_scale, axis=0)
+    elif k == "neg":
+        a = eval_expr_vec(expr.a, cs, cols, size, rot_scale, memo)
+        r = cpu_ref.fr_sub_vec(np.zeros_like(a), a)
+    elif k == "scaled":
+        r = cpu_ref.fr_scale_vec(eval_expr_vec(expr.a, cs, cols, size, rot_scale, memo), L(expr.v))
+    elif k == "sum":
+        r = cpu_ref.fr_add_vec(eval_expr_vec(expr.a, cs, cols, size, rot_scale, memo),
+                               eval_expr_vec(expr.b, cs, cols, size, rot_scale, memo))
+    elif k == "prod":
+        r = cpu_ref.fr_mul_vec(eval_expr_vec(expr.a, cs, cols, size, rot_scale, memo),
+                               eval_expr_vec(expr.b, cs, cols, size, rot_scale, memo))
+    else:
+        raise ValueError(k)
+    memo[key] = np.ascontiguousarray(r)
+    return memo[key]
+
+
+def canon_ints(arr) -> list:
+    raw = cpu_ref.fr_from_mont(arr)
+    return [int(r[0]) | (int(r[1]) << 64) | (int(r[2]) << 128) | (int(r[3]) << 192) for r in raw]
+
+
+# ---- commitments -----------------------------------------------------------------------------
+class Committer:
+    def __init__(self, srs: Srs, domain: Domain, real_msm: bool):
+        self.srs, self.domain, self.real = srs, domain, real_msm
+
+    def commit_coeff(self, coeffs):
+        if self.real:
+            return bn254.g1_proj_from_limbs(cpu_ref.best_multiexp(coeffs, self.srs.g[:coeffs.shape[0]]))[0]
+        return bn254.g1_mul(bn254.G1_GEN, I(cpu_ref.fr_eval_poly(coeffs, L(self.srs.s))))
+
+    def commit_lagrange(self, values, coeffs=None):
+        if self.real:
+            return bn254.g1_proj_from_limbs(cpu_ref.best_multiexp(values, self.srs.g_lagrange))[0]
+        if coeffs is None:
+            coeffs = self.domain.lagrange_to_coeff(values)
+        return bn254.g1_mul(bn254.G1_GEN, I(cpu_ref.fr_eval_poly(coeffs, L(self.srs.s))))
+
+
+# ---- keygen ------------------------------------------------------------------------------------
+class ProvingKey:
+    pass
+
+
+def vk_transcript_repr(k, cs, fixed_commitments, perm_commitments) -> int:
+    """Stand-in for VerifyingKey::transcript_repr (Blake2b-512 personal "Halo2-Verify-Key" over the
+    Rust Debug rendering of the pinned vk, not restatable blind -- SURVEY.md B.10): same hash, over a
+    canonical serialisation of (k, cs shape, commitments).  Treated as a prover INPUT everywhere."""
+    h = hashlib.blake2b(digest_size=64, person=b"Halo2-Verify-Key")
+    h.update(("k=%d;adv=%d;fix=%d;inst=%d;deg=%d;perm=%d;lookups=%d;gates=%d" % (
+        k, cs.num_advice, cs.num_fixed, cs.num_instance, cs.degree(), len(cs.permutation), len(cs.lookups),
+        sum(len(g.polys) for g in cs.gates))).encode())
+    for p in list(fixed_commitments) + list(perm_commitments):
+        h.update(b"\0" * 64 if p is None else p[0].to_bytes(32, "little") + p[1].to_bytes(32, "little"))
+    return int.from_bytes(h.digest(), "little") % R_MOD
+
+
+def keygen(srs: Srs, cs, asm, real_msm=False) -> ProvingKey:
+    """keygen_vk + keygen_pk.  `asm` is the synthesized Assembly (zero image); selectors are compressed here."""
+    from zg_b200.plonk.mock import finalize_fixed
+    n, k = asm.n, asm.k
+    dom = Domain(k, cs.degree())
+    com = Committer(srs, dom, real_msm)
+    pk = ProvingKey()
+    pk.k, pk.n, pk.cs, pk.domain = k, n, cs, dom
+    fixed_int = finalize_fixed(cs, asm)
+    pk.fixed_values = [bn254.fr_to_limbs(c) for c in fixed_int]
+    pk.fixed_polys = [dom.lagrange_to_coeff(v) for v in pk.fixed_values]
+    pk.fixed_cosets = [dom.coeff_to_extended(c) for c in pk.fixed_polys]
+    pk.fixed_commitments = [com.commit_lagrange(v, c) for v, c in zip(pk.fixed_values, pk.fixed_polys)]
+    # permutation: sigma_c(w^r) = delta^{c'} w^{r'} for mapping[c][r] = (c', r')
+    m = len(asm.perm_cols)
+    wpow = [1] * n
+    for i in range(1, n):
+        wpow[i] = wpow[i - 1] * dom.omega % R_MOD
+    dpow = [pow(bn254.FR_DELTA, c, R_MOD) for c in range(m)]
+    pk.perm_values = []
+    for c in range(m):
+        pk.perm_values.append(bn254.fr_to_limbs([dpow[c2] * wpow[r2] % R_MOD for (c2, r2) in asm.mapping[c]]))
+    pk.perm_polys = [dom.lagrange_to_coeff(v) for v in pk.perm_values]
+    pk.perm_cosets = [dom.coeff_to_extended(c) for c in pk.perm_polys]
+    pk.perm_commitments = [com.commit_lagrange(v, c) for v, c in zip(pk.perm_values, pk.perm_polys)]
+    # l0, l_last, l_active_row on the extended domain
+    bf = cs.blinding_factors()
+    def coset_of(rows):
+        v = [0] * n
+        for r in rows:
+            v[r] = 1
+        return dom.coeff_to_extended(dom.lagrange_to_coeff(bn254.fr_to_limbs(v)))
+    pk.l0 = coset_of([0])
+    pk.l_last = coset_of([n - bf - 1])
+    l_blind = coset_of(range(n - bf, n))
+    one = np.tile(L(1), (dom.ext_n, 1))
+    pk.l_active = cpu_ref.fr_sub_vec(cpu_ref.fr_sub_vec(one, pk.l_last), l_blind)
+    pk.transcript_repr = vk_transcript_repr(k, cs, pk.fixed_commitments, pk.perm_commitments)
+    return pk
+
+
+# ---- constraint expressions at one point (shared by prover checks and the verifier) ------------------
+def expressions_at_point(cs, dom, ev, challenges, l0, l_last, l_blind, x):
+    """All constraint polynomial evaluations in the order evaluate_h / verify_proof fold them by y.
+    `ev` holds the claimed evaluations: advice[q], fixed[q], instance[q], perm_common[c],
+    perm_sets[i] = (z, z_next, z_last|None), lookups[i] = (z, z_next, a, a_inv, s)."""
+    theta, beta, gamma = challenges["theta"], challenges["beta"], challenges["gamma"]
+
+    def get(kind, qi):
+        return ev[kind][qi]
+    out = []
+    for g in cs.gates:
+        for p in g.polys:
+            out.append(p.evaluate(get))
+    active = (1 - (l_last + l_blind)) % R_MOD
+    sets = ev["perm_sets"]
+    chunk = cs.degree() - 2
+    cols = cs.permutation
+    if sets:
+        out.append(l0 * (1 - sets[0][0]) % R_MOD)
+        zl = sets[-1][0]
+        out.append(l_last * (zl * zl - zl) % R_MOD)
+        for i in range(1, len(sets)):
+            out.append(l0 * (sets[i][0] - sets[i - 1][2]) % R_MOD)
+        for i, (z, z_next, _) in enumerate(sets):
+            cc = cols[i * chunk:(i + 1) * chunk]
+            left, right = z_next, z
+            cur_delta = beta * x % R_MOD * pow(bn254.FR_DELTA, i * chunk, R_MOD) % R_MOD
+            for j, col in enumerate(cc):
+                qi = cs.queries[col.kind].index((col.index, 0))
+                v = ev[col.kind][qi]
+                left = left * ((v + beta * ev["perm_common"][i * chunk + j] + gamma) % R_MOD) % R_MOD
+                right = right * ((v + cur_delta + gamma) % R_MOD) % R_MOD
+                cur_delta = cur_delta * bn254.FR_DELTA % R_MOD
+            out.append((left - right) * active % R_MOD)
+    for l, (z, z_next, a, a_inv, s) in zip(cs.lookups, ev["lookups"]):
+        ci = 0
+        for e in l.inputs:
+            ci = (ci * theta + e.evaluate(get)) % R_MOD
+        ct = 0
+        for e in l.tables:
+            ct = (ct * theta + e.evaluate(get)) % R_MOD
+        out.append(l0 * (1 - z) % R_MOD)
+        out.append(l_last * (z * z - z) % R_MOD)
+        out.append((z_next * (a + beta) % R_MOD * (s + gamma) - z * (ci + beta) % R_MOD * (ct + gamma)) % R_MOD * active % R_MOD)
+        out.append(l0 * (a - s) % R_MOD)
+        out.append((a - s) * (a - a_inv) % R_MOD * active % R_MOD)
+    return out
+
+
+def build_queries(cs, dom, x, nsets):
+    """(kind, index, rotation-point) in create_proof's ProverQuery order; rotation as an int."""
+    bf = cs.blinding_factors()
+    q = []
+    for qi, (col, rot) in enumerate(cs.queries[ADVICE]):
+        q.append(("advice", col, rot, ("advice", qi)))
+    for i in range(nsets):
+        q.append(("perm_z", i, 0, ("perm_sets", i, 0)))
+        q.append(("perm_z", i, 1, ("perm_sets", i, 1)))
+    for i in reversed(range(nsets - 1)):
+        q.append(("perm_z", i, -(bf + 1), ("perm_sets", i, 2)))
+    for i in range(len(cs.lookups)):
+        q.append(("lk_z", i, 0, ("lookups", i, 0)))
+        q.append(("lk_a", i, 0, ("lookups", i, 2)))
+        q.append(("lk_s", i, 0, ("lookups", i, 4)))
+        q.append(("lk_a", i, -1, ("lookups", i, 3)))
+        q.append(("lk_z", i, 1, ("lookups", i, 1)))
+    for qi, (col, rot) in enumerate(cs.queries[FIXED]):
+        q.append(("fixed", col, rot, ("fixed", qi)))
+    for c in range(len(cs.permutation)):
+        q.append(("sigma", c, 0, ("perm_common", c)))
+    q.append(("h", 0, 0, ("h",)))
+    q.append(("random", 0, 0, ("random",)))
+    return q
+
+
+def group_by_point(queries):
+    """construct_intermediate_sets: first-appearance order of rotation points."""
+    sets = []
+    for qq in queries:
+        for rot, lst in sets:
+            if rot == qq[2]:
+                lst.append(qq)
+                break
+        else:
+            sets.append((qq[2], [qq]))
+    return sets
+
+
+# ---- create_proof ---------------------------------------------------------------------------------
+def permute_expression_pair(a_int, s_int, usable):
+    """lookup::prover::permute_expression_pair on canonical ints (without the blinding rows)."""
+    pa = sorted(a_int[:usable])
+    left = {}
+    for v in s_int[:usable]:
+        left[v] = left.get(v, 0) + 1
+    ps = [0] * usable
+    repeated = []
+    for row, v in enumerate(pa):
+        if row == 0 or v != pa[row - 1]:
+            ps[row] = v
+            if left.get(v, 0) <= 0:
+                raise ValueError("ConstraintSystemFailure: lookup input not in table")
+            left[v] -= 1
+        else:
+            repeated.append(row)
+    for v in sorted(left):
+        for _ in range(left[v]):
+            ps[repeated.pop()] = v
+    assert not repeated
+    return pa, ps
+
+
+def create_proof(srs: Srs, pk: ProvingKey, advice_int, instances, rng: XorShiftRng, real_msm=False, trace=None):
+    """plonk::create_proof for one circuit.  advice_int: 6 columns of n canonical ints (rows >= usable
+    are overwritten by blinding); instances: [[ints]] one list per instance column."""
+    cs, dom, n, k = pk.cs, pk.domain, pk.n, pk.k
+    com = Committer(srs, dom, real_msm)
+    tr = EvmTranscript()
+    bf = cs.blinding_factors()
+    usable = n - (bf + 1)
+    T = trace if trace is not None else {}
+    tr.common_scalar(pk.transcript_repr)
+    # 1. instance
+    inst_values = []
+    for vals in instances:
+        assert len(vals) <= usable
+        for v in vals:
+            tr.common_scalar(v)
+        inst_values.append(bn254.fr_to_limbs(list(vals) + [0] * (n - len(vals))))
+    inst_polys = [dom.lagrange_to_coeff(v) for v in inst_values]
+    # 2. advice
+    adv_values = []
+    for col in advice_int:
+        v = bn254.fr_to_limbs(col)
+        v[usable:] = rng.fr(n - usable)
+        adv_values.append(v)
+    for _ in adv_values:
+        rng.fr(1)                                  # Blind(Fr::random) per column (unused by KZG)
+    adv_polys = [dom.lagrange_to_coeff(v) for v in adv_values]
+    adv_comms = [com.commit_lagrange(v, c) for v, c in zip(adv_values, adv_polys)]
+    for c in adv_comms:
+        tr.write_point(c)
+    T["advice_commitments"] = adv_comms
+    theta = tr.squeeze()
+    # 3. lookups: compress, permute, commit
+    cols = {ADVICE: adv_values, FIXED: pk.fixed_values, INSTANCE: inst_values}
+    lookups = []
+    memo = {}
+    for lk in cs.lookups:
+        def compress(exprs):
+            acc = np.zeros((n, 4), dtype=np.uint64)
+            for e in exprs:
+                acc = cpu_ref.fr_mul_add_scalar(acc, L(theta), eval_expr_vec(e, cs, cols, n, 1, memo))
+            return acc
+        ci, ct = compress(lk.inputs), compress(lk.tables)
+        pa, ps = permute_expression_pair(canon_ints(ci), canon_ints(ct), usable)
+        pa_l = np.concatenate([bn254.fr_to_limbs(pa), rng.fr(bf + 1)])
+        ps_l = np.concatenate([bn254.fr_to_limbs(ps), rng.fr(bf + 1)])
+        pa_poly = dom.lagrange_to_coeff(pa_l)
+        rng.fr(1)
+        pa_comm = com.commit_lagrange(pa_l, pa_poly)
+        ps_poly = dom.lagrange_to_coeff(ps_l)
+        rng.fr(1)
+        ps_comm = com.commit_lagrange(ps_l, ps_poly)
+        tr.write_point(pa_comm)
+        tr.write_point(ps_comm)
+        lookups.append({"ci": ci, "ct": ct, "pa": pa_l, "ps": ps_l, "pa_poly": pa_poly, "ps_poly": ps_poly})
+    beta = tr.squeeze()
+    gamma = tr.squeeze()
+    T["challenges"] = {"theta": theta, "beta": beta, "gamma": gamma}
+    # 4. permutation product sets
+    chunk = cs.degree() - 2
+    pcols = cs.permutation
+    perm_sets = []
+    deltaomega = 1
+    last_z = 1
+    wpow = [1] * n
+    for i in range(1, n):
+        wpow[i] = wpow[i - 1] * dom.omega % R_MOD
+    wpow_l = bn254.fr_to_limbs(wpow)
+    for s0 in range(0, len(pcols), chunk):
+        cc = pcols[s0:s0 + chunk]
+        mod = np.tile(L(1), (n, 1))
+        for j, col in enumerate(cc):
+            v = cols[col.kind][col.index]
+            t = cpu_ref.fr_mul_add_scalar(pk.perm_values[s0 + j], L(beta), v)        # beta*sigma + value
+            t = cpu_ref.fr_add_vec(t, np.tile(L(gamma), (n, 1)))
+            mod = cpu_ref.fr_mul_vec(mod, t)
+        mod = cpu_ref.fr_batch_invert(mod)
+        for col in cc:
+            v = cols[col.kind][col.index]
+            t = cpu_ref.fr_mul_add_scalar(wpow_l, L(deltaomega * beta % R_MOD), v)     # delta^j w^i beta + value
+            t = cpu_ref.fr_add_vec(t, np.tile(L(gamma), (n, 1)))
+            mod = cpu_ref.fr_mul_vec(mod, t)
+            deltaomega = deltaomega * bn254.FR_DELTA % R_MOD
+        z = cpu_ref.fr_running_product(mod, L(last_z), n)
+        z[n - bf:] = rng.fr(bf)
+        last_z = I(z[n - (bf + 1)])
+        rng.fr(1)
+        z_poly = dom.lagrange_to_coeff(z)
+        z_comm = com.commit_lagrange(z, z_poly)
+        tr.write_point(z_comm)
+        perm_sets.append({"poly": z_poly, "coset": dom.coeff_to_extended(z_poly)})
+    # 5. lookup products
+    for lk in lookups:
+        den = cpu_ref.fr_mul_vec(cpu_ref.fr_add_vec(lk["pa"], np.tile(L(beta), (n, 1))),
+                                 cpu_ref.fr_add_vec(lk["ps"], np.tile(L(gamma), (n, 1))))
+        f = cpu_ref.fr_batch_invert(den)
+        f = cpu_ref.fr_mul_vec(f, cpu_ref.fr_add_vec(lk["ci"], np.tile(L(beta), (n, 1))))
+        f = cpu_ref.fr_mul_vec(f, cpu_ref.fr_add_vec(lk["ct"], np.tile(L(gamma), (n, 1))))
+        z = np.concatenate([cpu_ref.fr_running_product(f, L(1), n - bf), rng.fr(bf)])
+        rng.fr(1)
+        z_comm = com.commit_lagrange(z)
+        lk["z_poly"] = dom.lagrange_to_coeff(z)
+        tr.write_point(z_comm)
+    # 6. vanishing random polynomial
+    random_poly = rng.fr(n)
+    rng.fr(1)
+    tr.write_point(com.commit_coeff(random_poly))
+    y = tr.squeeze()
+    T["challenges"]["y"] = y
+    # 7. evaluate_h on the extended coset
+    en = dom.ext_n
+    rs = 1 << (dom.ext_k - k)
+    ecols = {ADVICE: [dom.coeff_to_extended(c) for c in adv_polys], FIXED: pk.fixed_cosets,
+             INSTANCE: [dom.coeff_to_extended(c) for c in inst_polys]}
+    yL = L(y)
+    h = np.zeros((en, 4), dtype=np.uint64)
+
+    def fold(term):
+        nonlocal h
+        h = cpu_ref.fr_mul_add_scalar(h, yL, term)
+    ememo = {}
+    for g in cs.gates:
+        for p in g.polys:
+            fold(eval_expr_vec(p, cs, ecols, en, rs, ememo))
+    one = np.tile(L(1), (en, 1))
+    tile = lambda v: np.tile(L(v), (en, 1))
+    roll = lambda a, rot: np.roll(a, -rot * rs, axis=0)
+    mul, add, sub = cpu_ref.fr_mul_vec, cpu_ref.fr_add_vec, cpu_ref.fr_sub_vec
+    if perm_sets:
+        z0, zl = perm_sets[0]["coset"], perm_sets[-1]["coset"]
+        fold(mul(sub(one, z0), pk.l0))
+        fold(mul(sub(mul(zl, zl), zl), pk.l_last))
+        for i in range(1, len(perm_sets)):
+            fold(mul(sub(perm_sets[i]["coset"], roll(perm_sets[i - 1]["coset"], -(bf + 1))), pk.l0))
+        # X on the coset: zeta * ext_omega^idx
+        xs = [dom.zeta] * en
+        for i in range(1, en):
+            xs[i] = xs[i - 1] * dom.ext_omega % R_MOD
+        xs_l = bn254.fr_to_limbs(xs)
+        cur_delta = beta
+        for i, st in enumerate(perm_sets):
+            cc = pcols[i * chunk:(i + 1) * chunk]
+            left, right = roll(st["coset"], 1), st["coset"]
+            for j, col in enumerate(cc):
+                v = ecols[col.kind][col.index]
+                left = mul(left, add(cpu_ref.fr_mul_add_scalar(pk.perm_cosets[i * chunk + j], L(beta), v), tile(gamma)))
+                right = mul(right, add(cpu_ref.fr_mul_add_scalar(xs_l, L(cur_delta), v), tile(gamma)))
+                cur_delta = cur_delta * bn254.FR_DELTA % R_MOD
+            fold(mul(sub(left, right), pk.l_active))
+    for lk_def, lk in zip(cs.lookups, lookups):
+        zc = dom.coeff_to_extended(lk["z_poly"])
+        ac = dom.coeff_to_extended(lk["pa_poly"])
+        sc = dom.coeff_to_extended(lk["ps_poly"])
+
+        def compress_ext(exprs):
+            acc = np.zeros((en, 4), dtype=np.uint64)
+            for e in exprs:
+                acc = cpu_ref.fr_mul_add_scalar(acc, L(theta), eval_expr_vec(e, cs, ecols, en, rs, ememo))
+            return acc
+        tv = mul(add(compress_ext(lk_def.inputs), tile(beta)), add(compress_ext(lk_def.tables), tile(gamma)))
+        a_minus_s = sub(ac, sc)
+        fold(mul(sub(one, zc), pk.l0))
+        fold(mul(sub(mul(zc, zc), zc), pk.l_last))
+        fold(mul(sub(mul(mul(roll(zc, 1), add(ac, tile(beta))), add(sc, tile(gamma))), mul(zc, tv)), pk.l_active))
+        fold(mul(a_minus_s, pk.l0))
+        fold(mul(mul(a_minus_s, sub(ac, roll(ac, -1))), pk.l_active))
+    # 8. vanishing::construct
+    h = dom.divide_by_vanishing(h)
+    h_coeff = dom.extended_to_coeff(h)
+    pieces = [h_coeff[i * n:(i + 1) * n] for i in range(dom.quotient_poly_degree)]
+    for _ in pieces:
+        rng.fr(1)
+    for p in pieces:
+        tr.write_point(com.commit_coeff(p))
+    x = tr.squeeze()
+    xn = pow(x, n, R_MOD)
+    T["challenges"]["x"] = x
+    # 9. evaluations
+    def ev(poly, rot):
+        return I(cpu_ref.fr_eval_poly(poly, L(dom.rotate_omega(x, rot))))
+    evals = {ADVICE: [ev(adv_polys[c], r) for c, r in cs.queries[ADVICE]]}
+    for v in evals[ADVICE]:
+        tr.write_scalar(v)
+    evals[FIXED] = [ev(pk.fixed_polys[c], r) for c, r in cs.queries[FIXED]]
+    for v in evals[FIXED]:
+        tr.write_scalar(v)
+    h_poly = np.zeros((n, 4), dtype=np.uint64)
+    for p in reversed(pieces):
+        h_poly = cpu_ref.fr_mul_add_scalar(h_poly, L(xn), p)
+    random_eval = ev(random_poly, 0)
+    tr.write_scalar(random_eval)
+    evals["perm_common"] = [ev(p, 0) for p in pk.perm_polys]
+    for v in evals["perm_common"]:
+        tr.write_scalar(v)
+    evals["perm_sets"] = []
+    for i, st in enumerate(perm_sets):
+        e = [ev(st["poly"], 0), ev(st["poly"], 1), None]
+        tr.write_scalar(e[0])
+        tr.write_scalar(e[1])
+        if i + 1 < len(perm_sets):
+            e[2] = ev(st["poly"], -(bf + 1))
+            tr.write_scalar(e[2])
+        evals["perm_sets"].append(e)
+    evals["lookups"] = []
+    for lk in lookups:
+        e = [ev(lk["z_poly"], 0), ev(lk["z_poly"], 1), ev(lk["pa_poly"], 0), ev(lk["pa_poly"], -1), ev(lk["ps_poly"], 0)]
+        for v in e:
+            tr.write_scalar(v)
+        evals["lookups"].append(e)
+    evals["h"] = ev(h_poly, 0)
+    evals["random"] = random_eval
+    T["evals"] = evals
+    # 10. GWC multi-open
+    polys = {"advice": adv_polys, "fixed": pk.fixed_polys, "sigma": pk.perm_polys, "perm_z": [s["poly"] for s in perm_sets],
+             "lk_z": [l["z_poly"] for l in lookups], "lk_a": [l["pa_poly"] for l in lookups],
+             "lk_s": [l["ps_poly"] for l in lookups], "h": [h_poly], "random": [random_poly]}
+
+    def get_eval(ref):
+        e = evals[ref[0]]
+        for i in ref[1:]:
+            e = e[i]
+        return e
+    v = tr.squeeze()
+    for rot, qs in group_by_point(build_queries(cs, dom, x, len(perm_sets))):
+        z = dom.rotate_omega(x, rot)
+        acc = np.zeros((n, 4), dtype=np.uint64)
+        eacc, pw = 0, 1
+        for (kind, idx, _, ref) in qs:
+            acc = cpu_ref.fr_mul_add_scalar(polys[kind][idx], L(pw), acc)
+            eacc = (eacc + get_eval(ref) * pw) % R_MOD
+            pw = pw * v % R_MOD
+        acc[0] = L((I(acc[0]) - eacc) % R_MOD)
+        w = cpu_ref.fr_kate_division(acc, L(z))
+        tr.write_point(com.commit_coeff(w))
+    return bytes(tr.out)
+
+
+# ---- verify_proof -----------------------------------------------------------------------------------
+def verify_proof(srs: Srs, pk: ProvingKey, instances, proof: bytes) -> bool:
+    """plonk::verify_proof + VerifierGWC with SingleStrategy.  The final pairing check
+    e(W', [s]G2) == e(R, G2) is done in G1 with the test SRS's known trapdoor: [s]W' == R."""
+    cs, dom, n = pk.cs, pk.domain, pk.n
+    try:
+        tr = EvmTranscript(proof)
+        tr.common_scalar(pk.transcript_repr)
+        for vals in instances:
+            for v in vals:
+                tr.common_scalar(v)
+        adv_c = [tr.read_point() for _ in range(cs.num_advice)]
+        theta = tr.squeeze()
+        lk_perm = [(tr.read_point(), tr.read_point()) for _ in cs.lookups]
+        beta, gamma = tr.squeeze(), tr.squeeze()
+        chunk = cs.degree() - 2
+        nsets = (len(cs.permutation) + chunk - 1) // chunk
+        perm_c = [tr.read_point() for _ in range(nsets)]
+        lk_z = [tr.read_point() for _ in cs.lookups]
+        random_c = tr.read_point()
+        y = tr.squeeze()
+        h_c = [tr.read_point() for _ in range(dom.quotient_poly_degree)]
+        x = tr.squeeze()
+        xn = pow(x, n, R_MOD)
+        bf = cs.blinding_factors()
+        ev = {ADVICE: [tr.read_scalar() for _ in cs.queries[ADVICE]]}
+        # instance evals from the public inputs (QUERY_INSTANCE = false)
+        ev[INSTANCE] = []
+        for col, rot in cs.queries[INSTANCE]:
+            vals = instances[col]
+            ls = dom.l_i_range(x, xn, range(-rot, len(vals) - rot))
+            ev[INSTANCE].append(sum(a * b for a, b in zip(vals, ls)) % R_MOD)
+        ev[FIXED] = [tr.read_scalar() for _ in cs.queries[FIXED]]
+        random_eval = tr.read_scalar()
+        ev["perm_common"] = [tr.read_scalar() for _ in cs.permutation]
+        ev["perm_sets"] = []
+        for i in range(nsets):
+            e = [tr.read_scalar(), tr.read_scalar(), None]
+            if i + 1 < nsets:
+                e[2] = tr.read_scalar()
+            ev["perm_sets"].append(e)
+        ev["lookups"] = [[tr.read_scalar() for _ in range(5)] for _ in cs.lookups]
+        l_evals = dom.l_i_range(x, xn, range(-(bf + 1), 1))
+        l_last, l_blind, l_0 = l_evals[0], sum(l_evals[1:1 + bf]) % R_MOD, l_evals[1 + bf]
+        exprs = expressions_at_point(cs, dom, ev, {"theta": theta, "beta": beta, "gamma": gamma}, l_0, l_last, l_blind, x)
+        expected_h = 0
+        for e in exprs:
+            expected_h = (expected_h * y + e) % R_MOD
+        expected_h = expected_h * pow(xn - 1, -1, R_MOD) % R_MOD
+        h_commit = None
+        for c in reversed(h_c):
+            h_commit = bn254.g1_add(bn254.g1_mul(h_commit, xn), c)
+        ev["h"], ev["random"] = expected_h, random_eval
+        comm = {"advice": adv_c, "fixed": pk.fixed_commitments, "sigma": pk.perm_commitments, "perm_z": perm_c,
+                "lk_z": lk_z, "lk_a": [p[0] for p in lk_perm], "lk_s": [p[1] for p in lk_perm], "h": [h_commit],
+                "random": [random_c]}
+
+        def get_eval(ref):
+            e = ev[ref[0]]
+            for i in ref[1:]:
+                e = e[i]
+            return e
+        v = tr.squeeze()
+        sets = group_by_point(build_queries(cs, dom, x, nsets))
+        ws = [tr.read_point() for _ in sets]
+        u = tr.squeeze()
+        if tr.pos != len(proof):
+            return False
+        lhs = None   # sum u^i W_i                     (paired with [s]G2)
+        rhs = None   # sum u^i (C_i - e_i G + z_i W_i) (paired with G2)
+        pu = 1
+        for (rot, qs), w in zip(sets, ws):
+            z = dom.rotate_omega(x, rot)
+            cacc, eacc, pw = None, 0, 1
+            for (kind, idx, _, ref) in qs:
+                cacc = bn254.g1_add(cacc, bn254.g1_mul(comm[kind][idx], pw))
+                eacc = (eacc + get_eval(ref) * pw) % R_MOD
+                pw = pw * v % R_MOD
+            term = bn254.g1_add(cacc, bn254.g1_mul(bn254.G1_GEN, (-eacc) % R_MOD))
+            term = bn254.g1_add(term, bn254.g1_mul(w, z))
+            rhs = bn254.g1_add(rhs, bn254.g1_mul(term, pu))
+            lhs = bn254.g1_add(lhs, bn254.g1_mul(w, pu))
+            pu = pu * u % R_MOD
+        return bn254.g1_mul(lhs, srs.s) == rhs
+    except (ValueError, IndexError):
+        return False

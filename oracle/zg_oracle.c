@@ -465,6 +465,45 @@ void zgo_fq_to_mont_vec(const uint64_t* in, fe* out, size_t n) {
     fe_mul(&out[i], &t, &FQ.r2, &FQ);
   }
 }
+/* serial running product as lookup::prover::commit_product / permutation::prover::commit:
+ * z[0] = start, z[i] = z[i-1] * f[i-1] for i < n_out */
+void zgo_fr_running_product(const fe* f, const fe* start, fe* z, size_t n_out) {
+  z[0] = *start;
+  for (size_t i = 1; i < n_out; i++) fe_mul(&z[i], &z[i - 1], &f[i - 1], &FR);
+}
+/* arithmetic::kate_division: q(X) = (a(X) - a(z)) / (X - z), q has n-1 coefficients */
+void zgo_fr_kate_division(const fe* a, size_t n, const fe* z, fe* q) {
+  fe tmp = {{0, 0, 0, 0}}, negz;
+  fe_neg(&negz, z, &FR);
+  for (size_t i = n - 1; i >= 1; i--) {
+    fe lead;
+    fe_sub(&lead, &a[i], &tmp, &FR);
+    q[i - 1] = lead;
+    fe_mul(&tmp, &lead, &negz, &FR);
+  }
+}
+/* out[i] = a[i] * s + b[i]   (polynomial folding: acc * theta + expr, acc * xn + piece, ...) */
+void zgo_fr_mul_add_scalar(const fe* a, const fe* s, const fe* b, fe* o, size_t n) {
+#pragma omp parallel for
+  for (size_t i = 0; i < n; i++) {
+    fe t;
+    fe_mul(&t, &a[i], s, &FR);
+    fe_add(&o[i], &t, &b[i], &FR);
+  }
+}
+/* Fr::from_u512 on n x 8 little-endian u64 words (halo2curves Fr::random draws) -> Montgomery */
+void zgo_fr_from_u512(const uint64_t* w, fe* out, size_t n) {
+  fe r3;
+  fe_mul(&r3, &FR.r2, &FR.r2, &FR); /* R^2 * R^2 / R = R^3 */
+  for (size_t i = 0; i < n; i++) {
+    fe d0, d1, t0, t1;
+    memcpy(d0.l, w + 8 * i, 32);
+    memcpy(d1.l, w + 8 * i + 4, 32);
+    fe_mul(&t0, &d0, &FR.r2, &FR);
+    fe_mul(&t1, &d1, &r3, &FR);
+    fe_add(&out[i], &t0, &t1, &FR);
+  }
+}
 int zgo_num_threads(void) { return omp_get_max_threads(); }
 
 /* Synthetic SRS-shaped bases for benchmarks: out[i] = [start + i + 1] * gen, affine.

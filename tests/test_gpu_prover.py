@@ -1,0 +1,99 @@
+"""End-to-end parity of the B200 prover (zg_pk_load + zg_create_proof through the C ABI) against the CPU
+oracle's restatement of halo2's keygen / create_proof (oracle/halo2_ref.py) for the WNN circuit:
+same SRS, same seeded RNG => identical vk commitments and identical proof BYTES; the restated
+verifier accepts the GPU proof and rejects tampering.  Models/images are the reference's own files."""
+import os
+
+import numpy as np
+import pytest
+
+import bn254
+import halo2_ref as H
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+SEED = bytes(range(16))
+
+
+def _stage_of(offset, cs):
+    """which proof section a byte offset falls in (for mismatch reports)."""
+    sections = [("advice commitments", 64 * cs.num_advice), ("lookup permuted commitments", 128 * len(cs.lookups)),
+                ("permutation z commitments", 64 * 2), ("lookup z commitments", 64 * len(cs.lookups)),
+                ("random poly commitment", 64), ("h piece commitments", 64 * (cs.degree() - 1)),
+                ("advice evals", 32 * len(cs.queries["advice"])), ("fixed evals", 32 * len(cs.queries["fixed"])),
+                ("random eval", 32), ("sigma evals", 32 * len(cs.permutation)), ("perm evals", 32 * 5),
+                ("lookup evals", 32 * 5 * len(cs.lookups)), ("gwc witnesses", 64 * 4)]
+    pos = 0
+    for name, ln in sections:
+        if offset < pos + ln:
+            return "%s (+%d)" % (name, offset - pos)
+        pos += ln
+    return "past end"
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    from zg_b200.io import load_wnn, load_grayscale_image
+    wnn = load_wnn(os.path.join(GOLD, "model_28input_256entry_1hash_1bpi.hdf5"))
+    img = load_grayscale_image(os.path.join(GOLD, "example_image_7.png"))
+    k = 14
+    srs = H.Srs(k, 0x1F3C5A7B9D2E4F60718293A4B5C6D7E8)
+    return wnn, img, k, srs
+
+
+def test_tiny_model_proof_bytes_match_oracle(ctx, tiny):
+    import zg_b200
+    from zg_b200.prover import ParamsKZG, keygen, create_proof
+    wnn, img, k, srs = tiny
+    outputs = wnn.predict(img)
+    assert outputs == [9, 6, 13, 10, 17, 10, 9, 26, 11, 16]     # tests/integration_test.rs:13-20
+    # oracle side
+    circ0, asm0 = wnn.synthesize(np.zeros((28, 28), dtype=np.uint8), k)
+    opk = H.keygen(srs, circ0.cs, asm0)
+    _, asm = wnn.synthesize(img, k)
+    oproof = H.create_proof(srs, opk, asm.advice, [outputs], H.XorShiftRng(SEED))
+    assert H.verify_proof(srs, opk, [outputs], oproof)
+    # B200 side (fresh constraint system: keygen compresses selectors in place)
+    params = ParamsKZG(k, srs.g, srs.g_lagrange)
+    circ1, asm1 = wnn.synthesize(np.zeros((28, 28), dtype=np.uint8), k)
+    pk = keygen(ctx, params, circ1.cs, asm1)
+    assert pk.fixed_commitments == opk.fixed_commitments
+    assert pk.perm_commitments == opk.perm_commitments
+    assert pk.transcript_repr == opk.transcript_repr
+    proof = create_proof(params, pk, asm.advice, [outputs], zg_b200.lib.XorShift.from_seed(SEED))
+    assert len(proof) == len(oproof) == 3840
+    if proof != oproof:
+        first = next(i for i in range(len(proof)) if proof[i] != oproof[i])
+        pytest.fail("proof bytes differ from the oracle first at offset %d: %s" % (first, _stage_of(first, circ0.cs)))
+    assert H.verify_proof(srs, opk, [outputs], proof)
+    bad = bytearray(proof)
+    bad[1000] ^= 1
+    assert not H.verify_proof(srs, opk, [outputs], bytes(bad))
+    # a second proof with another seed differs but verifies; same seed reproduces the bytes
+    p2 = create_proof(params, pk, asm.advice, [outputs], zg_b200.lib.XorShift.from_seed(bytes(range(1, 17))))
+    assert p2 != proof and H.verify_proof(srs, opk, [outputs], p2)
+    p3 = create_proof(params, pk, asm.advice, [outputs], zg_b200.lib.XorShift.from_seed(SEED))
+    assert p3 == proof
+    print("stage ms", pk.stage_ms())
+    pk.close()
+
+
+def test_lookup_failure_is_reported(ctx, tiny):
+    """a witness whose lookup input is not in the table must fail like plonk::Error::ConstraintSystemFailure"""
+    import zg_b200
+    from zg_b200.prover import ParamsKZG, keygen, create_proof
+    wnn, img, k, srs = tiny
+    params = ParamsKZG(k, srs.g, srs.g_lagrange)
+    circ, asm0 = wnn.synthesize(np.zeros((28, 28), dtype=np.uint8), k)
+    pk = keygen(ctx, params, circ.cs, asm0)
+    _, asm = wnn.synthesize(img, k)
+    adv = [list(c) for c in asm.advice]
+    # break a byte decomposition: a running-sum cell under the range-check lookup becomes huge
+    sel_rows = [r for r in range(asm.usable_rows) if asm.selectors[8][r]]
+    adv[5][sel_rows[0]] = (adv[5][sel_rows[0]] + (1 << 40)) % bn254.R_MOD
+    with pytest.raises(zg_b200.ZgError) as ei:
+        create_proof(params, pk, adv, [wnn.predict(img)], zg_b200.lib.XorShift.from_seed(SEED))
+    assert ei.value.code == -5
+    pk.close()
