@@ -351,9 +351,22 @@ __device__ __forceinline__ Fp<P> fp_mul_ptx(const Fp<P>& a, const Fp<P>& b) {
 }
 #endif
 
+#if defined(__CUDA_ARCH__) && defined(ZG_FP_MUL_NOINLINE)
+// Latency-bound kernels (one warp walking a chain of EC additions) want a SMALL instruction
+// footprint: with the multiplier inlined a single xyzz_add is ~96 KB of straight-line SASS, far beyond
+// the 32 KB L1.5 instruction cache, and a lone warp then runs at instruction-fetch speed.  Translation
+// units that define ZG_FP_MUL_NOINLINE call one shared copy of the multiplier instead.
+template <class P>
+__device__ __noinline__ Fp<P> fp_mul_outlined(Fp<P> a, Fp<P> b) {
+  return fp_mul_portable<P>(a, b);
+}
+#endif
+
 template <class P>
 ZG_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
-#if defined(__CUDA_ARCH__) && ZG_MUL_PTX
+#if defined(__CUDA_ARCH__) && defined(ZG_FP_MUL_NOINLINE)
+  return fp_mul_outlined<P>(a, b);
+#elif defined(__CUDA_ARCH__) && ZG_MUL_PTX
   return fp_mul_ptx<P>(a, b);
 #else
   return fp_mul_portable<P>(a, b);

@@ -7,8 +7,10 @@
 // (SURVEY.md Appendix B.3).  Call site: create_proof, /root/reference/src/wnn.rs:242-259.
 //
 // B200-first restatement that yields the same two columns without sorting the inputs:
-//   1. LSD radix sort of the (canonical) table values only (top 64 bits first, verified, full
-//      256-bit fallback), unique values U with multiplicities cntT;
+//   1. block-parallel LSD radix sort (8-bit digits, warp match_any ranking) of the canonical table
+//      values only -- top 64 bits first, checked, full 256-bit passes as the fallback -- then the
+//      unique values U with their multiplicities.  Tables that do not depend on theta (one table
+//      expression) are sorted once per proving key and cached by the caller;
 //   2. every input is ranked by binary search in U (an input that is not in the table raises the
 //      constraint-system failure flag) and counted: cntA;
 //   3. exclusive scans give the start of every value's run in A', the ascending list of left-over
@@ -47,9 +49,11 @@ __global__ void k_canonical(const Fr* __restrict__ in, Fr* __restrict__ out, uin
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) stf(out + i, fp_from_mont(ldf(in + i)));
 }
-__global__ void k_iota(uint32_t* a, uint32_t n) {
+__global__ void k_canonical_iota(const Fr* __restrict__ in, Fr* __restrict__ out, uint32_t* __restrict__ idx, uint32_t n) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) a[i] = i;
+  if (i >= n) return;
+  stf(out + i, fp_from_mont(ldf(in + i)));
+  idx[i] = i;
 }
 
 // ---- single-CTA exclusive scan of u32 (out has n+1 entries, out[n] = total) -----------------------
@@ -80,48 +84,115 @@ __global__ void __launch_bounds__(1024) k_scan_excl_u32(const uint32_t* __restri
   __syncthreads();
   uint32_t run = warp_sums[wid] + incl - sum;
   for (uint32_t i = b; i < e; i++) {
-    uint32_t v = in[i];   // in and out may not alias
+    uint32_t v = in[i];
+    out[i] = run;
+    run += v;
+  }
+  if (tid == 0) out[n] = total_s;
+}
+// three independent scans in one launch (grid = 3): cuts the launch latency of the bookkeeping
+struct Scan3 {
+  const uint32_t* in[3];
+  uint32_t* out[3];
+  uint32_t n;
+};
+__global__ void __launch_bounds__(1024) k_scan3(Scan3 S) {
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t total_s;
+  const uint32_t* in = S.in[blockIdx.x];
+  uint32_t* out = S.out[blockIdx.x];
+  const uint32_t n = S.n;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const uint32_t per = (n + 1023) / 1024;
+  const uint32_t b = min(tid * per, n), e = min(b + per, n);
+  uint32_t sum = 0;
+  for (uint32_t i = b; i < e; i++) sum += in[i];
+  uint32_t incl = sum;
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+    if ((int)lane >= d) incl += o;
+  }
+  if (lane == 31) warp_sums[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t ws = warp_sums[lane], wi = ws;
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t o = __shfl_up_sync(0xffffffffu, wi, d);
+      if ((int)lane >= d) wi += o;
+    }
+    warp_sums[lane] = wi - ws;
+    if (lane == 31) total_s = wi;
+  }
+  __syncthreads();
+  uint32_t run = warp_sums[wid] + incl - sum;
+  for (uint32_t i = b; i < e; i++) {
+    uint32_t v = in[i];
     out[i] = run;
     run += v;
   }
   if (tid == 0) out[n] = total_s;
 }
 
-// ---- LSD radix sort of indices by one key byte -----------------------------------------------------
-constexpr int RS_CHUNK = 64;     // elements per thread
-constexpr int RS_THREADS = 32;   // threads per CTA (one u32[256] offset table per thread in smem)
+// ---- block-parallel LSD radix sort of an index permutation by one key byte ---------------------------
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 4;                       // rounds per CTA
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;    // keys per CTA
 
 __device__ __forceinline__ uint32_t key_byte(const Fr* keys, uint32_t idx, uint32_t byte) {
   return (keys[idx].v[byte >> 2] >> ((byte & 3) * 8)) & 0xff;
 }
-
-// hist[d * T + t] = number of elements of chunk t whose digit is d
-__global__ void __launch_bounds__(RS_THREADS) k_rs_count(const Fr* __restrict__ keys, const uint32_t* __restrict__ idx, uint32_t n,
-                                                         uint32_t byte, uint32_t T, uint32_t* __restrict__ hist) {
-  __shared__ uint32_t cnt[256][RS_THREADS];
-  const uint32_t t = blockIdx.x * RS_THREADS + threadIdx.x;
-  for (int d = 0; d < 256; d++) cnt[d][threadIdx.x] = 0;
-  const uint32_t b = t * RS_CHUNK;
-  if (t < T) {
-    const uint32_t e = min(b + RS_CHUNK, n);
-    for (uint32_t i = b; i < e; i++) cnt[key_byte(keys, idx[i], byte)][threadIdx.x]++;
+// hist[d * nblocks + b]
+__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const Fr* __restrict__ keys, const uint32_t* __restrict__ idx, uint32_t n,
+                                                        uint32_t byte, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t base = blockIdx.x * RS_TILE;
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; r++) {
+    uint32_t i = base + r * RS_THREADS + threadIdx.x;
+    if (i < n) atomicAdd(&h[key_byte(keys, idx[i], byte)], 1u);
   }
   __syncthreads();
-  if (t < T)
-    for (int d = 0; d < 256; d++) hist[(size_t)d * T + t] = cnt[d][threadIdx.x];
+  hist[threadIdx.x * gridDim.x + blockIdx.x] = h[threadIdx.x];
 }
+// stable scatter: position = offs[d][block] + (same-digit items earlier in this CTA)
 __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const Fr* __restrict__ keys, const uint32_t* __restrict__ idx_in, uint32_t n,
-                                                           uint32_t byte, uint32_t T, const uint32_t* __restrict__ offs,
+                                                           uint32_t byte, const uint32_t* __restrict__ offs,
                                                            uint32_t* __restrict__ idx_out) {
-  __shared__ uint32_t pos[256][RS_THREADS];
-  const uint32_t t = blockIdx.x * RS_THREADS + threadIdx.x;
-  if (t >= T) return;
-  for (int d = 0; d < 256; d++) pos[d][threadIdx.x] = offs[(size_t)d * T + t];
-  const uint32_t b = t * RS_CHUNK, e = min(b + RS_CHUNK, n);
-  for (uint32_t i = b; i < e; i++) {
-    uint32_t id = idx_in[i];
-    uint32_t d = key_byte(keys, id, byte);
-    idx_out[pos[d][threadIdx.x]++] = id;
+  __shared__ uint32_t cnt[RS_THREADS / 32][256];   // per-warp digit counts of the current round
+  __shared__ uint32_t base_d[256];                 // running start of digit d for this CTA
+  const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  base_d[tid] = offs[tid * gridDim.x + blockIdx.x];
+  const uint32_t base = blockIdx.x * RS_TILE;
+  for (int r = 0; r < RS_ITEMS; r++) {
+    for (int d = lane; d < 256; d += 32) cnt[wid][d] = 0;
+    __syncwarp();
+    const uint32_t i = base + r * RS_THREADS + tid;
+    const bool valid = i < n;
+    uint32_t id = 0, d = 0xffffffffu;
+    if (valid) {
+      id = idx_in[i];
+      d = key_byte(keys, id, byte);
+    }
+    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    const uint32_t rank_in_warp = __popc(peers & ((1u << lane) - 1));
+    if (valid && rank_in_warp == 0) cnt[wid][d] = __popc(peers);
+    __syncthreads();
+    // thread `tid` owns digit `tid`: exclusive prefix over the warps, then advance the CTA base
+    {
+      uint32_t run = base_d[tid];
+#pragma unroll
+      for (int w = 0; w < RS_THREADS / 32; w++) {
+        uint32_t c = cnt[w][tid];
+        cnt[w][tid] = run;
+        run += c;
+      }
+      base_d[tid] = run;
+    }
+    __syncthreads();
+    if (valid) idx_out[cnt[wid][d] + rank_in_warp] = id;
+    __syncthreads();
   }
 }
 
@@ -138,16 +209,20 @@ __global__ void k_check_unique(const Fr* __restrict__ keys, const uint32_t* __re
   flag[i] = c != 0;
   if (c > 0) atomicOr(unsorted, 1u);
 }
-// U[upos[i]] = key, ustart[upos[i]] = i at unique positions
+// U[upos[i]] = key, ustart[upos[i]] = i at unique positions; ustart[D] = n; *D_out = D
 __global__ void k_collect_unique(const Fr* __restrict__ keys, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ flag,
-                                 const uint32_t* __restrict__ upos, uint32_t n, Fr* __restrict__ U, uint32_t* __restrict__ ustart) {
+                                 const uint32_t* __restrict__ upos, uint32_t n, Fr* __restrict__ U, uint32_t* __restrict__ ustart,
+                                 uint32_t* __restrict__ D_out) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   if (flag[i]) {
     stf(U + upos[i], ldf(keys + idx[i]));
     ustart[upos[i]] = i;
   }
-  if (i == 0) ustart[upos[n]] = n;
+  if (i == 0) {
+    ustart[upos[n]] = n;
+    *D_out = upos[n];
+  }
 }
 
 __device__ __forceinline__ int find_rank(const Fr* U, uint32_t D, const Fr& a) {
@@ -160,11 +235,12 @@ __device__ __forceinline__ int find_rank(const Fr* U, uint32_t D, const Fr& a) {
   if (lo < D && cmp256(ldf(U + lo), a) == 0) return (int)lo;
   return -1;
 }
-__global__ void k_rank_inputs(const Fr* __restrict__ A, uint32_t n, const Fr* __restrict__ U, const uint32_t* __restrict__ Dptr,
+// rank[i] of input i in U (Montgomery input converted on the fly) and the input histogram
+__global__ void k_rank_inputs(const Fr* __restrict__ a_mont, uint32_t n, const Fr* __restrict__ U, const uint32_t* __restrict__ Dptr,
                               uint32_t* __restrict__ rank, uint32_t* __restrict__ cntA, uint32_t* __restrict__ err) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  int r = find_rank(U, *Dptr, ldf(A + i));
+  int r = find_rank(U, *Dptr, fp_from_mont(ldf(a_mont + i)));
   if (r < 0) {
     atomicOr(err, 1u);
     rank[i] = 0xffffffffu;
@@ -199,18 +275,17 @@ __global__ void k_place(const uint32_t* __restrict__ rank, uint32_t n, const Fr*
   const uint32_t D = *Dptr;
   uint32_t k = atomicAdd(&cursorA[r], 1u);
   uint32_t slot = startA[r] + k;
-  Fr val = ldf(U + r);
-  stf(pa + slot, fp_to_mont(val));
+  Fr val = fp_to_mont(ldf(U + r));
+  stf(pa + slot, val);
   if (k == 0) {
-    stf(ps + slot, fp_to_mont(val));
+    stf(ps + slot, val);
     return;
   }
   const uint32_t distinct_total = dcount_excl[D];
   const uint32_t R = n - distinct_total;
   const uint32_t rr = slot - dcount_excl[r + 1];       // first-occurrence rows at or before `slot`
   const uint32_t j = R - 1 - rr;
-  // last r2 with lstart[r2] <= j
-  uint32_t lo = 0, hi = D;
+  uint32_t lo = 0, hi = D;                              // last r2 with lstart[r2] <= j
   while (hi - lo > 1) {
     uint32_t mid = (lo + hi) >> 1;
     if (lstart[mid] <= j) lo = mid; else hi = mid;
@@ -222,65 +297,83 @@ inline uint32_t nb(uint32_t n, uint32_t t = 256) { return (n + t - 1) / t; }
 
 }  // namespace
 
-size_t lookup_workspace_bytes(uint32_t n) {
-  size_t T = (n + RS_CHUNK - 1) / RS_CHUNK;
-  size_t words = 0;
-  words += 2 * (size_t)n;              // idx ping-pong
-  words += 2 * 256 * T + 2;            // hist, offs
-  words += 9 * ((size_t)n + 8);        // flag, upos, ustart, rank, cntA, startA, cursorA, first/left reuse, lstart, dcount
-  return words * 4 + 3 * (size_t)n * sizeof(Fr) + 4096;
+size_t lookup_table_bytes(uint32_t n) { return (size_t)(n + 8) * sizeof(Fr) + (size_t)(n + 16) * 4; }
+
+LookupTable lookup_table_carve(uint8_t* mem, uint32_t n) {
+  LookupTable t;
+  t.U = (Fr*)mem;
+  t.ustart = (uint32_t*)(t.U + (n + 8));
+  t.D = t.ustart + (n + 8);
+  return t;
 }
 
-int lookup_permute(const Fr* a_mont, const Fr* s_mont, uint32_t usable, Fr* pa, Fr* ps, uint8_t* ws, uint32_t* status_dev,
-                   bool full_sort, cudaStream_t st, LaunchCounter lc) {
+size_t lookup_workspace_bytes(uint32_t n) {
+  size_t nblocks = (n + RS_TILE - 1) / RS_TILE;
+  size_t words = 2 * (size_t)n + 2 * (256 * nblocks + 8) + 9 * ((size_t)n + 8);
+  return words * 4 + (size_t)n * sizeof(Fr) + lookup_table_bytes(n) + 4096;
+}
+
+LookupTable lookup_workspace_table(uint8_t* ws, uint32_t n) {
+  // the scratch table lives at the end of the workspace
+  size_t nblocks = (n + RS_TILE - 1) / RS_TILE;
+  size_t words = 2 * (size_t)n + 2 * (256 * nblocks + 8) + 9 * ((size_t)n + 8);
+  size_t off = (words * 4 + (size_t)n * sizeof(Fr) + 255) & ~(size_t)255;
+  return lookup_table_carve(ws + off, n);
+}
+
+int lookup_sort_table(const Fr* s_mont, uint32_t usable, const LookupTable& out, uint8_t* ws, uint32_t* unsorted_flag_dev,
+                      bool full_sort, cudaStream_t st, LaunchCounter lc) {
   const uint32_t n = usable;
-  const uint32_t T = (n + RS_CHUNK - 1) / RS_CHUNK;
-  // carve the workspace
-  Fr* Acan = (Fr*)ws;
-  Fr* Tcan = Acan + n;
-  Fr* U = Tcan + n;
-  uint32_t* w = (uint32_t*)(U + n);
+  const uint32_t nblocks = (n + RS_TILE - 1) / RS_TILE;
+  Fr* Tcan = (Fr*)ws;
+  uint32_t* w = (uint32_t*)(Tcan + n);
   uint32_t* idx0 = w; w += n;
   uint32_t* idx1 = w; w += n;
-  uint32_t* hist = w; w += 256 * (size_t)T + 1;
-  uint32_t* offs = w; w += 256 * (size_t)T + 1;
+  uint32_t* hist = w; w += 256 * (size_t)nblocks + 8;
+  uint32_t* offs = w; w += 256 * (size_t)nblocks + 8;
   uint32_t* flag = w; w += n + 8;
   uint32_t* upos = w; w += n + 8;
-  uint32_t* ustart = w; w += n + 8;
+  k_canonical_iota<<<nb(n), 256, 0, st>>>(s_mont, Tcan, idx0, n); lc++;
+  uint32_t* in = idx0;
+  uint32_t* o = idx1;
+  for (uint32_t byte = full_sort ? 0 : 24; byte < 32; byte++) {
+    k_rs_hist<<<nblocks, RS_THREADS, 0, st>>>(Tcan, in, n, byte, hist); lc++;
+    k_scan_excl_u32<<<1, 1024, 0, st>>>(hist, 256 * nblocks, offs); lc++;
+    k_rs_scatter<<<nblocks, RS_THREADS, 0, st>>>(Tcan, in, n, byte, offs, o); lc++;
+    uint32_t* tmp = in; in = o; o = tmp;
+  }
+  k_check_unique<<<nb(n), 256, 0, st>>>(Tcan, in, n, flag, unsorted_flag_dev); lc++;
+  k_scan_excl_u32<<<1, 1024, 0, st>>>(flag, n, upos); lc++;
+  k_collect_unique<<<nb(n), 256, 0, st>>>(Tcan, in, flag, upos, n, out.U, out.ustart, out.D); lc++;
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int lookup_permute(const Fr* a_mont, uint32_t usable, const LookupTable& tab, Fr* pa, Fr* ps, uint8_t* ws, uint32_t* missing_flag_dev,
+                   cudaStream_t st, LaunchCounter lc) {
+  const uint32_t n = usable;
+  const uint32_t nblocks = (n + RS_TILE - 1) / RS_TILE;
+  // bookkeeping arrays sit after the sort's own arrays (which are dead by now or unused for cached tables)
+  uint32_t* w = (uint32_t*)((Fr*)ws + n);
+  w += 2 * (size_t)n + 2 * (256 * (size_t)nblocks + 8) + 2 * ((size_t)n + 8);
   uint32_t* rank = w; w += n + 8;
-  uint32_t* cntA = w; w += n + 8;
-  uint32_t* startA = w; w += n + 8;
+  uint32_t* cntA = w; w += n + 8;        // cntA | cursorA contiguous: one memset
   uint32_t* cursorA = w; w += n + 8;
+  uint32_t* startA = w; w += n + 8;
   uint32_t* first = w; w += n + 8;
   uint32_t* left = w; w += n + 8;
-  // lstart / dcount reuse hist / offs (dead after the sort): both hold >= n + 1 words when T >= 1
-  uint32_t* lstart = hist;
-  uint32_t* dcount = offs;
-
-  k_canonical<<<nb(n), 256, 0, st>>>(a_mont, Acan, n); lc++;
-  k_canonical<<<nb(n), 256, 0, st>>>(s_mont, Tcan, n); lc++;
-  k_iota<<<nb(n), 256, 0, st>>>(idx0, n); lc++;
-  uint32_t* in = idx0;
-  uint32_t* out = idx1;
-  for (uint32_t byte = full_sort ? 0 : 24; byte < 32; byte++) {
-    k_rs_count<<<nb(T, RS_THREADS), RS_THREADS, 0, st>>>(Tcan, in, n, byte, T, hist); lc++;
-    k_scan_excl_u32<<<1, 1024, 0, st>>>(hist, 256 * T, offs); lc++;
-    k_rs_scatter<<<nb(T, RS_THREADS), RS_THREADS, 0, st>>>(Tcan, in, n, byte, T, offs, out); lc++;
-    uint32_t* tmp = in; in = out; out = tmp;
-  }
-  // status_dev[0] = unsorted flag (top-64-bit sort insufficient), status_dev[1] = input not in table
-  k_check_unique<<<nb(n), 256, 0, st>>>(Tcan, in, n, flag, status_dev); lc++;
-  k_scan_excl_u32<<<1, 1024, 0, st>>>(flag, n, upos); lc++;
-  k_collect_unique<<<nb(n), 256, 0, st>>>(Tcan, in, flag, upos, n, U, ustart); lc++;
-  const uint32_t* Dptr = upos + n;   // number of distinct table values
-  cudaMemsetAsync(cntA, 0, (size_t)(n + 8) * 4, st);
-  cudaMemsetAsync(cursorA, 0, (size_t)(n + 8) * 4, st);
-  k_rank_inputs<<<nb(n), 256, 0, st>>>(Acan, n, U, Dptr, rank, cntA, status_dev + 1); lc++;
-  k_scan_excl_u32<<<1, 1024, 0, st>>>(cntA, n, startA); lc++;
-  k_first_left<<<nb(n), 256, 0, st>>>(cntA, ustart, Dptr, n, first, left); lc++;
-  k_scan_excl_u32<<<1, 1024, 0, st>>>(left, n, lstart); lc++;
-  k_scan_excl_u32<<<1, 1024, 0, st>>>(first, n, dcount); lc++;
-  k_place<<<nb(n), 256, 0, st>>>(rank, n, U, Dptr, startA, cursorA, dcount, lstart, pa, ps); lc++;
+  uint32_t* lstart = w; w += n + 8;
+  // dcount reuses the first index buffer of the sort
+  uint32_t* dcount = (uint32_t*)((Fr*)ws + n);
+  cudaMemsetAsync(cntA, 0, (size_t)2 * (n + 8) * 4, st);
+  k_rank_inputs<<<nb(n), 256, 0, st>>>(a_mont, n, tab.U, tab.D, rank, cntA, missing_flag_dev); lc++;
+  k_first_left<<<nb(n), 256, 0, st>>>(cntA, tab.ustart, tab.D, n, first, left); lc++;
+  Scan3 S;
+  S.in[0] = cntA; S.out[0] = startA;
+  S.in[1] = left; S.out[1] = lstart;
+  S.in[2] = first; S.out[2] = dcount;
+  S.n = n;
+  k_scan3<<<3, 1024, 0, st>>>(S); lc++;
+  k_place<<<nb(n), 256, 0, st>>>(rank, n, tab.U, tab.D, startA, cursorA, dcount, lstart, pa, ps); lc++;
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

@@ -32,18 +32,6 @@ __device__ __forceinline__ void ld_fq2(const G1Affine* p, Fq& x, Fq& y) {
   y.v[4] = d.x; y.v[5] = d.y; y.v[6] = d.z; y.v[7] = d.w;
 }
 
-__device__ __forceinline__ G1Xyzz shfl_down_xyzz(const G1Xyzz& p, int d) {
-  G1Xyzz r;
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    r.x.v[i] = __shfl_down_sync(0xffffffffu, p.x.v[i], d);
-    r.y.v[i] = __shfl_down_sync(0xffffffffu, p.y.v[i], d);
-    r.zz.v[i] = __shfl_down_sync(0xffffffffu, p.zz.v[i], d);
-    r.zzz.v[i] = __shfl_down_sync(0xffffffffu, p.zzz.v[i], d);
-  }
-  return r;
-}
-
 // ---- window-table precompute (one-time, at SRS load) -----------------------------------
 __global__ void msm_precompute_kernel(const G1Affine* __restrict__ base, G1Affine* __restrict__ table,
                                       uint32_t n, uint32_t c, uint32_t W) {
@@ -231,155 +219,12 @@ __global__ void __launch_bounds__(128) msm_serial_reduce_kernel(
   }
 }
 
-// ---- warp-shuffle segmented reduction (small lists) ------------------------------------
-// One entry per lane.  After 5 shuffle steps the head lane of every run holds the run's sum
-// inside this warp.  Runs touching the warp's edges go to slots 2g / 2g+1 of the next level;
-// interior runs (and every run when `final_level`) are written to their bucket.
-__global__ void __launch_bounds__(128) msm_warp_reduce_kernel(
-    const uint32_t* __restrict__ keys, const G1Xyzz* __restrict__ pts, uint32_t n_in,
-    G1Xyzz* __restrict__ buckets, uint32_t* __restrict__ pkeys, G1Xyzz* __restrict__ ppts,
-    uint32_t nwarps, int final_level) {
-  const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t lane = threadIdx.x & 31;
-  if (g >= nwarps) return;  // whole warps only: blockDim is a multiple of 32
-  const uint32_t e = g * 32 + lane;
-  uint32_t key = (e < n_in) ? keys[e] : MSM_INVALID_KEY;
-  G1Xyzz acc = (key != MSM_INVALID_KEY) ? pts[e] : xyzz_identity();
-#pragma unroll 1
-  for (int d = 1; d < 32; d <<= 1) {
-    G1Xyzz other = shfl_down_xyzz(acc, d);
-    uint32_t okey = __shfl_down_sync(0xffffffffu, key, d);
-    if (lane + d < 32 && okey == key && key != MSM_INVALID_KEY) xyzz_add(acc, other);
-  }
-  uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
-  uint32_t last_key = __shfl_sync(0xffffffffu, key, 31);
-  const bool head = (lane == 0) || (prev != key);
-  if (final_level) {
-    if (head && key != MSM_INVALID_KEY) buckets[key] = acc;
-    return;
-  }
-  if (key == MSM_INVALID_KEY) {
-    if (lane == 0) pkeys[2 * g] = MSM_INVALID_KEY;
-    if (lane == 31) pkeys[2 * g + 1] = MSM_INVALID_KEY;
-    return;
-  }
-  if (!head) return;
-  const bool touch_end = (last_key == key);
-  if (lane == 0) {
-    pkeys[2 * g] = key;
-    ppts[2 * g] = acc;
-    if (touch_end) {
-      pkeys[2 * g + 1] = key;
-      ppts[2 * g + 1] = xyzz_identity();
-    }
-  } else if (touch_end) {
-    pkeys[2 * g + 1] = key;
-    ppts[2 * g + 1] = acc;
-  } else {
-    buckets[key] = acc;
-  }
-}
-
-// ---- weighted bucket sum ---------------------------------------------------------------
-// lanes hold X_l; returns in lane 0: s = sum X_l and t = sum l * X_l (suffix scan + tree sum).
-__device__ __forceinline__ void warp_weighted(G1Xyzz x, uint32_t lane, G1Xyzz& s, G1Xyzz& t) {
-#pragma unroll 1
-  for (int d = 1; d < 32; d <<= 1) {
-    G1Xyzz o = shfl_down_xyzz(x, d);
-    if (lane + d < 32) xyzz_add(x, o);
-  }
-  s = x;  // lane 0: total
-  G1Xyzz y = (lane >= 1) ? x : xyzz_identity();
-#pragma unroll 1
-  for (int d = 16; d >= 1; d >>= 1) {
-    G1Xyzz o = shfl_down_xyzz(y, d);
-    if (lane < (uint32_t)d) xyzz_add(y, o);
-  }
-  t = y;
-}
-__device__ __forceinline__ G1Xyzz warp_sum(G1Xyzz y, uint32_t lane) {
-#pragma unroll 1
-  for (int d = 16; d >= 1; d >>= 1) {
-    G1Xyzz o = shfl_down_xyzz(y, d);
-    if (lane < (uint32_t)d) xyzz_add(y, o);
-  }
-  return y;
-}
-
-// level 1: warp g of MSM m reduces buckets [32g, 32g+32) to (s1, t1)
-__global__ void __launch_bounds__(128) msm_bucket_l1_kernel(const G1Xyzz* __restrict__ buckets, uint32_t NB,
-                                                            uint32_t n1, G1Xyzz* __restrict__ s1,
-                                                            G1Xyzz* __restrict__ t1) {
-  const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t m = blockIdx.y;
-  if (g >= n1) return;
-  uint32_t b = g * 32 + lane;
-  G1Xyzz x = (b < NB) ? buckets[(size_t)m * NB + b] : xyzz_identity();
-  G1Xyzz s, t;
-  warp_weighted(x, lane, s, t);
-  if (lane == 0) {
-    s1[(size_t)m * n1 + g] = s;
-    t1[(size_t)m * n1 + g] = t;
-  }
-}
-
-__device__ __forceinline__ G1Xyzz xyzz_mul32(G1Xyzz p) {
-  for (int i = 0; i < 5; i++) p = xyzz_double(p);
-  return p;
-}
-
-// level 2: warp w of MSM m folds s1[32w..32w+32) -> (S2, T2) and sums t1[32w..32w+32) -> U
-__global__ void __launch_bounds__(32) msm_bucket_l2_kernel(const G1Xyzz* __restrict__ s1,
-                                                           const G1Xyzz* __restrict__ t1, uint32_t n1,
-                                                           G1Xyzz* __restrict__ l2out) {
-  const uint32_t w = blockIdx.x, m = blockIdx.y, lane = threadIdx.x;
-  const uint32_t nw = gridDim.x;
-  uint32_t i = w * 32 + lane;
-  G1Xyzz x = (i < n1) ? s1[(size_t)m * n1 + i] : xyzz_identity();
-  G1Xyzz tt = (i < n1) ? t1[(size_t)m * n1 + i] : xyzz_identity();
-  G1Xyzz s, t;
-  warp_weighted(x, lane, s, t);
-  G1Xyzz u = warp_sum(tt, lane);
-  if (lane == 0) {
-    G1Xyzz* o = l2out + (size_t)m * 3 * nw;
-    o[w] = s;
-    o[nw + w] = t;
-    o[2 * nw + w] = u;
-  }
-}
-
-// finish: one 3-warp CTA per MSM folds the nw <= 32 (S2, T2, U) triples:
-//   W(X) = sum U + 32 * ( sum T2 + 32 * t3 ),  result = W + S   (bucket `key` has weight key+1)
-__global__ void __launch_bounds__(96) msm_finish_kernel(const G1Xyzz* __restrict__ l2out, uint32_t nw,
-                                                        G1Jac* __restrict__ out) {
-  __shared__ G1Xyzz fin[4];
-  const uint32_t m = blockIdx.x;
-  const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const G1Xyzz* o = l2out + (size_t)m * 3 * nw;
-  if (wid == 0) {
-    G1Xyzz x = (lane < nw) ? o[lane] : xyzz_identity();
-    G1Xyzz s, t;
-    warp_weighted(x, lane, s, t);
-    if (lane == 0) {
-      fin[0] = s;  // S: sum of all buckets
-      fin[1] = t;  // t3
-    }
-  } else {
-    G1Xyzz x = (lane < nw) ? o[wid * nw + lane] : xyzz_identity();
-    x = warp_sum(x, lane);
-    if (lane == 0) fin[1 + wid] = x;  // fin[2] = sum T2, fin[3] = sum U
-  }
-  __syncthreads();
-  if (tid == 0) {
-    G1Xyzz r = xyzz_mul32(fin[1]);
-    xyzz_add(r, fin[2]);
-    r = xyzz_mul32(r);
-    xyzz_add(r, fin[3]);
-    xyzz_add(r, fin[0]);
-    out[m] = xyzz_to_jacobian(r);
-  }
-}
+void msm_tail_serial_level(const uint32_t* keys, const G1Xyzz* pts, uint32_t slots, G1Xyzz* buckets, uint32_t* pkeys_out,
+                           G1Xyzz* ppts_out, uint32_t T1, cudaStream_t st);
+void msm_tail_warp_level(const uint32_t* keys, const G1Xyzz* pts, uint32_t slots, G1Xyzz* buckets, uint32_t* pkeys_out,
+                         G1Xyzz* ppts_out, uint32_t nwarps, int fin, cudaStream_t st);
+void msm_tail_buckets(const G1Xyzz* buckets, uint32_t NB, uint32_t M, G1Xyzz* s1, G1Xyzz* t1, G1Xyzz* l2out, G1Jac* out,
+                      cudaStream_t st);
 
 // ---- host side ---------------------------------------------------------------------------
 uint32_t msm_pick_c(uint32_t k) {
@@ -469,8 +314,7 @@ cudaError_t msm_run(const MsmTable& tb, const Fr* scalars, size_t stride, uint32
   if (slots > 8192) {
     uint32_t T1 = (slots + 15) / 16;
     launches++;
-    msm_serial_reduce_kernel<false><<<(T1 + 127) / 128, 128, 0, st>>>(
-        pk[0], nullptr, pp[0], nullptr, slots, nullptr, 16, buckets, pk[1], pp[1], T1);
+    msm_tail_serial_level(pk[0], pp[0], slots, buckets, pk[1], pp[1], T1, st);
     slots = 2 * T1;
     cur = 1;
   }
@@ -478,22 +322,14 @@ cudaError_t msm_run(const MsmTable& tb, const Fr* scalars, size_t stride, uint32
     uint32_t nwarps = (slots + 31) / 32;
     int fin = nwarps == 1;
     launches++;
-    msm_warp_reduce_kernel<<<(nwarps + 3) / 4, 128, 0, st>>>(pk[cur], pp[cur], slots, buckets,
-                                                            pk[cur ^ 1], pp[cur ^ 1], nwarps, fin);
+    msm_tail_warp_level(pk[cur], pp[cur], slots, buckets, pk[cur ^ 1], pp[cur ^ 1], nwarps, fin, st);
     if (fin) break;
     slots = 2 * nwarps;
     cur ^= 1;
   }
-  uint32_t n1 = (NB + 31) / 32;
-  dim3 g1((n1 + 3) / 4, M);
-  launches++;
-  msm_bucket_l1_kernel<<<g1, 128, 0, st>>>(buckets, NB, n1, s1, t1);
-  uint32_t nw = (n1 + 31) / 32;
   G1Xyzz* l2out = (G1Xyzz*)(ws + l.off_l2);
-  launches++;
-  msm_bucket_l2_kernel<<<dim3(nw, M), 32, 0, st>>>(s1, t1, n1, l2out);
-  launches++;
-  msm_finish_kernel<<<M, 96, 0, st>>>(l2out, nw, out);
+  launches += 3;
+  msm_tail_buckets(buckets, NB, M, s1, t1, l2out, out, st);
   if (nl) *nl += launches;
   return cudaGetLastError();
 }

@@ -200,6 +200,9 @@ struct zg_pk {
   uint32_t* d_pidx;
   uint32_t* d_status;
   uint8_t* lookup_ws;
+  uint8_t* table_cache;
+  size_t table_cache_stride = 0;
+  std::vector<char> table_cached;
   uint64_t* rnd_words_dev;
   uint64_t* rnd_words_host = nullptr;  // pinned
   size_t n_draws = 0;
@@ -331,6 +334,7 @@ int zg_pk_load(zg_ctx* ctx, const zg_pk_desc* d, zg_pk** out) {
   pk->omega_inv = fp_inv(pk->omega);
   pk->delta = fr_delta();
   memcpy(pk->transcript_repr.v, &d->transcript_repr, 32);
+  pk->table_cached.assign(pk->n_lookups, 0);
   if (pk->n < pk->bf + 3) return ctx->fail(ZG_E_INVALID, "pk_load: not enough rows");
   const size_t n = pk->n, N = pk->N;
   const uint32_t A = pk->A, F = pk->F, I = pk->I, m = pk->m, Lk = pk->n_lookups, S = pk->nsets;
@@ -379,6 +383,8 @@ int zg_pk_load(zg_ctx* ctx, const zg_pk_desc* d, zg_pk** out) {
     pk->d_polyptrs = b.take<const Fr*>(n_queries + 8); pk->d_pidx = b.take<uint32_t>(n_queries + 8);
     pk->d_status = b.take<uint32_t>(64);
     pk->lookup_ws = b.take<uint8_t>(lookup_workspace_bytes(pk->usable));
+    pk->table_cache_stride = (lookup_table_bytes(pk->usable) + 255) & ~(size_t)255;
+    pk->table_cache = b.take<uint8_t>(pk->table_cache_stride * (Lk + 1));
     pk->rnd_words_dev = b.take<uint64_t>(8 * pk->n_draws);
     if (!pass) {
       cudaError_t e = cudaMalloc(&pk->arena, b.off);
@@ -555,7 +561,7 @@ int zg_create_proof(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice, const zg
   }
   // ---- 2. advice: upload, blind, commit ----------------------------------------------------------------------
   for (uint32_t c = 0; c < A; c++)
-    ZG_CUDA(cudaMemcpyAsync(pk->adv_values + c * n, advice[c], sizeof(Fr) * usable, cudaMemcpyHostToDevice, st));
+    ZG_CUDA(cudaMemcpyAsync(pk->adv_values + c * n, advice[c], sizeof(Fr) * usable, cudaMemcpyDefault, st));  // host or device
   for (uint32_t c = 0; c < A; c++) ZG_CUDA(blind_rows(pk->adv_values + c * n, usable, bf + 1));
   draw += A;  // one Blind(Fr::random) per column, unused by KZG
   {
@@ -594,42 +600,59 @@ int zg_create_proof(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice, const zg
   LookupProgs lp{pk->prog_off, pk->d_in_first, pk->d_in_count, pk->d_tab_first, pk->d_tab_count};
   if (Lk) {
     expr_compress_lookups(base_env, lp, Lk, theta, pk->ci, pk->ct, n, st, lc);
-    ZG_CUDA(cudaMemsetAsync(pk->d_status, 0, 4 * 2 * Lk, st));
-    for (uint32_t l = 0; l < Lk; l++)
-      if (lookup_permute(pk->ci + l * n, pk->ct + l * n, usable, pk->pa + l * n, pk->ps + l * n, pk->lookup_ws, pk->d_status + 2 * l,
-                         false, st, lc))
-        return ctx->cuda_fail(cudaGetLastError(), "lookup_permute");
-    std::vector<uint32_t> status(2 * Lk);
-    ZG_CUDA(cudaMemcpyAsync(status.data(), pk->d_status, 4 * 2 * Lk, cudaMemcpyDeviceToHost, st));
-    ZG_CUDA(cudaStreamSynchronize(st));
-    for (uint32_t l = 0; l < Lk; l++) {
-      if (status[2 * l]) {  // top-64-bit sort left ties out of order: redo this lookup with the full 256-bit sort
-        ZG_CUDA(cudaMemsetAsync(pk->d_status + 2 * l, 0, 8, st));
-        if (lookup_permute(pk->ci + l * n, pk->ct + l * n, usable, pk->pa + l * n, pk->ps + l * n, pk->lookup_ws,
-                           pk->d_status + 2 * l, true, st, lc))
+    // Tables with a single expression do not depend on theta: sorted once per proving key (full 256-bit
+    // sort) and cached.  The others are sorted per proof on their top 64 bits; the device flags the rare
+    // case where that left distinct keys out of order and the round is redone with the full sort.
+    const size_t draw_mark = draw;
+    std::vector<char> full(Lk, 0);
+    std::vector<Affine> aff(2 * Lk);
+    for (int attempt = 0;; attempt++) {
+      draw = draw_mark;
+      ZG_CUDA(cudaMemsetAsync(pk->d_status, 0, 4 * 2 * Lk, st));
+      for (uint32_t l = 0; l < Lk; l++) {
+        LookupTable tab;
+        if (pk->tab_count[l] == 1) {
+          tab = lookup_table_carve(pk->table_cache + (size_t)l * pk->table_cache_stride, usable);
+          if (!pk->table_cached[l]) {
+            if (lookup_sort_table(pk->ct + l * n, usable, tab, pk->lookup_ws, pk->d_status + 2 * l, true, st, lc))
+              return ctx->cuda_fail(cudaGetLastError(), "lookup_sort_table");
+            pk->table_cached[l] = 1;
+          }
+        } else {
+          tab = lookup_workspace_table(pk->lookup_ws, usable);
+          if (lookup_sort_table(pk->ct + l * n, usable, tab, pk->lookup_ws, pk->d_status + 2 * l, full[l] != 0, st, lc))
+            return ctx->cuda_fail(cudaGetLastError(), "lookup_sort_table");
+        }
+        if (lookup_permute(pk->ci + l * n, usable, tab, pk->pa + l * n, pk->ps + l * n, pk->lookup_ws, pk->d_status + 2 * l + 1, st, lc))
           return ctx->cuda_fail(cudaGetLastError(), "lookup_permute");
-        ZG_CUDA(cudaMemcpyAsync(status.data() + 2 * l, pk->d_status + 2 * l, 8, cudaMemcpyDeviceToHost, st));
-        ZG_CUDA(cudaStreamSynchronize(st));
       }
-      if (status[2 * l + 1]) return ctx->fail(ZG_E_SYNTH, "create_proof: lookup input not in table (ConstraintSystemFailure)");
-    }
-    // blinding rows: per lookup input rows, table rows, then two blinds
-    for (uint32_t l = 0; l < Lk; l++) {
-      ZG_CUDA(blind_rows(pk->pa + l * n, usable, bf + 1));
-      ZG_CUDA(blind_rows(pk->ps + l * n, usable, bf + 1));
-      draw += 2;
+      // blinding rows: per lookup input rows, table rows, then two blinds
+      for (uint32_t l = 0; l < Lk; l++) {
+        ZG_CUDA(blind_rows(pk->pa + l * n, usable, bf + 1));
+        ZG_CUDA(blind_rows(pk->ps + l * n, usable, bf + 1));
+        draw += 2;
+      }
+      rc = zg_msm_dev(ctx, ZG_BASIS_LAGRANGE, (const zg_fr*)pk->pa, n, n, 2 * Lk, (zg_g1*)ctx->d_msm_out);
+      if (rc) return rc;
+      std::vector<G1Jac> jac(2 * Lk);
+      std::vector<uint32_t> status(2 * Lk);
+      ZG_CUDA(cudaMemcpyAsync(jac.data(), ctx->d_msm_out, sizeof(G1Jac) * 2 * Lk, cudaMemcpyDeviceToHost, st));
+      ZG_CUDA(cudaMemcpyAsync(status.data(), pk->d_status, 4 * 2 * Lk, cudaMemcpyDeviceToHost, st));
+      rc = zg_lagrange_to_coeff_dev(ctx, (const zg_fr*)pk->pa, (zg_fr*)pk->pa_poly, pk->k, 2 * Lk, n);
+      if (rc) return rc;
+      ZG_CUDA(cudaEventRecord(ev[2], st));
+      ZG_CUDA(cudaStreamSynchronize(st));
+      bool retry = false;
+      for (uint32_t l = 0; l < Lk; l++) {
+        if (status[2 * l] && !full[l] && pk->tab_count[l] != 1) { full[l] = 1; retry = true; }
+      }
+      if (retry && attempt == 0) continue;
+      for (uint32_t l = 0; l < Lk; l++)
+        if (status[2 * l + 1]) return ctx->fail(ZG_E_SYNTH, "create_proof: lookup input not in table (ConstraintSystemFailure)");
+      batch_normalize(jac.data(), 2 * Lk, aff.data());
+      break;
     }
     // commitments: write order is (input_l, table_l) per lookup
-    std::vector<Affine> aff(2 * Lk);
-    rc = zg_msm_dev(ctx, ZG_BASIS_LAGRANGE, (const zg_fr*)pk->pa, n, n, 2 * Lk, (zg_g1*)ctx->d_msm_out);
-    if (rc) return rc;
-    std::vector<G1Jac> jac(2 * Lk);
-    ZG_CUDA(cudaMemcpyAsync(jac.data(), ctx->d_msm_out, sizeof(G1Jac) * 2 * Lk, cudaMemcpyDeviceToHost, st));
-    rc = zg_lagrange_to_coeff_dev(ctx, (const zg_fr*)pk->pa, (zg_fr*)pk->pa_poly, pk->k, 2 * Lk, n);
-    if (rc) return rc;
-    ZG_CUDA(cudaEventRecord(ev[2], st));
-    ZG_CUDA(cudaStreamSynchronize(st));
-    batch_normalize(jac.data(), 2 * Lk, aff.data());
     for (uint32_t l = 0; l < Lk; l++) {
       if (!tr.write_point(aff[l]) || !tr.write_point(aff[Lk + l]))
         return ctx->fail(ZG_E_SYNTH, "create_proof: lookup commitment is the identity");

@@ -3,13 +3,18 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
 
-Workloads (BASELINE.json metric: "WNN MNIST proofs/sec & proof latency; MSM pts/s, NTT GB/s"):
-  msm   one 2^LOGN-point BN254 G1 MSM per step (uniform scalars)       -> points/s
-  ntt   one 2^LOGN-point BN254 Fr NTT per step                         -> GB/s (algorithmic)
-`value` is timed with inputs resident in HBM (CUDA events on the launching stream, L2 flushed
-between steps); `e2e` goes through the host-pointer C-ABI call (pinned host buffers, H2D and D2H
-inside the timed region).  One process per GPU; N > 1 shards independent work units across ranks
-(weak scaling, no data-path collective), time = max over ranks.
+BASELINE.json metric: "WNN MNIST proofs/sec & proof latency; MSM pts/s, NTT GB/s vs roofline".
+Workloads:
+  proof (default)  one zero_g WNN proof per step: create_proof (KZG/BN254, GWC, EvmTranscript) for
+                   `--model` (default small = BASELINE configs[1], model_28input_1024entry_2hash_2bpi,
+                   k = 15) on benches/example_image_7.png.  Witness synthesis is host work outside the
+                   replaced path (BASELINE north_star) and is done once, untimed, for both arms.
+  msm              one 2^LOGN-point BN254 G1 MSM per step (uniform scalars)      -> points/s
+  ntt              one 2^LOGN-point BN254 Fr NTT per step                        -> GB/s (algorithmic)
+`value` is timed with inputs resident in HBM (CUDA events on the launching stream, L2 flushed between
+steps); `e2e` goes through the host-pointer C-ABI call (pinned host buffers in, result bytes out).
+One process per GPU; N > 1 proves / transforms independent units per rank (weak scaling, no data-path
+collective), time = max over ranks.
 """
 import argparse
 import json
@@ -26,6 +31,15 @@ for p in (os.path.join(ROOT, "0g-halo2_b200"), os.path.join(ROOT, "oracle")):
 
 import numpy as np  # noqa: E402
 
+GOLD = os.path.join(ROOT, "tests", "golden")
+MODELS = {
+    "tiny": ("model_28input_256entry_1hash_1bpi.hdf5", 14),
+    "small": ("model_28input_1024entry_2hash_2bpi.hdf5", 15),
+    "medium": ("model_28input_2048entry_2hash_3bpi.hdf5", 15),
+    "large": (None, 17),          # synthetic same-shape stand-in (the real file is absent upstream)
+}
+SRS_SECRET = 0x1F3C5A7B9D2E4F60718293A4B5C6D7E8
+
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -33,7 +47,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("ZG_BENCH_WORKLOAD", "msm"))
+    ap.add_argument("--workload", default=os.environ.get("ZG_BENCH_WORKLOAD", "proof"))
+    ap.add_argument("--model", default=os.environ.get("ZG_BENCH_MODEL", "small"), choices=list(MODELS))
     ap.add_argument("--logn", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -51,9 +66,7 @@ class ClockSampler:
     """nvidia-smi sampling during the timed region (recipe in B200_PROFILING.md)."""
 
     def __init__(self, index):
-        self.index = index
-        self.rows = []
-        self.proc = None
+        self.index, self.rows, self.proc = index, [], None
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -93,7 +106,7 @@ class ClockSampler:
 
 
 def rand_fr(n, seed):
-    import cpu_ref  # generating synthetic inputs (host side, outside every timed region)
+    import cpu_ref  # synthetic inputs (host side, outside every timed region)
     rng = np.random.default_rng(seed)
     raw = rng.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64)
     raw[:, 3] &= np.uint64((1 << 60) - 1)
@@ -117,20 +130,58 @@ def msm_imad(n, c):
     return ((254 + c - 1) // c) * (10 * n + 2 * (1 << (c - 1)) * 14) * 264
 
 
+def proof_msm_imad(n, k):
+    """30 MSMs per proof at the window the backend uses for 2^k points."""
+    c = max(8, min(16, k - 2))
+    return 30 * msm_imad(n, c), c
+
+
+# ---- the proof workload: model, witness, SRS -----------------------------------------------------------
+def load_model(name):
+    from zg_b200.io import load_wnn, load_grayscale_image, synthetic_wnn
+    fname, k = MODELS[name]
+    wnn = synthetic_wnn() if fname is None else load_wnn(os.path.join(GOLD, fname))
+    img = load_grayscale_image(os.path.join(GOLD, "example_image_7.png"))
+    return wnn, img, k
+
+
+def workload_name(args):
+    if args.workload == "proof":
+        fname, k = MODELS[args.model]
+        return "zero_g proof, %s (k=%d), example_image_7.png" % (fname or "synthetic 49input_8192entry_4hash_6bpi stand-in", k)
+    return "%s 2^%d, BN254, uniform scalars" % (args.workload, args.logn)
+
+
 def run_reference(args, rank, world):
-    """CPU arm: the oracle's restatement of upstream best_multiexp / best_fft on all host cores
-    (the Rust reference cannot be built in this image: kind = "port")."""
+    """CPU arm: the oracle's restatement of the upstream CPU prover (oracle/halo2_ref.py over
+    oracle/zg_oracle.c, OpenMP on all host cores; real best_multiexp commitments).  The Rust reference
+    cannot be built in this image, so kind = "port"."""
     if rank != 0:
         return
     import bn254
     import cpu_ref
-    n = 1 << args.logn
     cores = cpu_ref.num_threads()
-    if args.workload == "msm":
+    if args.workload == "proof":
+        import halo2_ref as H
+        wnn, img, k = load_model(args.model)
+        srs = H.Srs(k, SRS_SECRET)
+        circ0, asm0 = wnn.synthesize(np.zeros(wnn.img_shape(), dtype=np.uint8), k)
+        pk = H.keygen(srs, circ0.cs, asm0)
+        _, asm = wnn.synthesize(img, k)
+        out = wnn.predict(img)
+        seed = [0]
+
+        def fn():
+            seed[0] += 1
+            return H.create_proof(srs, pk, asm.advice, [out], H.XorShiftRng(bytes([seed[0] % 256] * 16)), real_msm=True)
+        metric, unit, units = "proofs_per_s", "proofs/s", 1
+    elif args.workload == "msm":
+        n = 1 << args.logn
         bases, sc = synth_bases(n), rand_fr(n, 7)
         fn = lambda: cpu_ref.best_multiexp(sc, bases)
         metric, unit, units = "msm_points_per_s", "points/s", n
     else:
+        n = 1 << args.logn
         a, w = rand_fr(n, 11), bn254.fr_to_limbs([bn254.omega(args.logn)])
         fn = lambda: cpu_ref.best_fft(a, w, args.logn)
         metric, unit, units = "ntt_algorithmic_gbs", "GB/s", ntt_bytes(args.logn) / 1e9
@@ -143,11 +194,11 @@ def run_reference(args, rank, world):
     v = units / dt
     print(json.dumps({
         "impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u256 (4x64 Montgomery)", "data": "synthetic",
-        "config": {"workload": "%s 2^%d" % (args.workload, args.logn)},
+        "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u256 (4x64-bit Montgomery)", "data": "synthetic",
+        "config": {"workload": workload_name(args)},
         "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": "port",
-                         "sample": "full workload, %d steps" % args.steps},
+                         "sample": "full workload per step, %d steps (witness synthesis excluded)" % args.steps},
         "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -177,21 +228,67 @@ def main():
     hbm_peak, peak_src = peaks()
     logn, n = args.logn, 1 << args.logn
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    cpu_fn = None
+    extra = {}
 
     # ---- set-up (untimed) ----
-    if args.workload == "msm":
+    if args.workload == "proof":
+        import halo2_ref as H                      # test SRS with a known trapdoor + the checker
+        from zg_b200.prover import ParamsKZG, keygen, advice_to_mont, create_proof_limbs
+        from zg_b200.bn254_host import to_limbs
+        wnn, img, k = load_model(args.model)
+        n = 1 << k
+        srs = H.Srs(k, SRS_SECRET)
+        params = ParamsKZG(k, srs.g, srs.g_lagrange)
+        circ0, asm0 = wnn.synthesize(np.zeros(wnn.img_shape(), dtype=np.uint8), k)
+        pk = keygen(ctx, params, circ0.cs, asm0)
+        _, asm = wnn.synthesize(img, k)
+        outputs = wnn.predict(img)
+        adv_host_t = [torch.from_numpy(a.view(np.int64)).pin_memory() for a in advice_to_mont(ctx, asm.advice)]
+        adv_host = [t.numpy().view(np.uint64) for t in adv_host_t]
+        adv_dev_t = [t.cuda() for t in adv_host_t]
+
+        class DevCol:                              # quacks like a numpy column for create_proof_limbs
+            def __init__(self, t):
+                self.t = t
+                self.ctypes = type("c", (), {"data": t.data_ptr()})
+                self.shape = (t.shape[0],)
+        adv_dev = [DevCol(t) for t in adv_dev_t]
+        inst = [to_limbs(list(outputs))]
+        seedc = [rank * 1000]
+
+        def rng():
+            seedc[0] += 1
+            return zg_b200.lib.XorShift.from_seed(int(seedc[0]).to_bytes(16, "little"))
+        step_dev = lambda: create_proof_limbs(pk, adv_dev, inst, rng())
+        step_e2e = lambda: create_proof_limbs(pk, adv_host, inst, rng())
+        # every measured proof is a real proof: check one against the restated verifier (untimed)
+        opk = None
+        if rank == 0:
+            circ_o, asm_o = wnn.synthesize(np.zeros(wnn.img_shape(), dtype=np.uint8), k)
+            opk = H.keygen(srs, circ_o.cs, asm_o)
+            assert pk.fixed_commitments == opk.fixed_commitments and pk.perm_commitments == opk.perm_commitments
+            assert H.verify_proof(srs, opk, [outputs], step_e2e()), "GPU proof rejected by the restated verifier"
+        metric, unit, units = "proofs_per_s", "proofs/s", 1
+        h2d, d2h = len(adv_host) * n * 32 + len(outputs) * 32, 3840
+        dom_kernel = "msm_serial_reduce_kernel<true>"
+        if not args.no_cpu_baseline and rank == 0:
+            cpu_fn = lambda: H.create_proof(srs, opk, asm.advice, [outputs], H.XorShiftRng(bytes(range(16))), real_msm=True)
+    elif args.workload == "msm":
         bases = synth_bases(n)
         ctx.srs_load(logn, bases, None)
         sc_host_t = torch.from_numpy(rand_fr(n, 7 + rank).view(np.int64)).pin_memory()
         sc_host = sc_host_t.numpy().view(np.uint64)
         sc_dev = sc_host_t.cuda()
         out_dev = torch.zeros(12, dtype=torch.int64, device="cuda")
-        c = int(os.environ.get("ZG_MSM_C", "0")) or max(8, min(16, logn - 2))
         step_dev = lambda: ctx.msm_dev(0, sc_dev.data_ptr(), n, n, 1, out_dev.data_ptr())
         step_e2e = lambda: ctx.msm(0, sc_host)
         metric, unit, units = "msm_points_per_s", "points/s", n
         h2d, d2h = n * 32, 96
         dom_kernel = "msm_serial_reduce_kernel<true>"
+        if not args.no_cpu_baseline and rank == 0:
+            import cpu_ref
+            cpu_fn = lambda: cpu_ref.best_multiexp(sc_host, bases)
     elif args.workload == "ntt":
         a_host_t = torch.from_numpy(rand_fr(n, 11 + rank).view(np.int64)).pin_memory()
         a_host = a_host_t.numpy().view(np.uint64)
@@ -203,6 +300,9 @@ def main():
         metric, unit, units = "ntt_algorithmic_gbs", "GB/s", ntt_bytes(logn) / 1e9
         h2d = d2h = n * 32
         dom_kernel = "ntt_pass_kernel"
+        if not args.no_cpu_baseline and rank == 0:
+            import cpu_ref
+            cpu_fn = lambda: cpu_ref.best_fft(a_host, w, logn)
     else:
         raise SystemExit("unknown workload %s" % args.workload)
 
@@ -224,7 +324,8 @@ def main():
             tot += e0.elapsed_time(e1)
         return tot  # ms
 
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step_dev()
     torch.cuda.synchronize()
     l0 = ctx.launch_count
@@ -235,8 +336,8 @@ def main():
     ms = timed(step_dev, args.steps)
     barrier()
     launches = ctx.launch_count - l0
-    # e2e: host buffers through the plain C-ABI call (H2D + compute + D2H), wall-clocked around a
-    # synchronising call
+    stage = pk.stage_ms() if args.workload == "proof" else None
+    # e2e: host buffers through the plain C-ABI call (H2D + compute + D2H of the result)
     for _ in range(2):
         step_e2e()
     barrier()
@@ -260,51 +361,57 @@ def main():
     ms_per_step = ms / args.steps
     value = units * world / (ms_per_step * 1e-3)
     e2e_value = units * world / (e2e_ms / args.steps * 1e-3)
-    # roofline of the dominant kernel
+    # integer-pipe denominators, measured in this run
     imad_peak = ctx.bench_int_pipe(0, 4096)
     imad_wide = ctx.bench_int_pipe(1, 4096)
     mulmod_rate = ctx.bench_int_pipe(2, 256)
     mulmod_ptx_rate = ctx.bench_int_pipe(3, 256)
+    int_pipe = {"imad_gops": imad_peak, "imad_wide_gops": imad_wide, "fr_mulmod_portable_gops": mulmod_rate,
+                "fr_mulmod_ptx_gops": mulmod_ptx_rate}
     if args.workload == "ntt":
         ach = ntt_bytes(logn) / 1e9 / (ms_per_step * 1e-3)
         roof = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                 "traffic": None, "peak_source": peak_src, "kernel": dom_kernel,
                 "note": "254-bit Montgomery butterflies make this kernel integer-pipe bound; see int_pipe"}
-        mulmods = (n // 2) * logn
-    else:
+        int_pipe["kernel_mulmod_gops"] = (n // 2) * logn / 1e9 / (ms_per_step * 1e-3)
+    elif args.workload == "msm":
+        c = int(os.environ.get("ZG_MSM_C", "0")) or max(8, min(16, logn - 2))
         ach = msm_imad(n, c) / 1e9 / (ms_per_step * 1e-3)
         roof = {"bound": "int", "achieved": ach, "peak": imad_peak, "unit": "GIMAD/s", "frac": ach / imad_peak,
                 "traffic": None, "peak_source": "measured in this run (zg_bench_int_pipe kind 0)",
                 "kernel": dom_kernel, "window_c": c}
-        mulmods = None
+    else:
+        imad, c = proof_msm_imad(n, k)
+        # MSM share of the step: stages that are MSM-dominated are reported by the library per proof
+        ach = imad / 1e9 / (ms_per_step * 1e-3)
+        roof = {"bound": "int", "achieved": ach, "peak": imad_peak, "unit": "GIMAD/s", "frac": ach / imad_peak,
+                "traffic": None, "peak_source": "measured in this run (zg_bench_int_pipe kind 0)",
+                "kernel": dom_kernel, "window_c": c,
+                "note": "algorithmic IMAD of the 30 MSMs of one proof / whole-proof time (lower bound on the kernel's own fraction)"}
+        extra["stage_ms_last_proof"] = stage
     out = {
         "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u256 (8x32-bit Montgomery limbs)", "data": "synthetic",
-        "config": {"workload": "%s 2^%d, BN254, uniform scalars" % (args.workload, logn), "l2": "flushed between steps"},
-        "roofline": roof,
-        "int_pipe": {"imad_gops": imad_peak, "imad_wide_gops": imad_wide, "fr_mulmod_portable_gops": mulmod_rate,
-                     "fr_mulmod_ptx_gops": mulmod_ptx_rate},
+        "config": {"workload": workload_name(args), "l2": "flushed between steps",
+                   "synthesis": "host witness synthesis excluded from both arms"},
+        "roofline": roof, "int_pipe": int_pipe,
         "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches), "clocks": clocks,
     }
-    if mulmods:
-        out["int_pipe"]["kernel_mulmod_gops"] = mulmods / 1e9 / (ms_per_step * 1e-3)
-    if not args.no_cpu_baseline:
+    out.update(extra)
+    if cpu_fn is not None:
         import cpu_ref
         cores = cpu_ref.num_threads()
-        if args.workload == "msm":
-            fn = lambda: cpu_ref.best_multiexp(sc_host, bases)
-        else:
-            fn = lambda: cpu_ref.best_fft(a_host, w, logn)
-        fn()
+        cpu_fn()
         reps, t0 = 0, time.perf_counter()
-        while reps < 3 or (time.perf_counter() - t0 < 5 and reps < 20):
-            fn()
+        while reps < 2 or (time.perf_counter() - t0 < 10 and reps < 20):
+            cpu_fn()
             reps += 1
         dt = (time.perf_counter() - t0) / reps
         out["cpu_baseline"] = {"value": units / dt, "unit": unit, "cores": cores, "kind": "port",
-                               "sample": "same workload, %d repetitions on host cores (oracle restatement of upstream)" % reps}
+                               "sample": "same workload, %d repetitions on host cores (oracle restatement of the upstream "
+                                         "CPU prover, OpenMP; witness synthesis excluded)" % reps}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

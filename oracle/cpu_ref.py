@@ -208,3 +208,36 @@ def fr_from_u512(words):
     o = np.zeros((w.shape[0], 4), dtype=np.uint64)
     lib().zgo_fr_from_u512(_p(w), _p(o), ctypes.c_size_t(w.shape[0]))
     return o
+
+
+def xorshift_fr(state: np.ndarray, count: int) -> np.ndarray:
+    """advances the 4 x u32 XorShiftRng state in place; returns `count` Fr::random draws (Montgomery)."""
+    assert state.dtype == np.uint32 and state.shape == (4,)
+    out = np.zeros((count, 4), dtype=np.uint64)
+    lib().zgo_xorshift_fr(_p(state), ctypes.c_size_t(count), _p(out))
+    return out
+
+
+def fr_powers(w, start, n: int) -> np.ndarray:
+    out = np.zeros((n, 4), dtype=np.uint64)
+    lib().zgo_fr_powers(_p(_fr(w)), _p(_fr(start)), _p(out), ctypes.c_size_t(n))
+    return out
+
+
+def permute_expression_pair(a, s, usable: int):
+    a, s = _fr(a), _fr(s)
+    pa = np.zeros((usable, 4), dtype=np.uint64)
+    ps = np.zeros((usable, 4), dtype=np.uint64)
+    lib().zgo_permute_expression_pair.restype = ctypes.c_int
+    rc = lib().zgo_permute_expression_pair(_p(a), _p(s), ctypes.c_size_t(usable), _p(pa), _p(ps))
+    if rc != 0:
+        raise ValueError("ConstraintSystemFailure: lookup input not in table")
+    return pa, ps
+
+
+def g1_fixed_base_mul_many(scalars, gen_affine) -> np.ndarray:
+    scalars = _fr(scalars)
+    out = np.zeros((scalars.shape[0], 8), dtype=np.uint64)
+    lib().zgo_g1_fixed_base_mul_many(_p(scalars), _p(np.ascontiguousarray(gen_affine, dtype=np.uint64)),
+                                     ctypes.c_size_t(scalars.shape[0]), _p(out))
+    return out

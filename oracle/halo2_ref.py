@@ -158,8 +158,12 @@ class XorShiftRng:
         return out
 
     def fr(self, count: int = 1) -> np.ndarray:
-        """`count` draws of Fr::random = from_u512 of eight next_u64 -> (count,4) Montgomery limbs."""
-        return cpu_ref.fr_from_u512(self.words(8 * count))
+        """`count` draws of Fr::random = from_u512 of eight next_u64 -> (count,4) Montgomery limbs
+        (the C oracle runs the same generator; `words` above is the readable definition)."""
+        st = np.array([self.x, self.y, self.z, self.w], dtype=np.uint32)
+        out = cpu_ref.xorshift_fr(st, count)
+        self.x, self.y, self.z, self.w = (int(v) for v in st)
+        return out
 
     def fr_int(self) -> int:
         return I(self.fr(1)[0])
@@ -170,14 +174,14 @@ class Srs:
     def __init__(self, k: int, s: int):
         self.k, self.n, self.s = k, 1 << k, s % R_MOD
         gen = bn254.g1_affine_to_limbs([bn254.G1_GEN])[0]
-        self.g = cpu_ref.srs_monomial(L(self.s), gen, self.n)
+        n = self.n
+        self.g = cpu_ref.g1_fixed_base_mul_many(cpu_ref.fr_powers(L(self.s), L(1), n), gen)
         # g_lagrange[i] = [L_i(s)]G,  L_i(s) = w^i (s^n - 1) / (n (s - w^i))
-        w = bn254.omega(k)
-        wi = [pow(w, i, R_MOD) for i in range(self.n)]
-        num = (pow(self.s, self.n, R_MOD) - 1) * pow(self.n, -1, R_MOD) % R_MOD
-        den = cpu_ref.fr_batch_invert(bn254.fr_to_limbs([(self.s - x) % R_MOD for x in wi]))
-        li = cpu_ref.fr_mul_vec(den, bn254.fr_to_limbs([x * num % R_MOD for x in wi]))
-        self.g_lagrange = cpu_ref.g1_mul_many(li, gen)
+        wi = cpu_ref.fr_powers(L(bn254.omega(k)), L(1), n)
+        num = (pow(self.s, n, R_MOD) - 1) * pow(n, -1, R_MOD) % R_MOD
+        den = cpu_ref.fr_batch_invert(cpu_ref.fr_sub_vec(np.tile(L(self.s), (n, 1)), wi))
+        li = cpu_ref.fr_mul_vec(den, cpu_ref.fr_scale_vec(wi, L(num)))
+        self.g_lagrange = cpu_ref.g1_fixed_base_mul_many(li, gen)
 
 
 class Domain:
@@ -497,9 +501,9 @@ def create_proof(srs: Srs, pk: ProvingKey, advice_int, instances, rng: XorShiftR
                 acc = cpu_ref.fr_mul_add_scalar(acc, L(theta), eval_expr_vec(e, cs, cols, n, 1, memo))
             return acc
         ci, ct = compress(lk.inputs), compress(lk.tables)
-        pa, ps = permute_expression_pair(canon_ints(ci), canon_ints(ct), usable)
-        pa_l = np.concatenate([bn254.fr_to_limbs(pa), rng.fr(bf + 1)])
-        ps_l = np.concatenate([bn254.fr_to_limbs(ps), rng.fr(bf + 1)])
+        pa, ps = cpu_ref.permute_expression_pair(ci, ct, usable)
+        pa_l = np.concatenate([pa, rng.fr(bf + 1)])
+        ps_l = np.concatenate([ps, rng.fr(bf + 1)])
         pa_poly = dom.lagrange_to_coeff(pa_l)
         rng.fr(1)
         pa_comm = com.commit_lagrange(pa_l, pa_poly)
@@ -518,10 +522,7 @@ def create_proof(srs: Srs, pk: ProvingKey, advice_int, instances, rng: XorShiftR
     perm_sets = []
     deltaomega = 1
     last_z = 1
-    wpow = [1] * n
-    for i in range(1, n):
-        wpow[i] = wpow[i - 1] * dom.omega % R_MOD
-    wpow_l = bn254.fr_to_limbs(wpow)
+    wpow_l = cpu_ref.fr_powers(L(dom.omega), L(1), n)
     for s0 in range(0, len(pcols), chunk):
         cc = pcols[s0:s0 + chunk]
         mod = np.tile(L(1), (n, 1))
@@ -589,10 +590,7 @@ def create_proof(srs: Srs, pk: ProvingKey, advice_int, instances, rng: XorShiftR
         for i in range(1, len(perm_sets)):
             fold(mul(sub(perm_sets[i]["coset"], roll(perm_sets[i - 1]["coset"], -(bf + 1))), pk.l0))
         # X on the coset: zeta * ext_omega^idx
-        xs = [dom.zeta] * en
-        for i in range(1, en):
-            xs[i] = xs[i - 1] * dom.ext_omega % R_MOD
-        xs_l = bn254.fr_to_limbs(xs)
+        xs_l = cpu_ref.fr_powers(L(dom.ext_omega), L(dom.zeta), en)
         cur_delta = beta
         for i, st in enumerate(perm_sets):
             cc = pcols[i * chunk:(i + 1) * chunk]

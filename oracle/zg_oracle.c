@@ -504,6 +504,129 @@ void zgo_fr_from_u512(const uint64_t* w, fe* out, size_t n) {
     fe_add(&out[i], &t0, &t1, &FR);
   }
 }
+/* rand_xorshift::XorShiftRng + Fr::random (eight next_u64 -> from_u512), `count` draws */
+void zgo_xorshift_fr(uint32_t st[4], size_t count, fe* out) {
+  uint32_t x = st[0], y = st[1], z = st[2], w = st[3];
+  fe r3;
+  fe_mul(&r3, &FR.r2, &FR.r2, &FR);
+  for (size_t i = 0; i < count; i++) {
+    uint64_t wd[8];
+    for (int j = 0; j < 8; j++) {
+      uint32_t t = x ^ (x << 11);
+      x = y; y = z; z = w;
+      w = w ^ (w >> 19) ^ (t ^ (t >> 8));
+      uint64_t lo = w;
+      t = x ^ (x << 11);
+      x = y; y = z; z = w;
+      w = w ^ (w >> 19) ^ (t ^ (t >> 8));
+      wd[j] = lo | ((uint64_t)w << 32);
+    }
+    fe d0, d1, t0, t1;
+    memcpy(d0.l, wd, 32);
+    memcpy(d1.l, wd + 4, 32);
+    fe_mul(&t0, &d0, &FR.r2, &FR);
+    fe_mul(&t1, &d1, &r3, &FR);
+    fe_add(&out[i], &t0, &t1, &FR);
+  }
+  st[0] = x; st[1] = y; st[2] = z; st[3] = w;
+}
+/* out[i] = start * w^i */
+void zgo_fr_powers(const fe* w, const fe* start, fe* out, size_t n) {
+  fe cur = *start;
+  for (size_t i = 0; i < n; i++) { out[i] = cur; fe_mul(&cur, &cur, w, &FR); }
+}
+/* lookup::prover::permute_expression_pair on the first `usable` rows (Montgomery in / out):
+ * sort the inputs by canonical value; first occurrences copy their value into the table column and
+ * consume one table copy; the remaining table values, ascending, fill the repeated rows from the
+ * HIGHEST repeated row down (upstream: BTreeMap iteration + repeated_input_rows.pop()).
+ * returns 0, or -1 when an input value is missing from the table (Error::ConstraintSystemFailure). */
+static int cmp_canon(const void* a, const void* b) {
+  const uint64_t* x = (const uint64_t*)a; const uint64_t* y = (const uint64_t*)b;
+  for (int i = 3; i >= 0; i--) { if (x[i] < y[i]) return -1; if (x[i] > y[i]) return 1; }
+  return 0;
+}
+int zgo_permute_expression_pair(const fe* a, const fe* s, size_t usable, fe* pa, fe* ps) {
+  uint64_t(*A)[4] = malloc(usable * 32);
+  uint64_t(*T)[4] = malloc(usable * 32);
+  for (size_t i = 0; i < usable; i++) { fe_from_mont(A[i], &a[i], &FR); fe_from_mont(T[i], &s[i], &FR); }
+  qsort(A, usable, 32, cmp_canon);
+  qsort(T, usable, 32, cmp_canon);
+  /* multiset of the table as (unique value, remaining count) in ascending order */
+  size_t nu = 0;
+  size_t* ustart = malloc((usable + 1) * sizeof(size_t));
+  uint32_t* left = malloc(usable * sizeof(uint32_t));
+  for (size_t i = 0; i < usable; i++)
+    if (i == 0 || cmp_canon(T[i], T[i - 1]) != 0) { ustart[nu] = i; left[nu] = 0; nu++; }
+  ustart[nu] = usable;
+  for (size_t u = 0; u < nu; u++) left[u] = (uint32_t)(ustart[u + 1] - ustart[u]);
+  uint64_t(*S)[4] = calloc(usable, 32);
+  size_t* repeated = malloc(usable * sizeof(size_t));
+  size_t nrep = 0;
+  int rc = 0;
+  for (size_t row = 0; row < usable && rc == 0; row++) {
+    if (row == 0 || cmp_canon(A[row], A[row - 1]) != 0) {
+      memcpy(S[row], A[row], 32);
+      size_t lo = 0, hi = nu;
+      while (lo < hi) { size_t mid = (lo + hi) / 2; if (cmp_canon(T[ustart[mid]], A[row]) < 0) lo = mid + 1; else hi = mid; }
+      if (lo == nu || cmp_canon(T[ustart[lo]], A[row]) != 0 || left[lo] == 0) rc = -1; else left[lo]--;
+    } else {
+      repeated[nrep++] = row;
+    }
+  }
+  if (rc == 0) {
+    for (size_t u = 0; u < nu; u++)
+      for (uint32_t c = 0; c < left[u]; c++) memcpy(S[repeated[--nrep]], T[ustart[u]], 32);
+    for (size_t i = 0; i < usable; i++) {
+      fe t;
+      memcpy(t.l, A[i], 32); fe_mul(&pa[i], &t, &FR.r2, &FR);
+      memcpy(t.l, S[i], 32); fe_mul(&ps[i], &t, &FR.r2, &FR);
+    }
+  }
+  free(A); free(T); free(S); free(ustart); free(left); free(repeated);
+  return rc;
+}
+/* fixed-base scalar multiplication of one generator by many scalars: 8-bit windows, 32 tables of 255
+ * multiples, mixed additions, one shared inversion per 1024 outputs.  Test-SRS generation only. */
+void zgo_g1_fixed_base_mul_many(const fe* scalars, const g1a* gen, size_t n, g1a* out) {
+  static g1a table[32][255];
+  g1j base; j_from_affine(&base, gen);
+  for (int w = 0; w < 32; w++) {
+    g1j acc = base;
+    g1j row[255];
+    for (int i = 0; i < 255; i++) { row[i] = acc; j_add(&acc, &acc, &base); }
+    for (int i = 0; i < 255; i++) j_to_affine(&table[w][i], &row[i]);
+    base = acc; /* 256 * base */
+  }
+  const size_t CH = 1024;
+  size_t nch = (n + CH - 1) / CH;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (size_t c = 0; c < nch; c++) {
+    size_t b = c * CH, e = b + CH < n ? b + CH : n, m = e - b;
+    g1j* jac = malloc(m * sizeof(g1j));
+    fe* pre = malloc(m * sizeof(fe));
+    for (size_t i = 0; i < m; i++) {
+      uint8_t bytes[32];
+      fe_from_mont((uint64_t*)bytes, &scalars[b + i], &FR);
+      g1j acc; j_set_id(&acc);
+      for (int w = 0; w < 32; w++) if (bytes[w]) j_add_affine(&acc, &acc, &table[w][bytes[w] - 1]);
+      jac[i] = acc;
+    }
+    fe run = FQ.r;
+    for (size_t i = 0; i < m; i++) { pre[i] = run; if (!j_is_id(&jac[i])) fe_mul(&run, &run, &jac[i].z, &FQ); }
+    fe inv; fe_inv(&inv, &run, &FQ);
+    for (size_t i = m; i-- > 0;) {
+      if (j_is_id(&jac[i])) { memset(&out[b + i], 0, sizeof(g1a)); continue; }
+      fe zi, zi2, zi3;
+      fe_mul(&zi, &inv, &pre[i], &FQ);
+      fe_mul(&inv, &inv, &jac[i].z, &FQ);
+      fe_sqr(&zi2, &zi, &FQ);
+      fe_mul(&zi3, &zi2, &zi, &FQ);
+      fe_mul(&out[b + i].x, &jac[i].x, &zi2, &FQ);
+      fe_mul(&out[b + i].y, &jac[i].y, &zi3, &FQ);
+    }
+    free(jac); free(pre);
+  }
+}
 int zgo_num_threads(void) { return omp_get_max_threads(); }
 
 /* Synthetic SRS-shaped bases for benchmarks: out[i] = [start + i + 1] * gen, affine.
