@@ -290,8 +290,89 @@ __global__ void k_lookup_fraction(const Fr* __restrict__ ci, const Fr* __restric
   stf(den + i, fp_mul(fp_add(ldf(pa + i), beta), fp_add(ldf(ps + i), gamma)));
 }
 
+struct RpBatch {
+  uint32_t n_out[16];
+};
+__global__ void k_rpb_chunk(const Fr* __restrict__ f, size_t f_stride, RpBatch B, uint32_t len, Fr* __restrict__ P) {
+  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t col = blockIdx.y;
+  const size_t m = B.n_out[col];
+  size_t b = (size_t)c * len;
+  if (b >= m) return;
+  size_t e = b + len < m ? b + len : m;
+  const Fr* fc = f + col * f_stride;
+  Fr acc = ldf(fc + b);
+  for (size_t i = b + 1; i < e; i++) acc = fp_mul(acc, ldf(fc + i));
+  stf(P + (size_t)col * 2 * SCAN_MAX_CHUNKS + c, acc);
+}
+__global__ void __launch_bounds__(1024) k_rpb_block_scan(Fr* __restrict__ PE, RpBatch B, uint32_t len) {
+  __shared__ Fr sm[1024];
+  const uint32_t t = threadIdx.x;
+  const uint32_t col = blockIdx.x;
+  const uint32_t chunks = (B.n_out[col] + len - 1) / len;
+  const Fr* P = PE + (size_t)col * 2 * SCAN_MAX_CHUNKS;
+  Fr* E = PE + (size_t)col * 2 * SCAN_MAX_CHUNKS + SCAN_MAX_CHUNKS;
+  Fr one = fp_one<FrParams>();
+  Fr a0 = (2 * t < chunks) ? ldf(P + 2 * t) : one;
+  Fr a1 = (2 * t + 1 < chunks) ? ldf(P + 2 * t + 1) : one;
+  Fr x = fp_mul(a0, a1);
+  sm[t] = x;
+  __syncthreads();
+  for (uint32_t d = 1; d < 1024; d <<= 1) {
+    Fr o = (t >= d) ? sm[t - d] : one;
+    __syncthreads();
+    if (t >= d) {
+      x = fp_mul(x, o);
+      sm[t] = x;
+    }
+    __syncthreads();
+  }
+  Fr e0 = (t > 0) ? sm[t - 1] : one;
+  if (2 * t < chunks) stf(E + 2 * t, e0);
+  if (2 * t + 1 < chunks) stf(E + 2 * t + 1, fp_mul(e0, a0));
+}
+__global__ void k_rpb_apply(const Fr* __restrict__ f, size_t f_stride, const Fr* __restrict__ PE, RpBatch B, uint32_t len,
+                            Fr* __restrict__ z, size_t z_stride) {
+  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t col = blockIdx.y;
+  const size_t n_out = B.n_out[col];
+  size_t b = (size_t)c * len;
+  if (b >= n_out) return;
+  size_t e = b + len < n_out ? b + len : n_out;
+  const Fr* fc = f + col * f_stride;
+  Fr* zc = z + col * z_stride;
+  Fr acc = ldf(PE + (size_t)col * 2 * SCAN_MAX_CHUNKS + SCAN_MAX_CHUNKS + c);
+  stf(zc + b, acc);
+  for (size_t i = b + 1; i < e; i++) {
+    acc = fp_mul(acc, ldf(fc + i - 1));
+    stf(zc + i, acc);
+  }
+}
+__global__ void k_scale_by_dev(Fr* a, const Fr* __restrict__ s, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) stf(a + i, fp_mul(ldf(a + i), ldf(s)));
+}
+
 }  // namespace
 
+void fr_running_product_batch(const Fr* f, size_t f_stride, Fr* z, size_t z_stride, const uint32_t* n_out, uint32_t count,
+                               Fr* scratch, cudaStream_t st, LaunchCounter lc) {
+  if (!count) return;
+  RpBatch B;
+  uint32_t mx = 0;
+  for (uint32_t i = 0; i < count; i++) { B.n_out[i] = n_out[i]; mx = n_out[i] > mx ? n_out[i] : mx; }
+  ScanGeom g = scan_geom(mx);
+  k_rpb_chunk<<<dim3(blocks_for(g.chunks, 128), count), 128, 0, st>>>(f, f_stride, B, g.len, scratch);
+  lc++;
+  k_rpb_block_scan<<<count, 1024, 0, st>>>(scratch, B, g.len);
+  lc++;
+  k_rpb_apply<<<dim3(blocks_for(g.chunks, 128), count), 128, 0, st>>>(f, f_stride, scratch, B, g.len, z, z_stride);
+  lc++;
+}
+void fr_scale_by_dev(Fr* a, const Fr* scalar_dev, size_t n, cudaStream_t st, LaunchCounter lc) {
+  k_scale_by_dev<<<blocks_for(n), EW_THREADS, 0, st>>>(a, scalar_dev, n);
+  lc++;
+}
 void fr_mul_vec(const Fr* a, const Fr* b, Fr* out, size_t n, cudaStream_t st, LaunchCounter lc) {
   k_mul_vec<<<blocks_for(n), EW_THREADS, 0, st>>>(a, b, out, n);
   lc++;

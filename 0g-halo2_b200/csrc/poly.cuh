@@ -27,6 +27,12 @@ void fr_batch_invert(Fr* a, size_t n, cudaStream_t st, LaunchCounter lc);
 // z[0] = *start_dev, z[i] = z[i-1] * f[i-1] for i < n_out  (grand products); scratch >= 3 * 2048 Fr
 void fr_running_product(const Fr* f, const Fr* start_dev, Fr* z, size_t n_out, Fr* scratch, cudaStream_t st,
                         LaunchCounter lc);
+// `count` (<= 16) independent running products with start 1: column c reads f + c*f_stride and writes
+// n_out[c] entries of z + c*z_stride; scratch >= count * 4096 Fr
+void fr_running_product_batch(const Fr* f, size_t f_stride, Fr* z, size_t z_stride, const uint32_t* n_out, uint32_t count,
+                               Fr* scratch, cudaStream_t st, LaunchCounter lc);
+// a[i] *= *scalar_dev
+void fr_scale_by_dev(Fr* a, const Fr* scalar_dev, size_t n, cudaStream_t st, LaunchCounter lc);
 // kate_division: q has n-1 coefficients, q[i-1] = a[i] + z*q[i]; a[0] is first replaced by a[0]-eval
 // (done by the caller).  scratch >= 4 * 2048 Fr
 void fr_kate_division(const Fr* a, size_t n, const Fr& z, Fr* q, Fr* scratch, cudaStream_t st, LaunchCounter lc);

@@ -373,7 +373,7 @@ int zg_pk_load(zg_ctx* ctx, const zg_pk_desc* d, zg_pk** out) {
     pk->pa_poly = b.take<Fr>(2 * Lk * n); pk->ps_poly = pk->pa_poly ? pk->pa_poly + (size_t)Lk * n : nullptr;
     pk->pz = b.take<Fr>((S + Lk) * n); pk->lz = pk->pz ? pk->pz + (size_t)S * n : nullptr;     // pz | lz contiguous
     pk->pz_poly = b.take<Fr>((S + Lk) * n); pk->lz_poly = pk->pz_poly ? pk->pz_poly + (size_t)S * n : nullptr;
-    pk->pz_coset = b.take<Fr>(S * N); pk->lk_cosets = b.take<Fr>(3 * N);
+    pk->pz_coset = b.take<Fr>(S * N); pk->lk_cosets = b.take<Fr>(3 * (size_t)Lk * N);
     pk->frac = b.take<Fr>(n); pk->rnd = b.take<Fr>(pk->n_draws); pk->random_poly = pk->rnd;  // set per proof
     pk->h = b.take<Fr>(N); pk->h_coeff = b.take<Fr>(N); pk->h_poly = b.take<Fr>(n);
     pk->fold = b.take<Fr>(n); pk->wpoly = b.take<Fr>(8 * n);
@@ -670,38 +670,46 @@ int zg_create_proof(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice, const zg
     uint32_t kind = pk->perm[c].first, idx = pk->perm[c].second;
     return kind == 0 ? pk->adv_values + idx * n : kind == 1 ? pk->fixed_values + idx * n : pk->inst_values + idx * n;
   };
-  Fr deltaomega = fr_one();
-  for (uint32_t s = 0; s < S; s++) {
-    uint32_t c0 = s * pk->chunk, c1 = std::min(c0 + pk->chunk, m);
-    std::vector<const Fr*> vals, sigs;
-    for (uint32_t c = c0; c < c1; c++) { vals.push_back(col_values(c)); sigs.push_back(pk->sigma_values + c * n); }
-    const Fr** dv = pk->d_polyptrs;
-    const Fr** ds = pk->d_polyptrs + vals.size();
-    ZG_CUDA(cudaMemcpyAsync(dv, vals.data(), vals.size() * sizeof(Fr*), cudaMemcpyHostToDevice, st));
-    ZG_CUDA(cudaMemcpyAsync(ds, sigs.data(), sigs.size() * sizeof(Fr*), cudaMemcpyHostToDevice, st));
-    Fr* num = pk->h_poly;   // scratch columns of n
-    Fr* den = pk->frac;
-    perm_fraction(dv, ds, (uint32_t)vals.size(), pk->omega_pows, beta, gamma, deltaomega, pk->delta, num, den, n, st, lc);
-    for (uint32_t c = c0; c < c1; c++) deltaomega = fp_mul(deltaomega, pk->delta);
-    fr_batch_invert(den, n, st, lc);
-    fr_mul_vec(num, den, den, n, st, lc);
-    Fr* z = pk->pz + s * n;
-    const Fr* start = s == 0 ? pk->one_dev : pk->pz + (s - 1) * n + (n - (bf + 1));
-    fr_running_product(den, start, z, n, pk->scratch, st, lc);
-    ZG_CUDA(blind_rows(z, n - bf, bf));
-    draw += 1;
-  }
-  // ---- 5. lookup grand products ---------------------------------------------------------------------------------------
-  for (uint32_t l = 0; l < Lk; l++) {
-    Fr* num = pk->h_poly;
-    Fr* den = pk->frac;
-    lookup_fraction(pk->ci + l * n, pk->ct + l * n, pk->pa + l * n, pk->ps + l * n, beta, gamma, num, den, n, st, lc);
-    fr_batch_invert(den, n, st, lc);
-    fr_mul_vec(num, den, den, n, st, lc);
-    Fr* z = pk->lz + l * n;
-    fr_running_product(den, pk->one_dev, z, n - bf, pk->scratch, st, lc);
-    ZG_CUDA(blind_rows(z, n - bf, bf));
-    draw += 1;
+  // All S + Lk fraction columns are built first so that ONE batch inversion, ONE multiply and ONE batched
+  // scan cover them (these kernels are latency-bound: one Fermat inversion / one block scan per launch).
+  // Permutation set s > 0 continues from set s-1's value at row n-(bf+1): its scan starts at 1 and the
+  // column is scaled afterwards, which is the same product.
+  {
+    const uint32_t cnt = S + Lk;
+    if ((size_t)cnt * n > N || cnt > 16) return ctx->fail(ZG_E_INVALID, "create_proof: too many grand-product columns");
+    Fr* num = pk->h;        // cnt columns of n
+    Fr* den = pk->h_coeff;
+    Fr deltaomega = fr_one();
+    for (uint32_t s = 0; s < S; s++) {
+      uint32_t c0 = s * pk->chunk, c1 = std::min(c0 + pk->chunk, m);
+      std::vector<const Fr*> vals, sigs;
+      for (uint32_t c = c0; c < c1; c++) { vals.push_back(col_values(c)); sigs.push_back(pk->sigma_values + c * n); }
+      const Fr** dv = pk->d_polyptrs + 2 * (size_t)pk->chunk * s;
+      const Fr** ds = dv + vals.size();
+      ZG_CUDA(cudaMemcpyAsync(dv, vals.data(), vals.size() * sizeof(Fr*), cudaMemcpyHostToDevice, st));
+      ZG_CUDA(cudaMemcpyAsync(ds, sigs.data(), sigs.size() * sizeof(Fr*), cudaMemcpyHostToDevice, st));
+      perm_fraction(dv, ds, (uint32_t)vals.size(), pk->omega_pows, beta, gamma, deltaomega, pk->delta, num + s * n, den + s * n, n, st, lc);
+      for (uint32_t c = c0; c < c1; c++) deltaomega = fp_mul(deltaomega, pk->delta);
+    }
+    for (uint32_t l = 0; l < Lk; l++)
+      lookup_fraction(pk->ci + l * n, pk->ct + l * n, pk->pa + l * n, pk->ps + l * n, beta, gamma, num + (S + l) * n, den + (S + l) * n, n,
+                      st, lc);
+    fr_batch_invert(den, (size_t)cnt * n, st, lc);
+    fr_mul_vec(num, den, den, (size_t)cnt * n, st, lc);
+    std::vector<uint32_t> nout(cnt);
+    for (uint32_t s = 0; s < S; s++) nout[s] = (uint32_t)n;
+    for (uint32_t l = 0; l < Lk; l++) nout[S + l] = (uint32_t)(n - bf);
+    fr_running_product_batch(den, n, pk->pz, n, nout.data(), cnt, pk->wpoly, st, lc);   // pz | lz are contiguous
+    for (uint32_t s = 0; s < S; s++) {
+      Fr* z = pk->pz + s * n;
+      if (s > 0) fr_scale_by_dev(z, pk->pz + (s - 1) * n + (n - (bf + 1)), n, st, lc);
+      ZG_CUDA(blind_rows(z, n - bf, bf));
+      draw += 1;
+    }
+    for (uint32_t l = 0; l < Lk; l++) {
+      ZG_CUDA(blind_rows(pk->lz + l * n, n - bf, bf));
+      draw += 1;
+    }
   }
   // ---- 6. vanishing random polynomial; commit round ------------------------------------------------------------------
   pk->random_poly = pk->rnd + draw;
@@ -753,18 +761,18 @@ int zg_create_proof(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice, const zg
     pe.last_rot = -(int32_t)(bf + 1);
     expr_h_permutation(pe, beta, gamma, y, pk->delta, pk->h, st, lc);
   }
-  for (uint32_t l = 0; l < Lk; l++) {
-    Fr* zc = pk->lk_cosets;
-    Fr* ac = pk->lk_cosets + N;
-    Fr* sc = pk->lk_cosets + 2 * N;
-    rc = zg_coeff_to_extended_dev(ctx, (const zg_fr*)(pk->lz_poly + l * n), n, pk->k, pk->ext_k, (zg_fr*)zc, N, 1);
+  if (Lk) {
+    // extended cosets of all lookup polynomials in two batched transforms: [a | s] (2 Lk columns), then z (Lk)
+    Fr* as_cos = pk->lk_cosets;
+    Fr* z_cos = pk->lk_cosets + 2 * (size_t)Lk * N;
+    rc = zg_coeff_to_extended_dev(ctx, (const zg_fr*)pk->pa_poly, n, pk->k, pk->ext_k, (zg_fr*)as_cos, N, 2 * Lk);
     if (rc) return rc;
-    rc = zg_coeff_to_extended_dev(ctx, (const zg_fr*)(pk->pa_poly + l * n), n, pk->k, pk->ext_k, (zg_fr*)ac, N, 1);
+    rc = zg_coeff_to_extended_dev(ctx, (const zg_fr*)pk->lz_poly, n, pk->k, pk->ext_k, (zg_fr*)z_cos, N, Lk);
     if (rc) return rc;
-    rc = zg_coeff_to_extended_dev(ctx, (const zg_fr*)(pk->ps_poly + l * n), n, pk->k, pk->ext_k, (zg_fr*)sc, N, 1);
-    if (rc) return rc;
-    LookupHEnv le{zc, ac, sc, pk->l0, pk->l_last, pk->l_active};
-    expr_h_lookup(ext_env, lp, l, le, theta, beta, gamma, y, pk->h, st, lc);
+    for (uint32_t l = 0; l < Lk; l++) {
+      LookupHEnv le{z_cos + l * N, as_cos + l * N, as_cos + (Lk + l) * N, pk->l0, pk->l_last, pk->l_active};
+      expr_h_lookup(ext_env, lp, l, le, theta, beta, gamma, y, pk->h, st, lc);
+    }
   }
   ZG_CUDA(cudaEventRecord(ev[4], st));
   // ---- 8. vanishing::construct: divide, back to coefficients, commit the pieces ---------------------------------------------

@@ -97,3 +97,53 @@ def test_lookup_failure_is_reported(ctx, tiny):
         create_proof(params, pk, adv, [wnn.predict(img)], zg_b200.lib.XorShift.from_seed(SEED))
     assert ei.value.code == -5
     pk.close()
+
+
+def _parity(ctx, wnn, img, k, srs):
+    import zg_b200
+    from zg_b200.prover import ParamsKZG, keygen, create_proof
+    outputs = wnn.predict(img)
+    zero = np.zeros(wnn.img_shape(), dtype=np.uint8)
+    circ0, asm0 = wnn.synthesize(zero, k)
+    opk = H.keygen(srs, circ0.cs, asm0)
+    _, asm = wnn.synthesize(img, k)
+    oproof = H.create_proof(srs, opk, asm.advice, [outputs], H.XorShiftRng(SEED))
+    assert H.verify_proof(srs, opk, [outputs], oproof)
+    params = ParamsKZG(k, srs.g, srs.g_lagrange)
+    circ1, asm1 = wnn.synthesize(zero, k)
+    pk = keygen(ctx, params, circ1.cs, asm1)
+    assert pk.fixed_commitments == opk.fixed_commitments and pk.perm_commitments == opk.perm_commitments
+    proof = create_proof(params, pk, asm.advice, [outputs], zg_b200.lib.XorShift.from_seed(SEED))
+    if proof != oproof:
+        first = next(i for i in range(min(len(proof), len(oproof))) if proof[i] != oproof[i])
+        pytest.fail("proof bytes differ from the oracle first at offset %d: %s" % (first, _stage_of(first, circ0.cs)))
+    assert H.verify_proof(srs, opk, [outputs], proof)
+    ms = pk.stage_ms()
+    pk.close()
+    return outputs, ms
+
+
+@pytest.mark.parametrize("name,expected", [
+    ("model_28input_1024entry_2hash_2bpi.hdf5", [17, 13, 25, 27, 29, 21, 15, 55, 27, 32]),     # integration_test.rs:30-37
+    ("model_28input_2048entry_2hash_3bpi.hdf5", [29, 21, 40, 47, 45, 41, 28, 82, 35, 66]),     # integration_test.rs:47-54
+])
+def test_small_and_medium_models_match_oracle(ctx, name, expected):
+    """BASELINE configs[1] and [2]: k = 15, seeded RNG, proof bytes identical to the CPU restatement."""
+    from zg_b200.io import load_wnn, load_grayscale_image
+    wnn = load_wnn(os.path.join(GOLD, name))
+    img = load_grayscale_image(os.path.join(GOLD, "example_image_7.png"))
+    srs = H.Srs(15, 0x1F3C5A7B9D2E4F60718293A4B5C6D7E8)
+    outputs, ms = _parity(ctx, wnn, img, 15, srs)
+    assert outputs == expected
+    print(name, "stage ms", ms)
+
+
+def test_large_shape_model_matches_oracle(ctx):
+    """BASELINE configs[3] shape (49 inputs/filter, 8192 entries, 4 hashes, 6 bits/input, k = 17) on the
+    synthetic stand-in for the model file that is absent from the reference checkout, with a synthetic image."""
+    from zg_b200.io import synthetic_wnn, synthetic_image
+    wnn = synthetic_wnn()
+    img = synthetic_image(0)
+    srs = H.Srs(17, 0x1F3C5A7B9D2E4F60718293A4B5C6D7E8)
+    outputs, ms = _parity(ctx, wnn, img, 17, srs)
+    print("large stage ms", ms)
