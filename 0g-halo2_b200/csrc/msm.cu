@@ -18,6 +18,12 @@
 //   * the weighted bucket sum  sum_b b * B_b  is a warp-shuffle suffix scan (32 buckets per
 //     warp) followed by a one-CTA finish kernel.
 //   * several MSMs over the same basis (one Fiat-Shamir round's commitments) share every launch.
+// The level-0 accumulation is 100 KB of SASS with the multiplier inlined and stalls on instruction fetch
+// (ncu: stalled_no_instruction 3.0 per issue, profiles/r01_ncu_full_msm_accumulate_small_proof.txt):
+// outline it (field.cuh).
+#ifndef ZG_MSM_INLINE_MUL
+#define ZG_FP_MUL_NOINLINE 1
+#endif
 #include <cstdlib>
 #include "msm.cuh"
 
