@@ -6,11 +6,13 @@
 // /root/reference/Cargo.toml:14-18 pins; call sites reach it through create_proof
 // (/root/reference/src/wnn.rs:242-259).
 //
-// Two multiplier bodies:
+// Three multiplier bodies:
 //   * a portable 64-bit-accumulator CIOS (host + device; the host build is what the CPU-side
-//     unit tests exercise against Python big integers), and
-//   * a PTX mad.lo.cc / madc.hi.cc carry-chain CIOS (device only, selected with ZG_MUL_PTX).
-// Both compute the same function bit for bit; tests/test_gpu_field.py checks one against the other.
+//     unit tests exercise against Python big integers),
+//   * a row-wise PTX mad.lo.cc / madc.hi.cc CIOS (device only, ZG_MUL_VARIANT=1), and
+//   * the even/odd carry-chain CIOS (device only, ZG_MUL_VARIANT=2, the default): 120 IMAD.WIDE.U32(.X)
+//     per product instead of 120 IMAD.WIDE + ~90 IMAD + ~240 IADD3 in what nvcc makes of the portable body.
+// All compute the same function bit for bit; tests/test_gpu_field.py checks them against each other.
 #pragma once
 #include <stdint.h>
 
@@ -22,8 +24,9 @@
 #define ZG_D inline
 #endif
 
-#ifndef ZG_MUL_PTX
-#define ZG_MUL_PTX 0
+// device multiplier: 0 = portable CIOS, 1 = row-wise mad.cc CIOS, 2 = even/odd carry chains (default)
+#ifndef ZG_MUL_VARIANT
+#define ZG_MUL_VARIANT 2
 #endif
 
 namespace zg {
@@ -351,6 +354,129 @@ __device__ __forceinline__ Fp<P> fp_mul_ptx(const Fp<P>& a, const Fp<P>& b) {
 }
 #endif
 
+#if defined(__CUDA_ARCH__)
+// ---- even/odd carry-chain multiplier (the production device multiplier) -----------------------------
+// The running CIOS accumulator T is kept as two 8-limb arrays, T = U + 2^32 * V.  Products of the EVEN
+// limbs of a (or p) are 64-bit values aligned on U's limb pairs (0,1)(2,3)(4,5)(6,7); products of the ODD
+// limbs are aligned on V's pairs.  Each group of four products is then ONE carry chain of
+// mad.lo.cc / madc.hi.cc pairs, which ptxas fuses into four IMAD.WIDE.U32(.X) with the carry in a
+// predicate -- 16 wide multiply-adds per row and no separate carry-save adds.  After a row U[0] == 0;
+// dividing by 2^32 renames the arrays: V becomes the new U, U >> 64 the new V, and the left-over limb
+// U[1] enters the next row through one add whose carry feeds the first V chain.
+// (validated limb for limb against Python big integers by tests/test_gpu_field.py)
+template <class P>
+__device__ __forceinline__ void eo_reduce(uint32_t (&u)[8], uint32_t (&w)[8]) {
+  asm("{\n\t"
+      ".reg .u32 m;\n\t"
+      "mul.lo.u32 m, %0, %16;\n\t"
+      "mad.lo.cc.u32 %8, m, %18, %8;\n\t"
+      "madc.hi.cc.u32 %9, m, %18, %9;\n\t"
+      "madc.lo.cc.u32 %10, m, %20, %10;\n\t"
+      "madc.hi.cc.u32 %11, m, %20, %11;\n\t"
+      "madc.lo.cc.u32 %12, m, %22, %12;\n\t"
+      "madc.hi.cc.u32 %13, m, %22, %13;\n\t"
+      "madc.lo.cc.u32 %14, m, %24, %14;\n\t"
+      "madc.hi.u32 %15, m, %24, %15;\n\t"
+      "mad.lo.cc.u32 %0, m, %17, %0;\n\t"
+      "madc.hi.cc.u32 %1, m, %17, %1;\n\t"
+      "madc.lo.cc.u32 %2, m, %19, %2;\n\t"
+      "madc.hi.cc.u32 %3, m, %19, %3;\n\t"
+      "madc.lo.cc.u32 %4, m, %21, %4;\n\t"
+      "madc.hi.cc.u32 %5, m, %21, %5;\n\t"
+      "madc.lo.cc.u32 %6, m, %23, %6;\n\t"
+      "madc.hi.cc.u32 %7, m, %23, %7;\n\t"
+      "addc.u32 %15, %15, 0;\n\t"
+      "}"
+      : "+r"(u[0]), "+r"(u[1]), "+r"(u[2]), "+r"(u[3]), "+r"(u[4]), "+r"(u[5]), "+r"(u[6]), "+r"(u[7]),
+        "+r"(w[0]), "+r"(w[1]), "+r"(w[2]), "+r"(w[3]), "+r"(w[4]), "+r"(w[5]), "+r"(w[6]), "+r"(w[7])
+      : "n"(P::INV), "n"(P::mod(0)), "n"(P::mod(1)), "n"(P::mod(2)), "n"(P::mod(3)), "n"(P::mod(4)),
+        "n"(P::mod(5)), "n"(P::mod(6)), "n"(P::mod(7)));
+}
+
+template <class P>
+__device__ __forceinline__ Fp<P> fp_mul_eo(const Fp<P>& a, const Fp<P>& b) {
+  uint32_t u[8], w[8];
+  // row 0: plain products
+  asm("mul.lo.u32 %0, %16, %24;\n\t"
+      "mul.hi.u32 %1, %16, %24;\n\t"
+      "mul.lo.u32 %2, %18, %24;\n\t"
+      "mul.hi.u32 %3, %18, %24;\n\t"
+      "mul.lo.u32 %4, %20, %24;\n\t"
+      "mul.hi.u32 %5, %20, %24;\n\t"
+      "mul.lo.u32 %6, %22, %24;\n\t"
+      "mul.hi.u32 %7, %22, %24;\n\t"
+      "mul.lo.u32 %8, %17, %24;\n\t"
+      "mul.hi.u32 %9, %17, %24;\n\t"
+      "mul.lo.u32 %10, %19, %24;\n\t"
+      "mul.hi.u32 %11, %19, %24;\n\t"
+      "mul.lo.u32 %12, %21, %24;\n\t"
+      "mul.hi.u32 %13, %21, %24;\n\t"
+      "mul.lo.u32 %14, %23, %24;\n\t"
+      "mul.hi.u32 %15, %23, %24;"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+        "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+      : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]),
+        "r"(a.v[7]), "r"(b.v[0]));
+  eo_reduce<P>(u, w);
+#pragma unroll
+  for (int i = 1; i < 8; i++) {
+    // divide by 2^32: new U = V, new V = U >> 64, carry limb U[1]
+    const uint32_t x1 = u[1];
+    uint32_t nw[8];
+#pragma unroll
+    for (int j = 0; j < 6; j++) nw[j] = u[j + 2];
+    nw[6] = 0;
+    nw[7] = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      u[j] = w[j];
+      w[j] = nw[j];
+    }
+    asm("add.cc.u32 %0, %0, %25;\n\t"
+        "madc.lo.cc.u32 %8, %17, %24, %8;\n\t"
+        "madc.hi.cc.u32 %9, %17, %24, %9;\n\t"
+        "madc.lo.cc.u32 %10, %19, %24, %10;\n\t"
+        "madc.hi.cc.u32 %11, %19, %24, %11;\n\t"
+        "madc.lo.cc.u32 %12, %21, %24, %12;\n\t"
+        "madc.hi.cc.u32 %13, %21, %24, %13;\n\t"
+        "madc.lo.cc.u32 %14, %23, %24, %14;\n\t"
+        "madc.hi.u32 %15, %23, %24, %15;\n\t"
+        "mad.lo.cc.u32 %0, %16, %24, %0;\n\t"
+        "madc.hi.cc.u32 %1, %16, %24, %1;\n\t"
+        "madc.lo.cc.u32 %2, %18, %24, %2;\n\t"
+        "madc.hi.cc.u32 %3, %18, %24, %3;\n\t"
+        "madc.lo.cc.u32 %4, %20, %24, %4;\n\t"
+        "madc.hi.cc.u32 %5, %20, %24, %5;\n\t"
+        "madc.lo.cc.u32 %6, %22, %24, %6;\n\t"
+        "madc.hi.cc.u32 %7, %22, %24, %7;\n\t"
+        "addc.u32 %15, %15, 0;"
+        : "+r"(u[0]), "+r"(u[1]), "+r"(u[2]), "+r"(u[3]), "+r"(u[4]), "+r"(u[5]), "+r"(u[6]), "+r"(u[7]),
+          "+r"(w[0]), "+r"(w[1]), "+r"(w[2]), "+r"(w[3]), "+r"(w[4]), "+r"(w[5]), "+r"(w[6]), "+r"(w[7])
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]),
+          "r"(a.v[7]), "r"(b.v[i]), "r"(x1));
+    eo_reduce<P>(u, w);
+  }
+  // T = (U >> 32) + V  (< 2p), then one conditional subtraction
+  uint32_t t[8];
+  asm("add.cc.u32 %0, %8, %16;\n\t"
+      "addc.cc.u32 %1, %9, %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32 %7, %15, 0;"
+      : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7])
+      : "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]),
+        "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]));
+  fp_final_sub<P>(t);
+  Fp<P> r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = t[i];
+  return r;
+}
+#endif
+
 #if defined(__CUDA_ARCH__) && defined(ZG_FP_MUL_NOINLINE)
 // Latency-bound kernels (one warp walking a chain of EC additions) want a SMALL instruction
 // footprint: with the multiplier inlined a single xyzz_add is ~96 KB of straight-line SASS, far beyond
@@ -358,7 +484,11 @@ __device__ __forceinline__ Fp<P> fp_mul_ptx(const Fp<P>& a, const Fp<P>& b) {
 // units that define ZG_FP_MUL_NOINLINE call one shared copy of the multiplier instead.
 template <class P>
 __device__ __noinline__ Fp<P> fp_mul_outlined(Fp<P> a, Fp<P> b) {
+#if ZG_MUL_VARIANT == 0
   return fp_mul_portable<P>(a, b);
+#else
+  return fp_mul_eo<P>(a, b);
+#endif
 }
 #endif
 
@@ -366,7 +496,9 @@ template <class P>
 ZG_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
 #if defined(__CUDA_ARCH__) && defined(ZG_FP_MUL_NOINLINE)
   return fp_mul_outlined<P>(a, b);
-#elif defined(__CUDA_ARCH__) && ZG_MUL_PTX
+#elif defined(__CUDA_ARCH__) && ZG_MUL_VARIANT == 2
+  return fp_mul_eo<P>(a, b);
+#elif defined(__CUDA_ARCH__) && ZG_MUL_VARIANT == 1
   return fp_mul_ptx<P>(a, b);
 #else
   return fp_mul_portable<P>(a, b);

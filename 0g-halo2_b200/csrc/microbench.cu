@@ -50,7 +50,8 @@ __global__ void __launch_bounds__(MB_THREADS) mb_mulmod_kernel(Fr* out, Fr seed,
     for (int i = 0; i < 4; i++) {
 #if defined(__CUDA_ARCH__)
       if (VARIANT == 0) x[i] = fp_mul_portable(x[i], y);
-      else x[i] = fp_mul_ptx(x[i], y);
+      else if (VARIANT == 1) x[i] = fp_mul_ptx(x[i], y);
+      else x[i] = fp_mul_eo(x[i], y);
 #endif
     }
   }
@@ -92,6 +93,10 @@ extern "C" int zg_bench_int_pipe(zg_ctx* ctx, int kind, uint32_t iters, double* 
         mb_mulmod_kernel<1><<<blocks, MB_THREADS, 0, ctx->stream>>>((Fr*)scratch, seed, iters);
         ops_per_thread = 4.0 * iters;
         break;
+      case 4:
+        mb_mulmod_kernel<2><<<blocks, MB_THREADS, 0, ctx->stream>>>((Fr*)scratch, seed, iters);
+        ops_per_thread = 4.0 * iters;
+        break;
       default:
         return ctx->fail(ZG_E_INVALID, "bench_int_pipe: unknown kind");
     }
@@ -125,6 +130,7 @@ __global__ void dbg_field_kernel(int op, const Fp<P>* a, const Fp<P>* b, Fp<P>* 
     case 5: r = fp_inv(x); break;
     case 6: r = fp_from_mont(x); break;
     case 7: r = fp_to_mont(x); break;
+    case 8: r = fp_mul_eo(x, y); break;
     default: r = fp_zero<P>(); break;
   }
   o[i] = r;
@@ -135,7 +141,7 @@ __global__ void dbg_field_kernel(int op, const Fp<P>* a, const Fp<P>* b, Fp<P>* 
 extern "C" int zg_debug_field_op(zg_ctx* ctx, int field, int op, const void* a, const void* b, void* out,
                                  size_t n) {
   if (n == 0) return ZG_OK;
-  if (op < 0 || op > 7 || field < 0 || field > 1) return ctx->fail(ZG_E_INVALID, "debug_field_op: bad op/field");
+  if (op < 0 || op > 8 || field < 0 || field > 1) return ctx->fail(ZG_E_INVALID, "debug_field_op: bad op/field");
   int rc = ws_reserve(ctx, ctx->ws_stage, 96 * n);
   if (rc) return rc;
   uint8_t* d = ctx->ws_stage.p;

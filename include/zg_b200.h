@@ -147,14 +147,14 @@ int zg_pk_last_stage_ms(const zg_pk* pk, float out[8]);
 /* ---- micro-benchmarks used for the integer-pipe roofline (bench.py) ---------------------- */
 /* runs `iters` dependent-free IMAD-class instructions per thread on every SM and returns the
  * achieved rate in 1e9 thread-instructions per second; kind 0 = IMAD (32-bit), 1 = IMAD.WIDE,
- * 2 = Fr Montgomery multiplications, portable body (result in 1e9 mulmod/s), 3 = same, PTX
- * carry-chain body */
+ * 2 = Fr Montgomery multiplications, portable body (result in 1e9 mulmod/s), 3 = same, row-wise PTX
+ * carry-chain body, 4 = same, even/odd carry-chain body (the one the kernels use) */
 int zg_bench_int_pipe(zg_ctx* ctx, int kind, uint32_t iters, double* giga_per_s);
 
 /* ---- diagnostics (parity tests) --------------------------------------------------------- */
 /* element-wise device field op on host arrays of n elements; field 0 = Fr, 1 = Fq;
- * op 0 mul, 1 mul (portable body), 2 mul (PTX body), 3 add, 4 sub, 5 inverse(a), 6 from_mont(a),
- * 7 to_mont(a) */
+ * op 0 mul, 1 mul (portable body), 2 mul (row-wise PTX body), 3 add, 4 sub, 5 inverse(a), 6 from_mont(a),
+ * 7 to_mont(a), 8 mul (even/odd carry-chain body) */
 int zg_debug_field_op(zg_ctx* ctx, int field, int op, const void* a, const void* b, void* out, size_t n);
 
 #ifdef __cplusplus

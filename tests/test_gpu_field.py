@@ -1,4 +1,4 @@
-"""Device field arithmetic (csrc/field.cuh, both multiplier bodies) against Python big integers."""
+"""Device field arithmetic (csrc/field.cuh, all multiplier bodies) against Python big integers."""
 import random
 
 import numpy as np
@@ -28,7 +28,7 @@ def test_field_ops_bit_exact(ctx, field, mod):
     a, b = _vectors(mod, 4096, 17 + field)
     A, B = bn254.ints_to_limbs(a, mod), bn254.ints_to_limbs(b, mod)
     exp_mul = bn254.ints_to_limbs([x * y for x, y in zip(a, b)], mod)
-    for op in (0, 1, 2):  # default, portable, PTX carry-chain bodies must agree bit for bit
+    for op in (0, 1, 2, 8):  # default, portable, row-wise PTX and even/odd carry-chain bodies agree bit for bit
         assert (ctx.debug_field_op(field, op, A, B) == exp_mul).all(), op
     assert (ctx.debug_field_op(field, 3, A, B) == bn254.ints_to_limbs([x + y for x, y in zip(a, b)], mod)).all()
     assert (ctx.debug_field_op(field, 4, A, B) == bn254.ints_to_limbs([x - y for x, y in zip(a, b)], mod)).all()
