@@ -264,6 +264,67 @@ static int commit_batch(zg_ctx* ctx, int basis, const Fr* cols, size_t stride, s
   return ZG_OK;
 }
 
+
+// environment of the RPN programs over the 2^k domain (ext = false) or the extended coset (ext = true)
+static ExprEnv make_env(const zg_pk* pk, bool ext) {
+  ExprEnv e;
+  for (int kind = 0; kind < 3; kind++) {
+    e.cols[kind] = ext ? pk->d_cols_ext[kind] : pk->d_cols_base[kind];
+    e.qcol[kind] = pk->d_qcol[kind];
+    e.qrot[kind] = pk->d_qrot[kind];
+  }
+  e.constants = pk->constants;
+  e.ops = pk->ops;
+  e.size = (uint32_t)(ext ? pk->N : pk->n);
+  e.rot_scale = ext ? pk->rot_scale : 1;
+  return e;
+}
+
+// Evaluator::evaluate_h: reads the coefficient forms in the pk workspace (adv_polys, inst_polys, pz_poly, pa_poly | ps_poly,
+// lz_poly), builds their extended cosets and leaves the y-folded numerator in pk->h.
+static int quotient_numerator(zg_ctx* ctx, zg_pk* pk, const Fr& theta, const Fr& beta, const Fr& gamma, const Fr& y) {
+  const size_t n = pk->n, N = pk->N;
+  const uint32_t A = pk->A, I = pk->I, Lk = pk->n_lookups, S = pk->nsets, bf = pk->bf, m = pk->m;
+  cudaStream_t st = ctx->stream;
+  LaunchCounter lc{&ctx->launches};
+  LookupProgs lp{pk->prog_off, pk->d_in_first, pk->d_in_count, pk->d_tab_first, pk->d_tab_count};
+  int rc;
+  rc = zg_coeff_to_extended_dev(ctx, (const zg_fr*)pk->adv_polys, n, pk->k, pk->ext_k, (zg_fr*)pk->adv_cosets, N, A);
+  if (rc) return rc;
+  if (I) {
+    rc = zg_coeff_to_extended_dev(ctx, (const zg_fr*)pk->inst_polys, n, pk->k, pk->ext_k, (zg_fr*)pk->inst_cosets, N, I);
+    if (rc) return rc;
+  }
+  if (S) {
+    rc = zg_coeff_to_extended_dev(ctx, (const zg_fr*)pk->pz_poly, n, pk->k, pk->ext_k, (zg_fr*)pk->pz_coset, N, S);
+    if (rc) return rc;
+  }
+  ExprEnv ext_env = make_env(pk, true);
+  expr_h_gates(ext_env, pk->prog_off, pk->n_gate_progs, y, pk->h, st, lc);
+  if (S) {
+    PermEnv pe;
+    pe.z_cosets = pk->d_z_cosets; pe.col_cosets = pk->d_perm_cosets; pe.sigma_cosets = pk->d_sigma_cosets;
+    pe.l0 = pk->l0; pe.l_last = pk->l_last; pe.l_active = pk->l_active; pe.coset_x = pk->coset_x;
+    pe.nsets = S; pe.m = m; pe.chunk = pk->chunk; pe.size = (uint32_t)N; pe.rot_scale = pk->rot_scale;
+    pe.last_rot = -(int32_t)(bf + 1);
+    expr_h_permutation(pe, beta, gamma, y, pk->delta, pk->h, st, lc);
+  }
+  if (Lk) {
+    // extended cosets of all lookup polynomials in two batched transforms: [a | s] (2 Lk columns), then z (Lk)
+    Fr* as_cos = pk->lk_cosets;
+    Fr* z_cos = pk->lk_cosets + 2 * (size_t)Lk * N;
+    rc = zg_coeff_to_extended_dev(ctx, (const zg_fr*)pk->pa_poly, n, pk->k, pk->ext_k, (zg_fr*)as_cos, N, 2 * Lk);
+    if (rc) return rc;
+    rc = zg_coeff_to_extended_dev(ctx, (const zg_fr*)pk->lz_poly, n, pk->k, pk->ext_k, (zg_fr*)z_cos, N, Lk);
+    if (rc) return rc;
+    for (uint32_t l = 0; l < Lk; l++) {
+      LookupHEnv le{z_cos + l * N, as_cos + l * N, as_cos + (Lk + l) * N, pk->l0, pk->l_last, pk->l_active};
+      expr_h_lookup(ext_env, lp, l, le, theta, beta, gamma, y, pk->h, st, lc);
+    }
+  }
+  return ZG_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -377,7 +438,7 @@ int zg_pk_load(zg_ctx* ctx, const zg_pk_desc* d, zg_pk** out) {
     pk->frac = b.take<Fr>(n); pk->rnd = b.take<Fr>(pk->n_draws); pk->random_poly = pk->rnd;  // set per proof
     pk->h = b.take<Fr>(N); pk->h_coeff = b.take<Fr>(N); pk->h_poly = b.take<Fr>(n);
     pk->fold = b.take<Fr>(n); pk->wpoly = b.take<Fr>(8 * n);
-    pk->scratch = b.take<Fr>(8192 + 64 * (size_t)n_queries);
+    pk->scratch = b.take<Fr>(8192 + std::max<size_t>(64, (n + 4095) / 4096) * (size_t)n_queries);
     pk->evals_dev = b.take<Fr>(n_queries + 8); pk->points_dev = b.take<Fr>(16); pk->coeff_dev = b.take<Fr>(n_queries + 8);
     pk->one_dev = b.take<Fr>(8);
     pk->d_polyptrs = b.take<const Fr*>(n_queries + 8); pk->d_pidx = b.take<uint32_t>(n_queries + 8);
@@ -587,16 +648,7 @@ int zg_create_proof(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice, const zg
   const Fr theta = tr.squeeze();
 
   // ---- 3. lookups: compress, permute, commit --------------------------------------------------------------------
-  ExprEnv base_env;
-  for (int kind = 0; kind < 3; kind++) {
-    base_env.cols[kind] = pk->d_cols_base[kind];
-    base_env.qcol[kind] = pk->d_qcol[kind];
-    base_env.qrot[kind] = pk->d_qrot[kind];
-  }
-  base_env.constants = pk->constants;
-  base_env.ops = pk->ops;
-  base_env.size = (uint32_t)n;
-  base_env.rot_scale = 1;
+  ExprEnv base_env = make_env(pk, false);
   LookupProgs lp{pk->prog_off, pk->d_in_first, pk->d_in_count, pk->d_tab_first, pk->d_tab_count};
   if (Lk) {
     expr_compress_lookups(base_env, lp, Lk, theta, pk->ci, pk->ct, n, st, lc);
@@ -738,42 +790,8 @@ int zg_create_proof(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice, const zg
   const Fr y = tr.squeeze();
 
   // ---- 7. quotient numerator on the extended coset ----------------------------------------------------------------------
-  rc = zg_coeff_to_extended_dev(ctx, (const zg_fr*)pk->adv_polys, n, pk->k, pk->ext_k, (zg_fr*)pk->adv_cosets, N, A);
+  rc = quotient_numerator(ctx, pk, theta, beta, gamma, y);
   if (rc) return rc;
-  if (I) {
-    rc = zg_coeff_to_extended_dev(ctx, (const zg_fr*)pk->inst_polys, n, pk->k, pk->ext_k, (zg_fr*)pk->inst_cosets, N, I);
-    if (rc) return rc;
-  }
-  if (S) {
-    rc = zg_coeff_to_extended_dev(ctx, (const zg_fr*)pk->pz_poly, n, pk->k, pk->ext_k, (zg_fr*)pk->pz_coset, N, S);
-    if (rc) return rc;
-  }
-  ExprEnv ext_env = base_env;
-  for (int kind = 0; kind < 3; kind++) ext_env.cols[kind] = pk->d_cols_ext[kind];
-  ext_env.size = (uint32_t)N;
-  ext_env.rot_scale = pk->rot_scale;
-  expr_h_gates(ext_env, pk->prog_off, pk->n_gate_progs, y, pk->h, st, lc);
-  if (S) {
-    PermEnv pe;
-    pe.z_cosets = pk->d_z_cosets; pe.col_cosets = pk->d_perm_cosets; pe.sigma_cosets = pk->d_sigma_cosets;
-    pe.l0 = pk->l0; pe.l_last = pk->l_last; pe.l_active = pk->l_active; pe.coset_x = pk->coset_x;
-    pe.nsets = S; pe.m = m; pe.chunk = pk->chunk; pe.size = (uint32_t)N; pe.rot_scale = pk->rot_scale;
-    pe.last_rot = -(int32_t)(bf + 1);
-    expr_h_permutation(pe, beta, gamma, y, pk->delta, pk->h, st, lc);
-  }
-  if (Lk) {
-    // extended cosets of all lookup polynomials in two batched transforms: [a | s] (2 Lk columns), then z (Lk)
-    Fr* as_cos = pk->lk_cosets;
-    Fr* z_cos = pk->lk_cosets + 2 * (size_t)Lk * N;
-    rc = zg_coeff_to_extended_dev(ctx, (const zg_fr*)pk->pa_poly, n, pk->k, pk->ext_k, (zg_fr*)as_cos, N, 2 * Lk);
-    if (rc) return rc;
-    rc = zg_coeff_to_extended_dev(ctx, (const zg_fr*)pk->lz_poly, n, pk->k, pk->ext_k, (zg_fr*)z_cos, N, Lk);
-    if (rc) return rc;
-    for (uint32_t l = 0; l < Lk; l++) {
-      LookupHEnv le{z_cos + l * N, as_cos + l * N, as_cos + (Lk + l) * N, pk->l0, pk->l_last, pk->l_active};
-      expr_h_lookup(ext_env, lp, l, le, theta, beta, gamma, y, pk->h, st, lc);
-    }
-  }
   ZG_CUDA(cudaEventRecord(ev[4], st));
   // ---- 8. vanishing::construct: divide, back to coefficients, commit the pieces ---------------------------------------------
   fr_mul_periodic(pk->h, pk->t_inv, pk->rot_scale, N, st, lc);
@@ -908,6 +926,44 @@ int zg_create_proof(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice, const zg
   if (tr.out.size() > proof_cap) return ctx->fail(ZG_E_INVALID, "create_proof: proof buffer too small");
   memcpy(proof_out, tr.out.data(), tr.out.size());
   *proof_len = tr.out.size();
+  return ZG_OK;
+}
+
+// plonk::evaluation::Evaluator::evaluate_h for one circuit: polynomials in coefficient form (host), result on the
+// extended coset (host).  divide != 0 also applies EvaluationDomain::divide_by_vanishing_poly.
+int zg_evaluate_h(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice_polys, const zg_fr* const* instance_polys,
+                  const zg_fr* const* lookup_input_polys, const zg_fr* const* lookup_table_polys,
+                  const zg_fr* const* lookup_product_polys, const zg_fr* const* perm_product_polys, const zg_fr challenges[4],
+                  int divide, zg_fr* h_out) {
+  if (!pk || !challenges || !h_out) return ctx->fail(ZG_E_INVALID, "evaluate_h: null argument");
+  const size_t n = pk->n, N = pk->N;
+  const uint32_t A = pk->A, I = pk->I, Lk = pk->n_lookups, S = pk->nsets;
+  if ((A && !advice_polys) || (I && !instance_polys) || (S && !perm_product_polys) ||
+      (Lk && (!lookup_input_polys || !lookup_table_polys || !lookup_product_polys)))
+    return ctx->fail(ZG_E_INVALID, "evaluate_h: missing polynomial list");
+  cudaStream_t st = ctx->stream;
+  LaunchCounter lc{&ctx->launches};
+  auto up = [&](Fr* dst, const zg_fr* const* src, uint32_t count) -> cudaError_t {
+    for (uint32_t c = 0; c < count; c++) {
+      if (!src[c]) return cudaErrorInvalidValue;
+      cudaError_t e = cudaMemcpyAsync(dst + c * n, src[c], sizeof(Fr) * n, cudaMemcpyHostToDevice, st);
+      if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+  };
+  ZG_CUDA(up(pk->adv_polys, advice_polys, A));
+  ZG_CUDA(up(pk->inst_polys, instance_polys, I));
+  ZG_CUDA(up(pk->pz_poly, perm_product_polys, S));
+  ZG_CUDA(up(pk->pa_poly, lookup_input_polys, Lk));
+  ZG_CUDA(up(pk->ps_poly, lookup_table_polys, Lk));
+  ZG_CUDA(up(pk->lz_poly, lookup_product_polys, Lk));
+  Fr ch[4];
+  memcpy(ch, challenges, sizeof(ch));   // theta, beta, gamma, y
+  int rc = quotient_numerator(ctx, pk, ch[0], ch[1], ch[2], ch[3]);
+  if (rc) return rc;
+  if (divide) fr_mul_periodic(pk->h, pk->t_inv, pk->rot_scale, N, st, lc);
+  ZG_CUDA(cudaMemcpyAsync(h_out, pk->h, sizeof(Fr) * N, cudaMemcpyDeviceToHost, st));
+  ZG_CUDA(cudaStreamSynchronize(st));
   return ZG_OK;
 }
 

@@ -31,6 +31,7 @@ EXPORTS = [
     "zg_bench_int_pipe", "zg_debug_field_op",
     "zg_xorshift_seed", "zg_xorshift_fill", "zg_pk_load", "zg_pk_free", "zg_pk_commitments", "zg_create_proof",
     "zg_pk_last_stage_ms",
+    "zg_lookup_permute", "zg_grand_product", "zg_batch_invert", "zg_eval_poly_batch", "zg_kate_division", "zg_evaluate_h",
 ]
 
 
@@ -91,6 +92,12 @@ def load_library() -> ctypes.CDLL:
     L.zg_pk_commitments.argtypes = [vp, vp, vp, vp]
     L.zg_create_proof.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, sz, ctypes.POINTER(sz)]
     L.zg_pk_last_stage_ms.argtypes = [vp, vp]
+    L.zg_lookup_permute.argtypes = [vp, vp, vp, sz, vp, vp]
+    L.zg_grand_product.argtypes = [vp, vp, vp, sz, vp]
+    L.zg_batch_invert.argtypes = [vp, vp, sz]
+    L.zg_eval_poly_batch.argtypes = [vp, vp, sz, sz, vp, vp]
+    L.zg_kate_division.argtypes = [vp, vp, sz, vp, vp]
+    L.zg_evaluate_h.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, ci, vp]
     _lib = L
     return L
 
@@ -205,6 +212,57 @@ class Context:
 
     def extended_to_coeff_dev(self, ext_ptr, k, ext_k, keep, out_ptr):
         self._ck(self._L.zg_extended_to_coeff_dev(self._h, ext_ptr, k, ext_k, keep, out_ptr))
+
+    # ---- single prover stages (host arrays) ----
+    def lookup_permute(self, a, s):
+        """permute_expression_pair over the rows given (no blinding rows): returns (a', s')."""
+        a, s = _np(a, 4), _np(s, 4)
+        assert a.shape == s.shape
+        pa, ps = np.zeros_like(a), np.zeros_like(s)
+        self._ck(self._L.zg_lookup_permute(self._h, _ptr(a), _ptr(s), a.shape[0], _ptr(pa), _ptr(ps)))
+        return pa, ps
+
+    def grand_product(self, num, den) -> np.ndarray:
+        num, den = _np(num, 4), _np(den, 4)
+        assert num.shape == den.shape
+        z = np.zeros_like(num)
+        self._ck(self._L.zg_grand_product(self._h, _ptr(num), _ptr(den), num.shape[0], _ptr(z)))
+        return z
+
+    def batch_invert(self, a) -> np.ndarray:
+        a = _np(a, 4).copy()
+        self._ck(self._L.zg_batch_invert(self._h, _ptr(a), a.shape[0]))
+        return a
+
+    def eval_poly_batch(self, polys, x) -> np.ndarray:
+        arrs = [_np(p, 4) for p in polys]
+        n = arrs[0].shape[0]
+        assert all(a.shape[0] == n for a in arrs)
+        ptrs = (ctypes.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+        xx = _np(x, 4).reshape(4)
+        out = np.zeros((len(arrs), 4), dtype=np.uint64)
+        self._ck(self._L.zg_eval_poly_batch(self._h, ptrs, n, len(arrs), _ptr(xx), _ptr(out)))
+        return out
+
+    def kate_division(self, a, z) -> np.ndarray:
+        a = _np(a, 4)
+        zz = _np(z, 4).reshape(4)
+        q = np.zeros((max(a.shape[0] - 1, 0), 4), dtype=np.uint64)
+        self._ck(self._L.zg_kate_division(self._h, _ptr(a), a.shape[0], _ptr(zz), _ptr(q)))
+        return q
+
+    def evaluate_h(self, pk_handle, ext_n, advice, instance, lk_in, lk_tab, lk_z, perm_z, challenges, divide=False):
+        """Evaluator::evaluate_h; polynomial lists are coefficient-form (n,4) arrays, challenges = (theta, beta, gamma, y)
+        as a (4,4) limb array."""
+        def plist(lst):
+            arrs = [_np(p, 4) for p in lst]
+            return arrs, (ctypes.c_void_p * max(len(arrs), 1))(*[a.ctypes.data for a in arrs])
+        keep = [plist(x) for x in (advice, instance, lk_in, lk_tab, lk_z, perm_z)]
+        ch = _np(challenges, 4)
+        assert ch.shape == (4, 4)
+        out = np.zeros((ext_n, 4), dtype=np.uint64)
+        self._ck(self._L.zg_evaluate_h(self._h, pk_handle, *[k[1] for k in keep], _ptr(ch), int(divide), _ptr(out)))
+        return out
 
     # ---- micro-benchmarks ----
     def bench_int_pipe(self, kind: int, iters: int = 4096) -> float:

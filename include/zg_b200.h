@@ -144,6 +144,34 @@ int zg_create_proof(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice, const zg
  * out[0..8) = advice, lookups, products, quotient, h-commit, evals, gwc, total */
 int zg_pk_last_stage_ms(const zg_pk* pk, float out[8]);
 
+/* ---- single prover stages (host pointers) --------------------------------------------------------
+ * zg_create_proof keeps a whole proof on the device.  A halo2_proofs fork that replaces ONE upstream function
+ * at a time binds these; each wraps exactly the kernels the proof path runs for that step.  Upstream names are
+ * halo2_proofs v2023_04_20 (un-vendored, /root/reference/Cargo.toml:21-25), all reached from create_proof
+ * (/root/reference/src/wnn.rs:242-259). */
+/* plonk::lookup::prover::permute_expression_pair without the blinding rows: a / s are the compressed input /
+ * table expressions over the first `usable` rows.  ZG_E_SYNTH when an input is not in the table
+ * (upstream Error::ConstraintSystemFailure). */
+int zg_lookup_permute(zg_ctx* ctx, const zg_fr* a, const zg_fr* s, size_t usable, zg_fr* a_perm, zg_fr* s_perm);
+/* grand product of plonk::permutation::prover::commit / plonk::lookup::prover::commit_product:
+ * z[0] = 1, z[i] = z[i-1] * num[i-1] / den[i-1] for i < len (one batch inversion of den) */
+int zg_grand_product(zg_ctx* ctx, const zg_fr* num, const zg_fr* den, size_t len, zg_fr* z);
+/* ff::BatchInvert::batch_invert in place; zeros stay zero */
+int zg_batch_invert(zg_ctx* ctx, zg_fr* a, size_t n);
+/* arithmetic::eval_polynomial: out[j] = polys[j](x), every polynomial has n coefficients */
+int zg_eval_poly_batch(zg_ctx* ctx, const zg_fr* const* polys, size_t n, size_t count, const zg_fr* x, zg_fr* out);
+/* arithmetic::kate_division: q(X) = (a(X) - a(z)) / (X - z); a has n coefficients, q receives n - 1 */
+int zg_kate_division(zg_ctx* ctx, const zg_fr* a, size_t n, const zg_fr* z, zg_fr* q);
+/* plonk::evaluation::Evaluator::evaluate_h for one circuit of `pk`: polynomials in coefficient form (2^k each):
+ * advice (num_advice), instance (num_instance), per lookup the permuted input / permuted table / product
+ * polynomials, per permutation set the product polynomial; challenges = {theta, beta, gamma, y}.
+ * h_out receives the 2^ext_k values of the y-folded numerator on the extended coset; with divide != 0 it is also
+ * multiplied by 1/(X^n - 1) (EvaluationDomain::divide_by_vanishing_poly).  Uses pk's per-proof workspace. */
+int zg_evaluate_h(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice_polys, const zg_fr* const* instance_polys,
+                  const zg_fr* const* lookup_input_polys, const zg_fr* const* lookup_table_polys,
+                  const zg_fr* const* lookup_product_polys, const zg_fr* const* perm_product_polys,
+                  const zg_fr challenges[4], int divide, zg_fr* h_out);
+
 /* ---- micro-benchmarks used for the integer-pipe roofline (bench.py) ---------------------- */
 /* runs `iters` dependent-free IMAD-class instructions per thread on every SM and returns the
  * achieved rate in 1e9 thread-instructions per second; kind 0 = IMAD (32-bit), 1 = IMAD.WIDE,

@@ -618,8 +618,17 @@ def create_proof(srs: Srs, pk: ProvingKey, advice_int, instances, rng: XorShiftR
         fold(mul(sub(mul(mul(roll(zc, 1), add(ac, tile(beta))), add(sc, tile(gamma))), mul(zc, tv)), pk.l_active))
         fold(mul(a_minus_s, pk.l0))
         fold(mul(mul(a_minus_s, sub(ac, roll(ac, -1))), pk.l_active))
+    if trace is not None:      # inputs and output of Evaluator::evaluate_h, for the per-stage parity tests
+        T["evaluate_h"] = {"advice_polys": adv_polys, "instance_polys": inst_polys,
+                           "lookup_input_polys": [l["pa_poly"] for l in lookups],
+                           "lookup_table_polys": [l["ps_poly"] for l in lookups],
+                           "lookup_product_polys": [l["z_poly"] for l in lookups],
+                           "perm_product_polys": [s["poly"] for s in perm_sets], "h_numerator": h.copy()}
+        T["lookup_columns"] = [{"ci": l["ci"], "ct": l["ct"], "pa": l["pa"], "ps": l["ps"]} for l in lookups]
     # 8. vanishing::construct
     h = dom.divide_by_vanishing(h)
+    if trace is not None:
+        T["evaluate_h"]["h_divided"] = h.copy()
     h_coeff = dom.extended_to_coeff(h)
     pieces = [h_coeff[i * n:(i + 1) * n] for i in range(dom.quotient_poly_degree)]
     for _ in pieces:
