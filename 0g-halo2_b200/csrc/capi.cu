@@ -164,25 +164,30 @@ const char* zg_last_error(const zg_ctx* ctx) { return ctx ? ctx->err.c_str() : "
 uint64_t zg_launch_count(const zg_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int zg_sync(zg_ctx* ctx) {
+  ZG_ENTER(ctx);
   ZG_CUDA(cudaStreamSynchronize(ctx->stream));
   return ZG_OK;
 }
 int zg_dev_alloc(zg_ctx* ctx, size_t bytes, void** out) {
+  ZG_ENTER(ctx);
   ZG_CUDA(cudaSetDevice(ctx->device));
   ZG_CUDA(cudaMalloc(out, bytes));
   return ZG_OK;
 }
 int zg_dev_free(zg_ctx* ctx, void* p) {
+  ZG_ENTER(ctx);
   ZG_CUDA(cudaStreamSynchronize(ctx->stream));
   ZG_CUDA(cudaFree(p));
   return ZG_OK;
 }
 int zg_h2d(zg_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  ZG_ENTER(ctx);
   ZG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
   ZG_CUDA(cudaStreamSynchronize(ctx->stream));
   return ZG_OK;
 }
 int zg_d2h(zg_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  ZG_ENTER(ctx);
   ZG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   ZG_CUDA(cudaStreamSynchronize(ctx->stream));
   return ZG_OK;
@@ -190,6 +195,7 @@ int zg_d2h(zg_ctx* ctx, void* dst, const void* src, size_t bytes) {
 
 // ---- SRS -------------------------------------------------------------------------------------
 int zg_srs_load(zg_ctx* ctx, uint32_t k, const zg_g1_affine* g, const zg_g1_affine* g_lagrange) {
+  ZG_ENTER(ctx);
   if (k < 1 || k > 26) return ctx->fail(ZG_E_INVALID, "srs_load: k out of range [1,26]");
   ZG_CUDA(cudaSetDevice(ctx->device));
   const size_t n = (size_t)1 << k;
@@ -222,6 +228,7 @@ int zg_srs_load(zg_ctx* ctx, uint32_t k, const zg_g1_affine* g, const zg_g1_affi
 // ---- MSM -------------------------------------------------------------------------------------
 int zg_msm_dev(zg_ctx* ctx, int basis, const zg_fr* scalars_dev, size_t stride, size_t n, size_t count,
                zg_g1* out_dev) {
+  ZG_ENTER(ctx);
   if (!ctx->srs_loaded) return ctx->fail(ZG_E_STATE, "msm: no SRS loaded");
   if (basis < 0 || basis > 1 || !ctx->table[basis].pts) return ctx->fail(ZG_E_STATE, "msm: basis not loaded");
   const MsmTable& t = ctx->table[basis];
@@ -239,6 +246,7 @@ int zg_msm_dev(zg_ctx* ctx, int basis, const zg_fr* scalars_dev, size_t stride, 
 }
 
 int zg_msm_batch(zg_ctx* ctx, int basis, const zg_fr* const* scalars, size_t n, size_t count, zg_g1* out) {
+  ZG_ENTER(ctx);
   if (count == 0) return ZG_OK;
   if (count > 64) return ctx->fail(ZG_E_INVALID, "msm_batch: count > 64");
   int rc = ws_reserve(ctx, ctx->ws_stage, sizeof(Fr) * n * count);
@@ -254,6 +262,7 @@ int zg_msm_batch(zg_ctx* ctx, int basis, const zg_fr* const* scalars, size_t n, 
 }
 
 int zg_msm(zg_ctx* ctx, int basis, const zg_fr* scalars, size_t n, zg_g1* out) {
+  ZG_ENTER(ctx);
   const zg_fr* arr[1] = {scalars};
   return zg_msm_batch(ctx, basis, arr, n, 1, out);
 }
@@ -261,6 +270,7 @@ int zg_msm(zg_ctx* ctx, int basis, const zg_fr* scalars, size_t n, zg_g1* out) {
 // ---- NTT -------------------------------------------------------------------------------------
 int zg_ntt_dev(zg_ctx* ctx, const zg_fr* in_dev, zg_fr* out_dev, uint32_t log_n, const zg_fr* omega,
                size_t batch, size_t stride) {
+  ZG_ENTER(ctx);
   Fr w = fr_from_abi(omega);
   uint32_t n = 1u << log_n;
   return ntt_generic_dev(ctx, (const Fr*)in_dev, stride, (Fr*)out_dev, stride, log_n, w, batch, n, n, 0,
@@ -268,6 +278,7 @@ int zg_ntt_dev(zg_ctx* ctx, const zg_fr* in_dev, zg_fr* out_dev, uint32_t log_n,
 }
 
 int zg_ntt(zg_ctx* ctx, zg_fr* a, uint32_t log_n, const zg_fr* omega) {
+  ZG_ENTER(ctx);
   if (log_n < 1 || log_n > 28) return ctx->fail(ZG_E_INVALID, "ntt: log_n out of range [1,28]");
   size_t n = (size_t)1 << log_n;
   int rc = ws_reserve(ctx, ctx->ws_stage, sizeof(Fr) * n);
@@ -283,6 +294,7 @@ int zg_ntt(zg_ctx* ctx, zg_fr* a, uint32_t log_n, const zg_fr* omega) {
 
 int zg_lagrange_to_coeff_dev(zg_ctx* ctx, const zg_fr* in_dev, zg_fr* out_dev, uint32_t k, size_t batch,
                              size_t stride) {
+  ZG_ENTER(ctx);
   if (k < 1 || k > 28) return ctx->fail(ZG_E_INVALID, "lagrange_to_coeff: k out of range");
   Fr winv = fp_inv(host_omega(k));
   Fr ninv = fp_inv(host_fr_from_u64(1ull << k));
@@ -293,6 +305,7 @@ int zg_lagrange_to_coeff_dev(zg_ctx* ctx, const zg_fr* in_dev, zg_fr* out_dev, u
 }
 
 int zg_lagrange_to_coeff(zg_ctx* ctx, zg_fr* a, uint32_t k) {
+  ZG_ENTER(ctx);
   if (k < 1 || k > 28) return ctx->fail(ZG_E_INVALID, "lagrange_to_coeff: k out of range");
   size_t n = (size_t)1 << k;
   int rc = ws_reserve(ctx, ctx->ws_stage, sizeof(Fr) * n);
@@ -308,6 +321,7 @@ int zg_lagrange_to_coeff(zg_ctx* ctx, zg_fr* a, uint32_t k) {
 
 int zg_coeff_to_extended_dev(zg_ctx* ctx, const zg_fr* coeff_dev, size_t in_stride, uint32_t k, uint32_t ext_k,
                              zg_fr* out_dev, size_t out_stride, size_t batch) {
+  ZG_ENTER(ctx);
   if (k < 1 || ext_k < k || ext_k > 28) return ctx->fail(ZG_E_INVALID, "coeff_to_extended: bad k/ext_k");
   Fr zeta = host_fr_zeta();
   Fr sc[3] = {fp_one<FrParams>(), zeta, fp_sqr(zeta)};
@@ -316,6 +330,7 @@ int zg_coeff_to_extended_dev(zg_ctx* ctx, const zg_fr* coeff_dev, size_t in_stri
 }
 
 int zg_coeff_to_extended(zg_ctx* ctx, const zg_fr* coeff, uint32_t k, uint32_t ext_k, zg_fr* out) {
+  ZG_ENTER(ctx);
   if (k < 1 || ext_k < k || ext_k > 28) return ctx->fail(ZG_E_INVALID, "coeff_to_extended: bad k/ext_k");
   size_t n = (size_t)1 << k, ne = (size_t)1 << ext_k;
   int rc = ws_reserve(ctx, ctx->ws_stage, sizeof(Fr) * (n + ne));
@@ -332,6 +347,7 @@ int zg_coeff_to_extended(zg_ctx* ctx, const zg_fr* coeff, uint32_t k, uint32_t e
 
 int zg_extended_to_coeff_dev(zg_ctx* ctx, const zg_fr* ext_dev, uint32_t k, uint32_t ext_k, size_t keep,
                              zg_fr* out_dev) {
+  ZG_ENTER(ctx);
   if (k < 1 || ext_k < k || ext_k > 28) return ctx->fail(ZG_E_INVALID, "extended_to_coeff: bad k/ext_k");
   size_t ne = (size_t)1 << ext_k;
   if (keep == 0 || keep > ne) return ctx->fail(ZG_E_INVALID, "extended_to_coeff: keep out of range");
@@ -344,6 +360,7 @@ int zg_extended_to_coeff_dev(zg_ctx* ctx, const zg_fr* ext_dev, uint32_t k, uint
 }
 
 int zg_extended_to_coeff(zg_ctx* ctx, const zg_fr* ext, uint32_t k, uint32_t ext_k, size_t keep, zg_fr* out) {
+  ZG_ENTER(ctx);
   if (k < 1 || ext_k < k || ext_k > 28) return ctx->fail(ZG_E_INVALID, "extended_to_coeff: bad k/ext_k");
   size_t ne = (size_t)1 << ext_k;
   if (keep == 0 || keep > ne) return ctx->fail(ZG_E_INVALID, "extended_to_coeff: keep out of range");

@@ -65,6 +65,14 @@ int ws_reserve(zg_ctx* ctx, Workspace& w, size_t bytes);
 int get_domain(zg_ctx* ctx, uint32_t logn, const Fr& omega, Domain** out);
 }  // namespace zg
 
+// CUDA's current device is per host thread: every entry point selects the context's device first
+#define ZG_ENTER(ctx)                                              \
+  do {                                                             \
+    if (!(ctx)) return ZG_E_INVALID;                               \
+    cudaError_t e__ = cudaSetDevice((ctx)->device);                \
+    if (e__ != cudaSuccess) return (ctx)->cuda_fail(e__, "cudaSetDevice"); \
+  } while (0)
+
 #define ZG_CUDA(call)                                             \
   do {                                                            \
     cudaError_t e__ = (call);                                     \

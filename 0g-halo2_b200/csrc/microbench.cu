@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(MB_THREADS) mb_mulmod_kernel(Fr* out, Fr seed,
 }  // namespace
 
 extern "C" int zg_bench_int_pipe(zg_ctx* ctx, int kind, uint32_t iters, double* giga_per_s) {
+  ZG_ENTER(ctx);
   if (!giga_per_s || iters == 0) return ctx->fail(ZG_E_INVALID, "bench_int_pipe: bad arguments");
   cudaDeviceProp prop;
   ZG_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
@@ -140,6 +141,7 @@ __global__ void dbg_field_kernel(int op, const Fp<P>* a, const Fp<P>* b, Fp<P>* 
 
 extern "C" int zg_debug_field_op(zg_ctx* ctx, int field, int op, const void* a, const void* b, void* out,
                                  size_t n) {
+  ZG_ENTER(ctx);
   if (n == 0) return ZG_OK;
   if (op < 0 || op > 8 || field < 0 || field > 1) return ctx->fail(ZG_E_INVALID, "debug_field_op: bad op/field");
   int rc = ws_reserve(ctx, ctx->ws_stage, 96 * n);

@@ -17,6 +17,7 @@
 //     lanes that walk consecutive columns read consecutive table entries.
 //   * 254-bit Montgomery butterflies make this kernel integer-pipe bound (about 10 mulmods per
 //     element at 2^20 against 64 B of traffic per pass), see DESIGN.md.
+#include <atomic>
 #include "ntt.cuh"
 
 namespace zg {
@@ -188,11 +189,14 @@ cudaError_t ntt_run(const NttPlan& P, cudaStream_t stream, uint64_t* nl) {
   if (npass == 0) npass = 1;
   uint32_t bits_left = logn;
   uint32_t hi = logn;
-  static bool attr_set = false;
-  if (!attr_set) {
+  // the attribute is per device; one process may drive several devices / host threads
+  static std::atomic<uint64_t> attr_devices{0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!(attr_devices.load(std::memory_order_acquire) >> (dev & 63) & 1)) {
     cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)((sizeof(Fr) << NTT_MAX_S) << NTT_LOGC));
-    attr_set = true;
+    attr_devices.fetch_or(1ull << (dev & 63), std::memory_order_release);
   }
   for (uint32_t p = 0; p < npass; p++) {
     uint32_t S = (bits_left + (npass - p) - 1) / (npass - p);

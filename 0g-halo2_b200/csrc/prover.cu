@@ -366,6 +366,7 @@ int zg_pk_last_stage_ms(const zg_pk* pk, float out[8]) {
 }
 
 int zg_pk_commitments(zg_ctx* ctx, const zg_pk* pk, zg_g1_affine* fixed_out, zg_g1_affine* sigma_out) {
+  ZG_ENTER(ctx);
   if (!pk) return ctx->fail(ZG_E_INVALID, "pk_commitments: null pk");
   if (fixed_out) memcpy(fixed_out, pk->fixed_comm.data(), sizeof(G1Affine) * pk->F);
   if (sigma_out) memcpy(sigma_out, pk->sigma_comm.data(), sizeof(G1Affine) * pk->m);
@@ -373,6 +374,7 @@ int zg_pk_commitments(zg_ctx* ctx, const zg_pk* pk, zg_g1_affine* fixed_out, zg_
 }
 
 int zg_pk_load(zg_ctx* ctx, const zg_pk_desc* d, zg_pk** out) {
+  ZG_ENTER(ctx);
   if (!d || !out) return ctx->fail(ZG_E_INVALID, "pk_load: null argument");
   *out = nullptr;
   if (!ctx->srs_loaded || ctx->srs_k != d->k || !ctx->table[0].pts || !ctx->table[1].pts)
@@ -580,6 +582,7 @@ int zg_pk_load(zg_ctx* ctx, const zg_pk_desc* d, zg_pk** out) {
 
 int zg_create_proof(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice, const zg_fr* const* instances, const size_t* instance_lens,
                     zg_rng_fill_fn rng, void* rng_state, uint8_t* proof_out, size_t proof_cap, size_t* proof_len) {
+  ZG_ENTER(ctx);
   if (!pk || !advice || !rng || !proof_out || !proof_len) return ctx->fail(ZG_E_INVALID, "create_proof: null argument");
   const size_t n = pk->n, N = pk->N;
   const uint32_t A = pk->A, I = pk->I, Lk = pk->n_lookups, S = pk->nsets, bf = pk->bf, usable = pk->usable, m = pk->m;
@@ -935,6 +938,7 @@ int zg_evaluate_h(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice_polys, cons
                   const zg_fr* const* lookup_input_polys, const zg_fr* const* lookup_table_polys,
                   const zg_fr* const* lookup_product_polys, const zg_fr* const* perm_product_polys, const zg_fr challenges[4],
                   int divide, zg_fr* h_out) {
+  ZG_ENTER(ctx);
   if (!pk || !challenges || !h_out) return ctx->fail(ZG_E_INVALID, "evaluate_h: null argument");
   const size_t n = pk->n, N = pk->N;
   const uint32_t A = pk->A, I = pk->I, Lk = pk->n_lookups, S = pk->nsets;

@@ -34,6 +34,7 @@ extern "C" {
 // plonk::lookup::prover::permute_expression_pair (without the blinding rows): a, s = compressed input / table
 // expressions over the first `usable` rows.
 int zg_lookup_permute(zg_ctx* ctx, const zg_fr* a, const zg_fr* s, size_t usable, zg_fr* a_perm, zg_fr* s_perm) {
+  ZG_ENTER(ctx);
   if (!a || !s || !a_perm || !s_perm) return ctx->fail(ZG_E_INVALID, "lookup_permute: null argument");
   if (usable == 0) return ZG_OK;
   if (usable >= (1u << 28)) return ctx->fail(ZG_E_INVALID, "lookup_permute: too many rows");
@@ -68,6 +69,7 @@ int zg_lookup_permute(zg_ctx* ctx, const zg_fr* a, const zg_fr* s, size_t usable
 // The grand-product step shared by plonk::permutation::prover::commit and plonk::lookup::prover::commit_product:
 // z[0] = 1, z[i] = z[i-1] * num[i-1] / den[i-1] for i < len (denominators inverted with one batch inversion).
 int zg_grand_product(zg_ctx* ctx, const zg_fr* num, const zg_fr* den, size_t len, zg_fr* z) {
+  ZG_ENTER(ctx);
   if (!num || !den || !z) return ctx->fail(ZG_E_INVALID, "grand_product: null argument");
   if (len == 0) return ZG_OK;
   const size_t col = pad(sizeof(Fr) * len);
@@ -93,6 +95,7 @@ int zg_grand_product(zg_ctx* ctx, const zg_fr* num, const zg_fr* den, size_t len
 
 // ff::BatchInvert::batch_invert (zeros stay zero), in place
 int zg_batch_invert(zg_ctx* ctx, zg_fr* a, size_t n) {
+  ZG_ENTER(ctx);
   if (!a) return ctx->fail(ZG_E_INVALID, "batch_invert: null argument");
   if (n == 0) return ZG_OK;
   int rc = ws_reserve(ctx, ctx->ws_stage, sizeof(Fr) * n);
@@ -109,6 +112,7 @@ int zg_batch_invert(zg_ctx* ctx, zg_fr* a, size_t n) {
 
 // arithmetic::eval_polynomial for `count` polynomials of n coefficients at one point x
 int zg_eval_poly_batch(zg_ctx* ctx, const zg_fr* const* polys, size_t n, size_t count, const zg_fr* x, zg_fr* out) {
+  ZG_ENTER(ctx);
   if (!polys || !x || !out) return ctx->fail(ZG_E_INVALID, "eval_poly_batch: null argument");
   if (count == 0) return ZG_OK;
   if (n == 0 || count > 4096) return ctx->fail(ZG_E_INVALID, "eval_poly_batch: n == 0 or count > 4096");
@@ -141,6 +145,7 @@ int zg_eval_poly_batch(zg_ctx* ctx, const zg_fr* const* polys, size_t n, size_t 
 
 // arithmetic::kate_division: q(X) = (a(X) - a(z)) / (X - z); a has n coefficients, q has n - 1
 int zg_kate_division(zg_ctx* ctx, const zg_fr* a, size_t n, const zg_fr* z, zg_fr* q) {
+  ZG_ENTER(ctx);
   if (!a || !z || !q) return ctx->fail(ZG_E_INVALID, "kate_division: null argument");
   if (n < 2) return ZG_OK;
   const size_t col = pad(sizeof(Fr) * n);

@@ -51,6 +51,9 @@ def parse():
     ap.add_argument("--model", default=os.environ.get("ZG_BENCH_MODEL", "small"), choices=list(MODELS))
     ap.add_argument("--logn", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--inflight", type=int, default=int(os.environ.get("ZG_BENCH_INFLIGHT", "4")),
+                    help="proof workload: independent proofs in flight per GPU (one context + stream + host thread each); "
+                         "a step is one batch of that many proofs")
     return ap.parse_args()
 
 
@@ -234,46 +237,72 @@ def main():
     # ---- set-up (untimed) ----
     if args.workload == "proof":
         import halo2_ref as H                      # test SRS with a known trapdoor + the checker
+        from concurrent.futures import ThreadPoolExecutor
         from zg_b200.prover import ParamsKZG, keygen, advice_to_mont, create_proof_limbs
         from zg_b200.bn254_host import to_limbs
         wnn, img, k = load_model(args.model)
         n = 1 << k
         srs = H.Srs(k, SRS_SECRET)
-        params = ParamsKZG(k, srs.g, srs.g_lagrange)
-        circ0, asm0 = wnn.synthesize(np.zeros(wnn.img_shape(), dtype=np.uint8), k)
-        pk = keygen(ctx, params, circ0.cs, asm0)
         _, asm = wnn.synthesize(img, k)
         outputs = wnn.predict(img)
-        adv_host_t = [torch.from_numpy(a.view(np.int64)).pin_memory() for a in advice_to_mont(ctx, asm.advice)]
-        adv_host = [t.numpy().view(np.uint64) for t in adv_host_t]
-        adv_dev_t = [t.cuda() for t in adv_host_t]
+        inst = [to_limbs(list(outputs))]
 
         class DevCol:                              # quacks like a numpy column for create_proof_limbs
             def __init__(self, t):
                 self.t = t
                 self.ctypes = type("c", (), {"data": t.data_ptr()})
                 self.shape = (t.shape[0],)
-        adv_dev = [DevCol(t) for t in adv_dev_t]
-        inst = [to_limbs(list(outputs))]
-        seedc = [rank * 1000]
 
-        def rng():
-            seedc[0] += 1
-            return zg_b200.lib.XorShift.from_seed(int(seedc[0]).to_bytes(16, "little"))
-        step_dev = lambda: create_proof_limbs(pk, adv_dev, inst, rng())
-        step_e2e = lambda: create_proof_limbs(pk, adv_host, inst, rng())
-        # every measured proof is a real proof: check one against the restated verifier (untimed)
+        class Lane:
+            """one in-flight proof: own context (stream, SRS tables, workspaces) and proving key"""
+            def __init__(self, idx, lane_ctx):
+                self.ctx = lane_ctx
+                params = ParamsKZG(k, srs.g, srs.g_lagrange)
+                circ0, asm0 = wnn.synthesize(np.zeros(wnn.img_shape(), dtype=np.uint8), k)
+                self.pk = keygen(lane_ctx, params, circ0.cs, asm0)
+                self.adv_host_t = [torch.from_numpy(a.view(np.int64)).pin_memory() for a in advice_to_mont(lane_ctx, asm.advice)]
+                self.adv_host = [t.numpy().view(np.uint64) for t in self.adv_host_t]
+                self.adv_dev_t = [t.cuda() for t in self.adv_host_t]
+                self.adv_dev = [DevCol(t) for t in self.adv_dev_t]
+                self.seed = rank * 100000 + idx * 1000
+
+            def rng(self):
+                self.seed += 1
+                return zg_b200.lib.XorShift.from_seed(int(self.seed).to_bytes(16, "little"))
+
+            def prove_dev(self):
+                return create_proof_limbs(self.pk, self.adv_dev, inst, self.rng())
+
+            def prove_e2e(self):
+                return create_proof_limbs(self.pk, self.adv_host, inst, self.rng())
+
+        K = max(1, args.inflight)
+        lane_streams = [stream] + [torch.cuda.Stream() for _ in range(K - 1)]
+        lanes = [Lane(0, ctx)] + [Lane(i, zg_b200.Context(local, lane_streams[i].cuda_stream)) for i in range(1, K)]
+        pk = lanes[0].pk
+        pool = ThreadPoolExecutor(K) if K > 1 else None
+
+        def run_all(method):
+            if pool is None:
+                return [getattr(lanes[0], method)()]
+            return [f.result() for f in [pool.submit(getattr(l, method)) for l in lanes]]
+        step_dev = lambda: run_all("prove_dev")
+        step_e2e = lambda: run_all("prove_e2e")
+        # every measured proof is a real proof: check one per lane against the restated verifier (untimed)
         opk = None
         if rank == 0:
             circ_o, asm_o = wnn.synthesize(np.zeros(wnn.img_shape(), dtype=np.uint8), k)
             opk = H.keygen(srs, circ_o.cs, asm_o)
             assert pk.fixed_commitments == opk.fixed_commitments and pk.perm_commitments == opk.perm_commitments
-            assert H.verify_proof(srs, opk, [outputs], step_e2e()), "GPU proof rejected by the restated verifier"
-        metric, unit, units = "proofs_per_s", "proofs/s", 1
-        h2d, d2h = len(adv_host) * n * 32 + len(outputs) * 32, 3840
+            for pr in step_e2e():
+                assert H.verify_proof(srs, opk, [outputs], pr), "GPU proof rejected by the restated verifier"
+        metric, unit, units = "proofs_per_s", "proofs/s", K
+        h2d, d2h = K * (len(lanes[0].adv_host) * n * 32 + len(outputs) * 32), K * 3840
         dom_kernel = "msm_serial_reduce_kernel<true>"
+        extra["inflight"] = K
         if not args.no_cpu_baseline and rank == 0:
             cpu_fn = lambda: H.create_proof(srs, opk, asm.advice, [outputs], H.XorShiftRng(bytes(range(16))), real_msm=True)
+            cpu_units = 1
     elif args.workload == "msm":
         bases = synth_bases(n)
         ctx.srs_load(logn, bases, None)
@@ -316,9 +345,10 @@ def main():
         tot = 0.0
         for _ in range(steps):
             flush.fill_(1)
+            torch.cuda.synchronize()               # every lane's stream is idle when the start event is recorded
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            step()
+            step()                                  # (multi-lane steps end with every lane's stream drained)
             e1.record()
             e1.synchronize()
             tot += e0.elapsed_time(e1)
@@ -328,15 +358,21 @@ def main():
     for _ in range(warm):
         step_dev()
     torch.cuda.synchronize()
-    l0 = ctx.launch_count
+    all_ctx = [l.ctx for l in lanes] if args.workload == "proof" else [ctx]
+    l0 = sum(c.launch_count for c in all_ctx)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     barrier()
     ms = timed(step_dev, args.steps)
     barrier()
-    launches = ctx.launch_count - l0
-    stage = pk.stage_ms() if args.workload == "proof" else None
+    launches = sum(c.launch_count for c in all_ctx) - l0
+    stage = None
+    if args.workload == "proof":
+        # single-proof latency (one lane alone), the other half of BASELINE's "proofs/s & proof latency"
+        lat_ms = timed(lambda: lanes[0].prove_dev(), args.steps) / args.steps
+        stage = pk.stage_ms()
+        extra["latency_ms_single_proof"] = lat_ms
     # e2e: host buffers through the plain C-ABI call (H2D + compute + D2H of the result)
     for _ in range(2):
         step_e2e()
@@ -384,7 +420,7 @@ def main():
     else:
         imad, c = proof_msm_imad(n, k)
         # MSM share of the step: stages that are MSM-dominated are reported by the library per proof
-        ach = imad / 1e9 / (ms_per_step * 1e-3)
+        ach = units * imad / 1e9 / (ms_per_step * 1e-3)
         roof = {"bound": "int", "achieved": ach, "peak": imad_peak, "unit": "GIMAD/s", "frac": ach / imad_peak,
                 "traffic": None, "peak_source": "measured in this run (zg_bench_int_pipe kind 0)",
                 "kernel": dom_kernel, "window_c": c,
@@ -410,7 +446,7 @@ def main():
             cpu_fn()
             reps += 1
         dt = (time.perf_counter() - t0) / reps
-        out["cpu_baseline"] = {"value": units / dt, "unit": unit, "cores": cores, "kind": "port",
+        out["cpu_baseline"] = {"value": (cpu_units if args.workload == "proof" else units) / dt, "unit": unit, "cores": cores, "kind": "port",
                                "sample": "same workload, %d repetitions on host cores (oracle restatement of the upstream "
                                          "CPU prover, OpenMP; witness synthesis excluded)" % reps}
     print(json.dumps(out))
