@@ -17,6 +17,7 @@
 //      table copies, and the index of every repeated row, from which each row of S' is a direct
 //      look-up (no serial walk).
 #include "lookup.cuh"
+#include "scan.cuh"
 
 namespace zg {
 
@@ -54,83 +55,6 @@ __global__ void k_canonical_iota(const Fr* __restrict__ in, Fr* __restrict__ out
   if (i >= n) return;
   stf(out + i, fp_from_mont(ldf(in + i)));
   idx[i] = i;
-}
-
-// ---- single-CTA exclusive scan of u32 (out has n+1 entries, out[n] = total) -----------------------
-__global__ void __launch_bounds__(1024) k_scan_excl_u32(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ out) {
-  __shared__ uint32_t warp_sums[32];
-  __shared__ uint32_t total_s;
-  const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const uint32_t per = (n + 1023) / 1024;
-  const uint32_t b = min(tid * per, n), e = min(b + per, n);
-  uint32_t sum = 0;
-  for (uint32_t i = b; i < e; i++) sum += in[i];
-  uint32_t incl = sum;
-  for (int d = 1; d < 32; d <<= 1) {
-    uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-    if ((int)lane >= d) incl += o;
-  }
-  if (lane == 31) warp_sums[wid] = incl;
-  __syncthreads();
-  if (wid == 0) {
-    uint32_t ws = warp_sums[lane], wi = ws;
-    for (int d = 1; d < 32; d <<= 1) {
-      uint32_t o = __shfl_up_sync(0xffffffffu, wi, d);
-      if ((int)lane >= d) wi += o;
-    }
-    warp_sums[lane] = wi - ws;
-    if (lane == 31) total_s = wi;
-  }
-  __syncthreads();
-  uint32_t run = warp_sums[wid] + incl - sum;
-  for (uint32_t i = b; i < e; i++) {
-    uint32_t v = in[i];
-    out[i] = run;
-    run += v;
-  }
-  if (tid == 0) out[n] = total_s;
-}
-// three independent scans in one launch (grid = 3): cuts the launch latency of the bookkeeping
-struct Scan3 {
-  const uint32_t* in[3];
-  uint32_t* out[3];
-  uint32_t n;
-};
-__global__ void __launch_bounds__(1024) k_scan3(Scan3 S) {
-  __shared__ uint32_t warp_sums[32];
-  __shared__ uint32_t total_s;
-  const uint32_t* in = S.in[blockIdx.x];
-  uint32_t* out = S.out[blockIdx.x];
-  const uint32_t n = S.n;
-  const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const uint32_t per = (n + 1023) / 1024;
-  const uint32_t b = min(tid * per, n), e = min(b + per, n);
-  uint32_t sum = 0;
-  for (uint32_t i = b; i < e; i++) sum += in[i];
-  uint32_t incl = sum;
-  for (int d = 1; d < 32; d <<= 1) {
-    uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-    if ((int)lane >= d) incl += o;
-  }
-  if (lane == 31) warp_sums[wid] = incl;
-  __syncthreads();
-  if (wid == 0) {
-    uint32_t ws = warp_sums[lane], wi = ws;
-    for (int d = 1; d < 32; d <<= 1) {
-      uint32_t o = __shfl_up_sync(0xffffffffu, wi, d);
-      if ((int)lane >= d) wi += o;
-    }
-    warp_sums[lane] = wi - ws;
-    if (lane == 31) total_s = wi;
-  }
-  __syncthreads();
-  uint32_t run = warp_sums[wid] + incl - sum;
-  for (uint32_t i = b; i < e; i++) {
-    uint32_t v = in[i];
-    out[i] = run;
-    run += v;
-  }
-  if (tid == 0) out[n] = total_s;
 }
 
 // ---- block-parallel LSD radix sort of an index permutation by one key byte ---------------------------
@@ -310,7 +234,12 @@ LookupTable lookup_table_carve(uint8_t* mem, uint32_t n) {
 size_t lookup_workspace_bytes(uint32_t n) {
   size_t nblocks = (n + RS_TILE - 1) / RS_TILE;
   size_t words = 2 * (size_t)n + 2 * (256 * nblocks + 8) + 9 * ((size_t)n + 8);
-  return words * 4 + (size_t)n * sizeof(Fr) + lookup_table_bytes(n) + 4096;
+  return words * 4 + (size_t)n * sizeof(Fr) + lookup_table_bytes(n) + 4096 + scan_scratch_words(n + 8, 3) * 4;
+}
+// tile sums of the multi-CTA scans: the last bytes of the workspace
+static uint32_t* lookup_scan_scratch(uint8_t* ws, uint32_t n) {
+  size_t off = lookup_workspace_bytes(n) - scan_scratch_words(n + 8, 3) * 4;
+  return (uint32_t*)(ws + (off & ~(size_t)15));
 }
 
 LookupTable lookup_workspace_table(uint8_t* ws, uint32_t n) {
@@ -338,12 +267,20 @@ int lookup_sort_table(const Fr* s_mont, uint32_t usable, const LookupTable& out,
   uint32_t* o = idx1;
   for (uint32_t byte = full_sort ? 0 : 24; byte < 32; byte++) {
     k_rs_hist<<<nblocks, RS_THREADS, 0, st>>>(Tcan, in, n, byte, hist); lc++;
-    k_scan_excl_u32<<<1, 1024, 0, st>>>(hist, 256 * nblocks, offs); lc++;
+    {
+      ScanJobs sj{};
+      sj.in[0] = hist; sj.out[0] = offs;
+      scan_excl_u32(sj, 1, 256 * nblocks, lookup_scan_scratch(ws, n), st, lc);
+    }
     k_rs_scatter<<<nblocks, RS_THREADS, 0, st>>>(Tcan, in, n, byte, offs, o); lc++;
     uint32_t* tmp = in; in = o; o = tmp;
   }
   k_check_unique<<<nb(n), 256, 0, st>>>(Tcan, in, n, flag, unsorted_flag_dev); lc++;
-  k_scan_excl_u32<<<1, 1024, 0, st>>>(flag, n, upos); lc++;
+  {
+    ScanJobs sj{};
+    sj.in[0] = flag; sj.out[0] = upos;
+    scan_excl_u32(sj, 1, n, lookup_scan_scratch(ws, n), st, lc);
+  }
   k_collect_unique<<<nb(n), 256, 0, st>>>(Tcan, in, flag, upos, n, out.U, out.ustart, out.D); lc++;
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
@@ -367,12 +304,11 @@ int lookup_permute(const Fr* a_mont, uint32_t usable, const LookupTable& tab, Fr
   cudaMemsetAsync(cntA, 0, (size_t)2 * (n + 8) * 4, st);
   k_rank_inputs<<<nb(n), 256, 0, st>>>(a_mont, n, tab.U, tab.D, rank, cntA, missing_flag_dev); lc++;
   k_first_left<<<nb(n), 256, 0, st>>>(cntA, tab.ustart, tab.D, n, first, left); lc++;
-  Scan3 S;
-  S.in[0] = cntA; S.out[0] = startA;
-  S.in[1] = left; S.out[1] = lstart;
-  S.in[2] = first; S.out[2] = dcount;
-  S.n = n;
-  k_scan3<<<3, 1024, 0, st>>>(S); lc++;
+  ScanJobs sj{};
+  sj.in[0] = cntA; sj.out[0] = startA;
+  sj.in[1] = left; sj.out[1] = lstart;
+  sj.in[2] = first; sj.out[2] = dcount;
+  scan_excl_u32(sj, 3, n, lookup_scan_scratch(ws, n), st, lc);
   k_place<<<nb(n), 256, 0, st>>>(rank, n, tab.U, tab.D, startA, cursorA, dcount, lstart, pa, ps); lc++;
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

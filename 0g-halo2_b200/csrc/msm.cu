@@ -26,6 +26,7 @@
 #endif
 #include <cstdlib>
 #include "msm.cuh"
+#include "scan.cuh"
 
 namespace zg {
 
@@ -90,8 +91,7 @@ __device__ __forceinline__ int32_t msm_digit(const uint32_t (&s)[8], uint32_t w,
 template <bool SCATTER>
 __global__ void msm_digits_kernel(const Fr* __restrict__ scalars, size_t stride, uint32_t n_used,
                                   uint32_t n_tab, uint32_t c, uint32_t W, uint32_t NB,
-                                  uint32_t* __restrict__ counters, uint32_t* __restrict__ keys,
-                                  uint32_t* __restrict__ vals) {
+                                  uint32_t* __restrict__ counters, uint2* __restrict__ entries) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t m = blockIdx.y;
   if (i >= n_used) return;
@@ -107,67 +107,24 @@ __global__ void msm_digits_kernel(const Fr* __restrict__ scalars, size_t stride,
     uint32_t key = m * NB + (mag - 1);
     if (SCATTER) {
       uint32_t pos = atomicAdd(&counters[key], 1u);
-      keys[pos] = key;
-      vals[pos] = (w * n_tab + i) | (neg << 31);
+      entries[pos] = make_uint2(key, (w * n_tab + i) | (neg << 31));   // one 8-byte store per digit
     } else {
       atomicAdd(&counters[key], 1u);
     }
   }
 }
 
-// single-CTA exclusive scan of `cnt` counters: offsets[0..cnt] and a cursor copy
-__global__ void __launch_bounds__(1024) msm_scan_kernel(const uint32_t* __restrict__ hist, uint32_t cnt,
-                                                        uint32_t* __restrict__ offsets,
-                                                        uint32_t* __restrict__ cursor) {
-  __shared__ uint32_t warp_sums[32];
-  __shared__ uint32_t carry_s;
-  const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const uint32_t per = (cnt + 1023) / 1024;
-  const uint32_t b = tid * per, e = min(b + per, cnt);
-  uint32_t sum = 0;
-  for (uint32_t i = b; i < e; i++) sum += hist[i];
-  // block exclusive scan of the per-thread sums
-  uint32_t incl = sum;
-  for (int d = 1; d < 32; d <<= 1) {
-    uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-    if ((int)lane >= d) incl += o;
-  }
-  if (lane == 31) warp_sums[wid] = incl;
-  __syncthreads();
-  if (wid == 0) {
-    uint32_t ws = warp_sums[lane];
-    uint32_t wi = ws;
-    for (int d = 1; d < 32; d <<= 1) {
-      uint32_t o = __shfl_up_sync(0xffffffffu, wi, d);
-      if ((int)lane >= d) wi += o;
-    }
-    warp_sums[lane] = wi - ws;
-    if (lane == 31) carry_s = wi;
-  }
-  __syncthreads();
-  uint32_t run = warp_sums[wid] + incl - sum;
-  for (uint32_t i = b; i < e; i++) {
-    offsets[i] = run;
-    cursor[i] = run;
-    run += hist[i];
-  }
-  if (tid == 0) offsets[cnt] = carry_s;
-}
-
 // ---- serial segmented reduction over the sorted list -----------------------------------
-// LEVEL0: entries are (key, table index|sign) and are gathered from the affine window table.
-// !LEVEL0: entries are (key, XYZZ partial sum).
+// Level 0 of the accumulation: entries are packed (bucket key, table index | sign) pairs, gathered from the
+// affine window table.  (The XYZZ-partial levels live in msm_tail.cu.)
 // Thread t owns entries [t*K, t*K+K).  Runs strictly inside the chunk go straight to their bucket
 // (nobody else holds that key); the first and last runs go to partial slots 2t, 2t+1.
-template <bool LEVEL0>
-__global__ void __launch_bounds__(128) msm_serial_reduce_kernel(
-    const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
-    const G1Xyzz* __restrict__ pts_in, const uint32_t* __restrict__ count_ptr, uint32_t count_static,
-    const G1Affine* __restrict__ table, uint32_t K, G1Xyzz* __restrict__ buckets,
-    uint32_t* __restrict__ pkeys, G1Xyzz* __restrict__ ppts, uint32_t nthreads) {
+__global__ void __launch_bounds__(128) msm_accumulate_kernel(
+    const uint2* __restrict__ entries, const uint32_t* __restrict__ count_ptr, const G1Affine* __restrict__ table,
+    uint32_t K, G1Xyzz* __restrict__ buckets, uint32_t* __restrict__ pkeys, G1Xyzz* __restrict__ ppts, uint32_t nthreads) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nthreads) return;
-  const uint32_t L = count_ptr ? *count_ptr : count_static;
+  const uint32_t L = *count_ptr;
   const uint64_t start64 = (uint64_t)t * K;
   if (start64 >= L) {
     pkeys[2 * t] = MSM_INVALID_KEY;
@@ -176,22 +133,13 @@ __global__ void __launch_bounds__(128) msm_serial_reduce_kernel(
   }
   const uint32_t start = (uint32_t)start64;
   const uint32_t end = (start64 + K < L) ? start + K : L;
-  uint32_t cur = keys[start];
-  uint32_t e = start;
-  if (!LEVEL0) {
-    // the list may end in invalid slots
-    if (cur == MSM_INVALID_KEY) {
-      pkeys[2 * t] = MSM_INVALID_KEY;
-      pkeys[2 * t + 1] = MSM_INVALID_KEY;
-      return;
-    }
-  }
+  uint2 ent = __ldg(entries + start);
+  uint32_t cur = ent.x;
   G1Xyzz acc = xyzz_identity();
   uint32_t nruns = 0;
-  for (; e < end; e++) {
-    uint32_t k = keys[e];
-    if (!LEVEL0 && k == MSM_INVALID_KEY) break;
-    if (k != cur) {
+  for (uint32_t e = start; e < end; e++) {
+    const uint2 nxt = (e + 1 < end) ? __ldg(entries + e + 1) : ent;   // prefetch the next pair
+    if (ent.x != cur) {
       if (nruns == 0) {
         pkeys[2 * t] = cur;
         ppts[2 * t] = acc;
@@ -199,20 +147,16 @@ __global__ void __launch_bounds__(128) msm_serial_reduce_kernel(
         buckets[cur] = acc;
       }
       nruns++;
-      cur = k;
+      cur = ent.x;
       acc = xyzz_identity();
     }
-    if (LEVEL0) {
-      uint32_t v = vals[e];
-      Fq x, y;
-      ld_fq2(table + (v & 0x7fffffffu), x, y);
-      if (fp_is_zero(x) && fp_is_zero(y)) continue;
-      if (v >> 31) y = fp_neg(y);
+    Fq x, y;
+    ld_fq2(table + (ent.y & 0x7fffffffu), x, y);
+    if (!(fp_is_zero(x) && fp_is_zero(y))) {
+      if (ent.y >> 31) y = fp_neg(y);
       xyzz_madd(acc, x, y);
-    } else {
-      G1Xyzz p = pts_in[e];
-      xyzz_add(acc, p);
     }
+    ent = nxt;
   }
   if (nruns == 0) {
     pkeys[2 * t] = cur;
@@ -263,8 +207,8 @@ MsmWorkspaceLayout msm_workspace_layout(uint32_t n, uint32_t c, uint32_t W, uint
   l.off_hist = o; o = align_up(o + (cnt + 1) * 4);
   l.off_cursor = o; o = align_up(o + (cnt + 1) * 4);
   l.off_offsets = o; o = align_up(o + (cnt + 1) * 4);
-  l.off_keys = o; o = align_up(o + (size_t)l.L_max * 4);
-  l.off_vals = o; o = align_up(o + (size_t)l.L_max * 4);
+  l.off_keys = o; o = align_up(o + (size_t)l.L_max * 8);   // packed (key, val) entries
+  l.off_vals = o;
   l.off_buckets = o; o = align_up(o + cnt * sizeof(G1Xyzz));
   l.off_pkeys_a = o; o = align_up(o + (size_t)l.slots_a * 4);
   l.off_ppts_a = o; o = align_up(o + (size_t)l.slots_a * sizeof(G1Xyzz));
@@ -274,6 +218,7 @@ MsmWorkspaceLayout msm_workspace_layout(uint32_t n, uint32_t c, uint32_t W, uint
   l.off_s1 = o; o = align_up(o + (size_t)M * n1 * sizeof(G1Xyzz));
   l.off_t1 = o; o = align_up(o + (size_t)M * n1 * sizeof(G1Xyzz));
   l.off_l2 = o; o = align_up(o + (size_t)M * 3 * ((n1 + 31) / 32) * sizeof(G1Xyzz));
+  l.off_scan = o; o = align_up(o + scan_scratch_words((uint32_t)cnt, 1) * 4);
   l.bytes = o;
   return l;
 }
@@ -291,8 +236,7 @@ cudaError_t msm_run(const MsmTable& tb, const Fr* scalars, size_t stride, uint32
   uint32_t* hist = (uint32_t*)(ws + l.off_hist);
   uint32_t* cursor = (uint32_t*)(ws + l.off_cursor);
   uint32_t* offsets = (uint32_t*)(ws + l.off_offsets);
-  uint32_t* keys = (uint32_t*)(ws + l.off_keys);
-  uint32_t* vals = (uint32_t*)(ws + l.off_vals);
+  uint2* entries = (uint2*)(ws + l.off_keys);
   G1Xyzz* buckets = (G1Xyzz*)(ws + l.off_buckets);
   uint32_t* pk[2] = {(uint32_t*)(ws + l.off_pkeys_a), (uint32_t*)(ws + l.off_pkeys_b)};
   G1Xyzz* pp[2] = {(G1Xyzz*)(ws + l.off_ppts_a), (G1Xyzz*)(ws + l.off_ppts_b)};
@@ -304,17 +248,19 @@ cudaError_t msm_run(const MsmTable& tb, const Fr* scalars, size_t stride, uint32
   dim3 dgrid((n_used + 127) / 128, M);
   launches++;
   msm_digits_kernel<false><<<dgrid, 128, 0, st>>>(scalars, stride, n_used, tb.n, tb.c, tb.W, NB, hist,
-                                                  nullptr, nullptr);
-  launches++;
-  msm_scan_kernel<<<1, 1024, 0, st>>>(hist, cnt, offsets, cursor);
+                                                  nullptr);
+  {
+    ScanJobs sj{};
+    sj.in[0] = hist; sj.out[0] = offsets; sj.out2[0] = cursor;
+    scan_excl_u32(sj, 1, cnt, (uint32_t*)(ws + l.off_scan), st, LaunchCounter{&launches});
+  }
   launches++;
   msm_digits_kernel<true><<<dgrid, 128, 0, st>>>(scalars, stride, n_used, tb.n, tb.c, tb.W, NB, cursor,
-                                                 keys, vals);
+                                                 entries);
   // level 0: serial chunks over the sorted list (length offsets[cnt], read on device)
   uint32_t T0 = l.T0;
   launches++;
-  msm_serial_reduce_kernel<true><<<(T0 + 127) / 128, 128, 0, st>>>(
-      keys, vals, nullptr, offsets + cnt, 0, tb.pts, l.K0, buckets, pk[0], pp[0], T0);
+  msm_accumulate_kernel<<<(T0 + 127) / 128, 128, 0, st>>>(entries, offsets + cnt, tb.pts, l.K0, buckets, pk[0], pp[0], T0);
   uint32_t slots = 2 * T0;
   int cur = 0;
   if (slots > 8192) {

@@ -298,7 +298,7 @@ def main():
                 assert H.verify_proof(srs, opk, [outputs], pr), "GPU proof rejected by the restated verifier"
         metric, unit, units = "proofs_per_s", "proofs/s", K
         h2d, d2h = K * (len(lanes[0].adv_host) * n * 32 + len(outputs) * 32), K * 3840
-        dom_kernel = "msm_serial_reduce_kernel<true>"
+        dom_kernel = "msm_accumulate_kernel"
         extra["inflight"] = K
         if not args.no_cpu_baseline and rank == 0:
             cpu_fn = lambda: H.create_proof(srs, opk, asm.advice, [outputs], H.XorShiftRng(bytes(range(16))), real_msm=True)
@@ -314,7 +314,7 @@ def main():
         step_e2e = lambda: ctx.msm(0, sc_host)
         metric, unit, units = "msm_points_per_s", "points/s", n
         h2d, d2h = n * 32, 96
-        dom_kernel = "msm_serial_reduce_kernel<true>"
+        dom_kernel = "msm_accumulate_kernel"
         if not args.no_cpu_baseline and rank == 0:
             import cpu_ref
             cpu_fn = lambda: cpu_ref.best_multiexp(sc_host, bases)
