@@ -135,7 +135,13 @@ int zg_ctx_create(int device, void* stream, zg_ctx** out) {
     }
     ctx->own_stream = true;
   }
-  if (cudaMalloc(&ctx->d_msm_out, sizeof(G1Jac) * 64) != cudaSuccess) {
+  int least = 0, greatest = 0;
+  cudaDeviceGetStreamPriorityRange(&least, &greatest);
+  if (cudaMalloc(&ctx->d_msm_out, sizeof(G1Jac) * 64) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&ctx->hp, cudaStreamNonBlocking, greatest) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&ctx->aux, cudaStreamNonBlocking, least) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) {
     delete ctx;
     return ZG_E_CUDA;
   }
@@ -156,6 +162,10 @@ void zg_ctx_destroy(zg_ctx* ctx) {
   if (ctx->ws_ntt.p) cudaFree(ctx->ws_ntt.p);
   if (ctx->ws_stage.p) cudaFree(ctx->ws_stage.p);
   if (ctx->d_msm_out) cudaFree(ctx->d_msm_out);
+  if (ctx->hp) { cudaStreamSynchronize(ctx->hp); cudaStreamDestroy(ctx->hp); }
+  if (ctx->aux) { cudaStreamSynchronize(ctx->aux); cudaStreamDestroy(ctx->aux); }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

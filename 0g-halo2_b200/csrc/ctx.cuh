@@ -35,6 +35,10 @@ struct zg_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  // create_proof runs its critical path (MSM -> transcript) on `hp` (highest priority) and the transforms nobody waits
+  // for until the quotient stage on `aux` (lowest priority); both are forked from / joined to `stream` with events
+  cudaStream_t hp = nullptr, aux = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::string err;
   uint64_t launches = 0;
 

@@ -24,6 +24,7 @@
 #ifndef ZG_MSM_INLINE_MUL
 #define ZG_FP_MUL_NOINLINE 1
 #endif
+#include <atomic>
 #include <cstdlib>
 #include "msm.cuh"
 #include "scan.cuh"
@@ -88,28 +89,74 @@ __device__ __forceinline__ int32_t msm_digit(const uint32_t (&s)[8], uint32_t w,
   return (int32_t)v;
 }
 
+// Counting sort of the digits by bucket WITHOUT global atomics: CTA (j, m) owns scalars [j*chunk, (j+1)*chunk) of
+// MSM m and keeps that MSM's 2^(c-1) bucket counters in shared memory.
+//   count pass   : shared-memory histogram of the chunk, flushed to H[m][j][bucket]
+//   offsets      : msm_hist_total / scan / msm_hist_offsets turn H into the first output slot of (m, bucket, j)
+//   scatter pass : the CTA reloads its slice of H as cursors and writes packed (bucket key, table index | sign)
+// The global-atomic version spent 3.6 ms of a 30 ms k = 17 proof here (profiles/r01_launches_proof_large_a.csv).
+constexpr int DG_THREADS = 512;
+
 template <bool SCATTER>
-__global__ void msm_digits_kernel(const Fr* __restrict__ scalars, size_t stride, uint32_t n_used,
-                                  uint32_t n_tab, uint32_t c, uint32_t W, uint32_t NB,
-                                  uint32_t* __restrict__ counters, uint2* __restrict__ entries) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t m = blockIdx.y;
-  if (i >= n_used) return;
-  Fr sc = scalars[(size_t)m * stride + i];
-  if (fp_is_zero(sc)) return;
-  Fr can = fp_from_mont(sc);
-  uint32_t carry = 0;
-  for (uint32_t w = 0; w < W; w++) {
-    int32_t d = msm_digit(can.v, w, c, carry);
-    if (d == 0) continue;
-    uint32_t neg = d < 0;
-    uint32_t mag = neg ? (uint32_t)(-d) : (uint32_t)d;
-    uint32_t key = m * NB + (mag - 1);
-    if (SCATTER) {
-      uint32_t pos = atomicAdd(&counters[key], 1u);
-      entries[pos] = make_uint2(key, (w * n_tab + i) | (neg << 31));   // one 8-byte store per digit
-    } else {
-      atomicAdd(&counters[key], 1u);
+__global__ void __launch_bounds__(DG_THREADS) msm_digits_kernel(const Fr* __restrict__ scalars, size_t stride, uint32_t n_used,
+                                                                uint32_t n_tab, uint32_t c, uint32_t W, uint32_t NB, uint32_t chunk,
+                                                                uint32_t* __restrict__ H, uint2* __restrict__ entries) {
+  extern __shared__ uint32_t dg_sh[];   // NB counters / cursors
+  const uint32_t m = blockIdx.y, j = blockIdx.x, J = gridDim.x;
+  uint32_t* Hb = H + ((size_t)m * J + j) * NB;
+  for (uint32_t b = threadIdx.x; b < NB; b += DG_THREADS) dg_sh[b] = SCATTER ? Hb[b] : 0u;
+  __syncthreads();
+  const uint32_t lo = j * chunk;
+  const uint32_t hi = min(lo + chunk, n_used);
+  for (uint32_t i = lo + threadIdx.x; i < hi; i += DG_THREADS) {
+    Fr sc = scalars[(size_t)m * stride + i];
+    if (fp_is_zero(sc)) continue;
+    Fr can = fp_from_mont(sc);
+    uint32_t carry = 0;
+    for (uint32_t w = 0; w < W; w++) {
+      int32_t d = msm_digit(can.v, w, c, carry);
+      if (d == 0) continue;
+      uint32_t neg = d < 0;
+      uint32_t mag = neg ? (uint32_t)(-d) : (uint32_t)d;
+      uint32_t pos = atomicAdd(&dg_sh[mag - 1], 1u);
+      if (SCATTER) entries[pos] = make_uint2(m * NB + (mag - 1), (w * n_tab + i) | (neg << 31));
+    }
+  }
+  if (!SCATTER) {
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < NB; b += DG_THREADS) Hb[b] = dg_sh[b];
+  }
+}
+
+// total[m*NB + b] = sum_j H[m][j][b]
+__global__ void msm_hist_total_kernel(const uint32_t* __restrict__ H, uint32_t J, uint32_t NB, uint32_t cnt,
+                                      uint32_t* __restrict__ total) {
+  uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= cnt) return;
+  const uint32_t m = idx / NB, b = idx - m * NB;
+  const uint32_t* p = H + (size_t)m * J * NB + b;
+  uint32_t s = 0;
+#pragma unroll 8
+  for (uint32_t j = 0; j < J; j++) s += __ldg(p + (size_t)j * NB);
+  total[idx] = s;
+}
+// H[m][j][b] <- offsets[m*NB + b] + sum_{j' < j} H[m][j'][b]
+// (loads are issued eight at a time: the in-place update would otherwise serialise on one load latency per chunk)
+__global__ void msm_hist_offsets_kernel(uint32_t* __restrict__ H, uint32_t J, uint32_t NB, uint32_t cnt,
+                                        const uint32_t* __restrict__ offsets) {
+  uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= cnt) return;
+  const uint32_t m = idx / NB, b = idx - m * NB;
+  uint32_t* p = H + (size_t)m * J * NB + b;
+  uint32_t run = offsets[idx];
+  for (uint32_t j0 = 0; j0 < J; j0 += 8) {
+    uint32_t v[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) v[u] = (j0 + u < J) ? p[(size_t)(j0 + u) * NB] : 0u;
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      if (j0 + u < J) p[(size_t)(j0 + u) * NB] = run;
+      run += v[u];
     }
   }
 }
@@ -204,8 +251,17 @@ MsmWorkspaceLayout msm_workspace_layout(uint32_t n, uint32_t c, uint32_t W, uint
   l.slots_b = 2 * (t1s > t1w ? t1s : t1w);
   size_t o = 0;
   size_t cnt = (size_t)M * l.NB;
-  l.off_hist = o; o = align_up(o + (cnt + 1) * 4);
-  l.off_cursor = o; o = align_up(o + (cnt + 1) * 4);
+  // digit-sort geometry: J chunks per MSM, about four CTAs per SM over the whole batch
+  uint32_t J = (592 + M - 1) / M;
+  // a CTA zeroes and flushes all NB counters: keep its chunk at >= NB/8 scalars (>= 2 W digits per counter)
+  uint32_t min_chunk = l.NB / 8 > 256 ? l.NB / 8 : 256;
+  uint32_t jmax = (n + min_chunk - 1) / min_chunk;
+  if (J > jmax) J = jmax;
+  if (J < 1) J = 1;
+  l.chunk = (n + J - 1) / J;
+  l.J = (n + l.chunk - 1) / l.chunk;
+  l.off_hist = o; o = align_up(o + (cnt + 1) * 4);                 // per-bucket totals
+  l.off_cursor = o; o = align_up(o + (size_t)cnt * l.J * 4);       // H[m][j][bucket]
   l.off_offsets = o; o = align_up(o + (cnt + 1) * 4);
   l.off_keys = o; o = align_up(o + (size_t)l.L_max * 8);   // packed (key, val) entries
   l.off_vals = o;
@@ -232,6 +288,17 @@ cudaError_t msm_precompute_table(const G1Affine* base, uint32_t n, uint32_t c, u
 cudaError_t msm_run(const MsmTable& tb, const Fr* scalars, size_t stride, uint32_t n_used, uint32_t M,
                     G1Jac* out, uint8_t* ws, const MsmWorkspaceLayout& l, cudaStream_t st, uint64_t* nl) {
   uint64_t launches = 0;
+  {
+    // up to 2^15 bucket counters (c = 16) in shared memory: opt in once per device
+    static std::atomic<uint64_t> attr_devices{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(attr_devices.load(std::memory_order_acquire) >> (dev & 63) & 1)) {
+      cudaFuncSetAttribute(msm_digits_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+      cudaFuncSetAttribute(msm_digits_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+      attr_devices.fetch_or(1ull << (dev & 63), std::memory_order_release);
+    }
+  }
   const uint32_t NB = l.NB, cnt = M * NB;
   uint32_t* hist = (uint32_t*)(ws + l.off_hist);
   uint32_t* cursor = (uint32_t*)(ws + l.off_cursor);
@@ -243,20 +310,24 @@ cudaError_t msm_run(const MsmTable& tb, const Fr* scalars, size_t stride, uint32
   G1Xyzz* s1 = (G1Xyzz*)(ws + l.off_s1);
   G1Xyzz* t1 = (G1Xyzz*)(ws + l.off_t1);
 
-  cudaMemsetAsync(hist, 0, (size_t)(cnt + 1) * 4, st);
   cudaMemsetAsync(buckets, 0, (size_t)cnt * sizeof(G1Xyzz), st);
-  dim3 dgrid((n_used + 127) / 128, M);
+  // the layout was sized for n_used == l.n; fewer scalars simply leave trailing chunks empty
+  uint32_t* H = cursor;
+  dim3 dgrid(l.J, M);
+  const size_t dsm = (size_t)NB * 4;
   launches++;
-  msm_digits_kernel<false><<<dgrid, 128, 0, st>>>(scalars, stride, n_used, tb.n, tb.c, tb.W, NB, hist,
-                                                  nullptr);
+  msm_digits_kernel<false><<<dgrid, DG_THREADS, dsm, st>>>(scalars, stride, n_used, tb.n, tb.c, tb.W, NB, l.chunk, H, nullptr);
+  launches++;
+  msm_hist_total_kernel<<<(cnt + 255) / 256, 256, 0, st>>>(H, l.J, NB, cnt, hist);
   {
     ScanJobs sj{};
-    sj.in[0] = hist; sj.out[0] = offsets; sj.out2[0] = cursor;
+    sj.in[0] = hist; sj.out[0] = offsets;
     scan_excl_u32(sj, 1, cnt, (uint32_t*)(ws + l.off_scan), st, LaunchCounter{&launches});
   }
   launches++;
-  msm_digits_kernel<true><<<dgrid, 128, 0, st>>>(scalars, stride, n_used, tb.n, tb.c, tb.W, NB, cursor,
-                                                 entries);
+  msm_hist_offsets_kernel<<<(cnt + 255) / 256, 256, 0, st>>>(H, l.J, NB, cnt, offsets);
+  launches++;
+  msm_digits_kernel<true><<<dgrid, DG_THREADS, dsm, st>>>(scalars, stride, n_used, tb.n, tb.c, tb.W, NB, l.chunk, H, entries);
   // level 0: serial chunks over the sorted list (length offsets[cnt], read on device)
   uint32_t T0 = l.T0;
   launches++;

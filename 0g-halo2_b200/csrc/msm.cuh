@@ -22,6 +22,7 @@ struct MsmWorkspaceLayout {
   size_t off_hist, off_cursor, off_offsets, off_keys, off_vals, off_buckets;
   size_t off_pkeys_a, off_ppts_a, off_pkeys_b, off_ppts_b, off_s1, off_t1, off_l2, off_scan;
   uint32_t L_max, K0, T0, slots_a, slots_b, NB, M;
+  uint32_t J, chunk;   // digit sort: J chunks of `chunk` scalars per MSM
 };
 MsmWorkspaceLayout msm_workspace_layout(uint32_t n, uint32_t c, uint32_t W, uint32_t M);
 

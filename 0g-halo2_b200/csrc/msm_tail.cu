@@ -172,8 +172,61 @@ __device__ __forceinline__ G1Xyzz warp_sum(G1Xyzz y, uint32_t lane) {
   return y;
 }
 
-// level 1: warp g of MSM m reduces buckets [32g, 32g+32) to (s1, t1)
+// level 1: group g of MSM m = buckets [32g, 32g+32) -> s1[g] = sum X_l, t1[g] = sum l * X_l.
+// Four lanes per group, eight consecutive buckets per lane with the running-sum trick (15 serial additions and no
+// idle lanes), then two shuffle steps merge the four (s, t) pairs: t = t_a + t_b + width * s_b.
+// (The one-bucket-per-lane version ran 10 additions on all 32 lanes for 31 useful ones and was throughput-bound at
+// k = 17: 232 us per batch of 8 MSMs, profiles/r01_launches_proof_large_a.csv.)
+__device__ __forceinline__ G1Xyzz xyzz_mul_pow2(G1Xyzz p, int log2w) {
+#pragma unroll 1
+  for (int i = 0; i < log2w; i++) p = xyzz_double(p);
+  return p;
+}
 __global__ void __launch_bounds__(128) msm_bucket_l1_kernel(const G1Xyzz* __restrict__ buckets, uint32_t NB,
+                                                            uint32_t n1, G1Xyzz* __restrict__ s1,
+                                                            G1Xyzz* __restrict__ t1) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;   // eighth-of-a-warp index: buckets [8q, 8q+8)
+  const uint32_t m = blockIdx.y;
+  const uint32_t g = q >> 2, sub = q & 3;
+  const bool live = g < n1;                                    // whole warps stay in the shuffles
+  const G1Xyzz* B = buckets + (size_t)m * NB + (size_t)q * 8;
+  G1Xyzz run = xyzz_identity(), acc = xyzz_identity();
+  if (live) {
+#pragma unroll 1
+    for (int l = 7; l >= 1; l--) {
+      if ((size_t)q * 8 + l < NB) {
+        G1Xyzz x = B[l];
+        xyzz_add(run, x);
+      }
+      xyzz_add(acc, run);                                      // acc = sum_{l >= 1} l * X_l
+    }
+    if ((size_t)q * 8 < NB) {
+      G1Xyzz x = B[0];
+      xyzz_add(run, x);                                        // run = sum X_l
+    }
+  }
+  // merge pairs: (sub 0, 1) and (2, 3) with width 8, then (0, 2) with width 16
+#pragma unroll 1
+  for (int step = 0; step < 2; step++) {
+    const int d = 1 << step;
+    G1Xyzz so = shfl_down_xyzz(run, d);
+    G1Xyzz to = shfl_down_xyzz(acc, d);
+    if ((sub & (2 * d - 1)) == 0) {
+      xyzz_add(run, so);
+      xyzz_add(acc, to);
+      so = xyzz_mul_pow2(so, 3 + step);
+      xyzz_add(acc, so);
+    }
+  }
+  if (live && sub == 0) {
+    s1[(size_t)m * n1 + g] = run;
+    t1[(size_t)m * n1 + g] = acc;
+  }
+}
+
+// level 1, latency-optimal form (one bucket per lane, 10 serial additions, 32 lanes busy for 31 useful sums): used
+// when the batch has few buckets and the kernel is bound by the addition chain, not by throughput
+__global__ void __launch_bounds__(128) msm_bucket_l1_warp_kernel(const G1Xyzz* __restrict__ buckets, uint32_t NB,
                                                             uint32_t n1, G1Xyzz* __restrict__ s1,
                                                             G1Xyzz* __restrict__ t1) {
   const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -260,7 +313,12 @@ void msm_tail_warp_level(const uint32_t* keys, const G1Xyzz* pts, uint32_t slots
 void msm_tail_buckets(const G1Xyzz* buckets, uint32_t NB, uint32_t M, G1Xyzz* s1, G1Xyzz* t1, G1Xyzz* l2out, G1Jac* out,
                       cudaStream_t st) {
   uint32_t n1 = (NB + 31) / 32;
-  msm_bucket_l1_kernel<<<dim3((n1 + 3) / 4, M), 128, 0, st>>>(buckets, NB, n1, s1, t1);
+  // <= 2 warps per SM sub-partition in the one-bucket-per-lane form: the chain of 10 additions decides; beyond that
+  // the 8-buckets-per-lane form (4x fewer lane-additions) wins
+  if ((uint64_t)n1 * M <= 2 * 592)
+    msm_bucket_l1_warp_kernel<<<dim3((n1 + 3) / 4, M), 128, 0, st>>>(buckets, NB, n1, s1, t1);
+  else
+    msm_bucket_l1_kernel<<<dim3((4 * n1 + 127) / 128, M), 128, 0, st>>>(buckets, NB, n1, s1, t1);
   uint32_t nw = (n1 + 31) / 32;
   msm_bucket_l2_kernel<<<dim3(nw, M), 32, 0, st>>>(s1, t1, n1, l2out);
   msm_finish_kernel<<<M, 96, 0, st>>>(l2out, nw, out);

@@ -265,6 +265,25 @@ static int commit_batch(zg_ctx* ctx, int basis, const Fr* cols, size_t stride, s
 }
 
 
+// Work enqueued while an AuxScope is alive goes to the context's low-priority stream; it starts after everything
+// enqueued on the proof's main stream so far (fork) and is awaited by join_aux before the quotient stage.
+struct AuxScope {
+  zg_ctx* ctx;
+  cudaStream_t saved;
+  cudaError_t err;
+  explicit AuxScope(zg_ctx* c) : ctx(c), saved(c->stream) {
+    err = cudaEventRecord(c->ev_fork, c->stream);
+    if (err == cudaSuccess) err = cudaStreamWaitEvent(c->aux, c->ev_fork, 0);
+    c->stream = c->aux;
+  }
+  ~AuxScope() { ctx->stream = saved; }
+};
+static cudaError_t join_aux(zg_ctx* ctx) {
+  cudaError_t e = cudaEventRecord(ctx->ev_join, ctx->aux);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
+  return e;
+}
+
 // environment of the RPN programs over the 2^k domain (ext = false) or the extended coset (ext = true)
 static ExprEnv make_env(const zg_pk* pk, bool ext) {
   ExprEnv e;
@@ -280,23 +299,44 @@ static ExprEnv make_env(const zg_pk* pk, bool ext) {
   return e;
 }
 
+// extended-coset forms of the per-proof polynomials (coefficient form -> zeta * <omega_ext>), in the batches the prover
+// builds them: advice + instance, lookup permuted [a | s], product polynomials (permutation z, lookup z)
+static int coset_advice_instance(zg_ctx* ctx, zg_pk* pk) {
+  int rc = zg_coeff_to_extended_dev(ctx, (const zg_fr*)pk->adv_polys, pk->n, pk->k, pk->ext_k, (zg_fr*)pk->adv_cosets, pk->N, pk->A);
+  if (rc || !pk->I) return rc;
+  return zg_coeff_to_extended_dev(ctx, (const zg_fr*)pk->inst_polys, pk->n, pk->k, pk->ext_k, (zg_fr*)pk->inst_cosets, pk->N, pk->I);
+}
+static int coset_lookup_permuted(zg_ctx* ctx, zg_pk* pk) {
+  if (!pk->n_lookups) return ZG_OK;
+  return zg_coeff_to_extended_dev(ctx, (const zg_fr*)pk->pa_poly, pk->n, pk->k, pk->ext_k, (zg_fr*)pk->lk_cosets, pk->N,
+                                  2 * pk->n_lookups);
+}
+static int coset_products(zg_ctx* ctx, zg_pk* pk) {
+  int rc = ZG_OK;
+  if (pk->nsets)
+    rc = zg_coeff_to_extended_dev(ctx, (const zg_fr*)pk->pz_poly, pk->n, pk->k, pk->ext_k, (zg_fr*)pk->pz_coset, pk->N, pk->nsets);
+  if (rc || !pk->n_lookups) return rc;
+  return zg_coeff_to_extended_dev(ctx, (const zg_fr*)pk->lz_poly, pk->n, pk->k, pk->ext_k,
+                                  (zg_fr*)(pk->lk_cosets + 2 * (size_t)pk->n_lookups * pk->N), pk->N, pk->n_lookups);
+}
+
 // Evaluator::evaluate_h: reads the coefficient forms in the pk workspace (adv_polys, inst_polys, pz_poly, pa_poly | ps_poly,
 // lz_poly), builds their extended cosets and leaves the y-folded numerator in pk->h.
-static int quotient_numerator(zg_ctx* ctx, zg_pk* pk, const Fr& theta, const Fr& beta, const Fr& gamma, const Fr& y) {
+// `transform` = false when the caller has already built the cosets (create_proof does so early, off the critical path).
+static int quotient_numerator(zg_ctx* ctx, zg_pk* pk, const Fr& theta, const Fr& beta, const Fr& gamma, const Fr& y,
+                              bool transform) {
   const size_t n = pk->n, N = pk->N;
   const uint32_t A = pk->A, I = pk->I, Lk = pk->n_lookups, S = pk->nsets, bf = pk->bf, m = pk->m;
   cudaStream_t st = ctx->stream;
   LaunchCounter lc{&ctx->launches};
   LookupProgs lp{pk->prog_off, pk->d_in_first, pk->d_in_count, pk->d_tab_first, pk->d_tab_count};
   int rc;
-  rc = zg_coeff_to_extended_dev(ctx, (const zg_fr*)pk->adv_polys, n, pk->k, pk->ext_k, (zg_fr*)pk->adv_cosets, N, A);
-  if (rc) return rc;
-  if (I) {
-    rc = zg_coeff_to_extended_dev(ctx, (const zg_fr*)pk->inst_polys, n, pk->k, pk->ext_k, (zg_fr*)pk->inst_cosets, N, I);
+  if (transform) {
+    rc = coset_advice_instance(ctx, pk);
     if (rc) return rc;
-  }
-  if (S) {
-    rc = zg_coeff_to_extended_dev(ctx, (const zg_fr*)pk->pz_poly, n, pk->k, pk->ext_k, (zg_fr*)pk->pz_coset, N, S);
+    rc = coset_products(ctx, pk);
+    if (rc) return rc;
+    rc = coset_lookup_permuted(ctx, pk);
     if (rc) return rc;
   }
   ExprEnv ext_env = make_env(pk, true);
@@ -310,13 +350,8 @@ static int quotient_numerator(zg_ctx* ctx, zg_pk* pk, const Fr& theta, const Fr&
     expr_h_permutation(pe, beta, gamma, y, pk->delta, pk->h, st, lc);
   }
   if (Lk) {
-    // extended cosets of all lookup polynomials in two batched transforms: [a | s] (2 Lk columns), then z (Lk)
-    Fr* as_cos = pk->lk_cosets;
+    Fr* as_cos = pk->lk_cosets;                           // [a | s] (2 Lk columns), then z (Lk)
     Fr* z_cos = pk->lk_cosets + 2 * (size_t)Lk * N;
-    rc = zg_coeff_to_extended_dev(ctx, (const zg_fr*)pk->pa_poly, n, pk->k, pk->ext_k, (zg_fr*)as_cos, N, 2 * Lk);
-    if (rc) return rc;
-    rc = zg_coeff_to_extended_dev(ctx, (const zg_fr*)pk->lz_poly, n, pk->k, pk->ext_k, (zg_fr*)z_cos, N, Lk);
-    if (rc) return rc;
     for (uint32_t l = 0; l < Lk; l++) {
       LookupHEnv le{z_cos + l * N, as_cos + l * N, as_cos + (Lk + l) * N, pk->l0, pk->l_last, pk->l_active};
       expr_h_lookup(ext_env, lp, l, le, theta, beta, gamma, y, pk->h, st, lc);
@@ -580,9 +615,32 @@ int zg_pk_load(zg_ctx* ctx, const zg_pk_desc* d, zg_pk** out) {
   return ZG_OK;
 }
 
+static int create_proof_impl(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice, const zg_fr* const* instances,
+                             const size_t* instance_lens, zg_rng_fill_fn rng, void* rng_state, uint8_t* proof_out, size_t proof_cap,
+                             size_t* proof_len);
+
 int zg_create_proof(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice, const zg_fr* const* instances, const size_t* instance_lens,
                     zg_rng_fill_fn rng, void* rng_state, uint8_t* proof_out, size_t proof_cap, size_t* proof_len) {
   ZG_ENTER(ctx);
+  // The proof runs on the context's own high-priority stream, ordered after whatever the caller has enqueued on
+  // ctx->stream (e.g. device-resident advice); it is host-synchronous, so the caller's stream needs no join.
+  cudaStream_t caller = ctx->stream;
+  ZG_CUDA(cudaEventRecord(ctx->ev_fork, caller));
+  ZG_CUDA(cudaStreamWaitEvent(ctx->hp, ctx->ev_fork, 0));
+  ctx->stream = ctx->hp;
+  int rc = create_proof_impl(ctx, pk, advice, instances, instance_lens, rng, rng_state, proof_out, proof_cap, proof_len);
+  ctx->stream = caller;
+  // leave nothing in flight, also on the error paths (the workspace is reused by the next proof)
+  cudaError_t e1 = cudaStreamSynchronize(ctx->hp), e2 = cudaStreamSynchronize(ctx->aux);
+  if (rc == ZG_OK && (e1 != cudaSuccess || e2 != cudaSuccess)) return ctx->cuda_fail(e1 != cudaSuccess ? e1 : e2, "create_proof");
+  return rc;
+}
+
+}  // extern "C"
+
+static int create_proof_impl(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice, const zg_fr* const* instances,
+                             const size_t* instance_lens, zg_rng_fill_fn rng, void* rng_state, uint8_t* proof_out, size_t proof_cap,
+                             size_t* proof_len) {
   if (!pk || !advice || !rng || !proof_out || !proof_len) return ctx->fail(ZG_E_INVALID, "create_proof: null argument");
   const size_t n = pk->n, N = pk->N;
   const uint32_t A = pk->A, I = pk->I, Lk = pk->n_lookups, S = pk->nsets, bf = pk->bf, usable = pk->usable, m = pk->m;
@@ -619,16 +677,25 @@ int zg_create_proof(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice, const zg
     }
     if (len) ZG_CUDA(cudaMemcpyAsync(pk->inst_values + c * n, instances[c], sizeof(Fr) * len, cudaMemcpyHostToDevice, st));
   }
-  if (I) {
-    rc = zg_lagrange_to_coeff_dev(ctx, (const zg_fr*)pk->inst_values, (zg_fr*)pk->inst_polys, pk->k, I, n);
-    if (rc) return rc;
-  }
   // ---- 2. advice: upload, blind, commit ----------------------------------------------------------------------
   for (uint32_t c = 0; c < A; c++)
     ZG_CUDA(cudaMemcpyAsync(pk->adv_values + c * n, advice[c], sizeof(Fr) * usable, cudaMemcpyDefault, st));  // host or device
   for (uint32_t c = 0; c < A; c++) ZG_CUDA(blind_rows(pk->adv_values + c * n, usable, bf + 1));
   draw += A;  // one Blind(Fr::random) per column, unused by KZG
   {
+    // coefficient and extended-coset forms: nobody waits for them before the quotient stage -> low-priority stream
+    {
+      AuxScope aux(ctx);
+      if (aux.err != cudaSuccess) return ctx->cuda_fail(aux.err, "fork to aux stream");
+      if (I) {
+        rc = zg_lagrange_to_coeff_dev(ctx, (const zg_fr*)pk->inst_values, (zg_fr*)pk->inst_polys, pk->k, I, n);
+        if (rc) return rc;
+      }
+      rc = zg_lagrange_to_coeff_dev(ctx, (const zg_fr*)pk->adv_values, (zg_fr*)pk->adv_polys, pk->k, A, n);
+      if (rc) return rc;
+      rc = coset_advice_instance(ctx, pk);
+      if (rc) return rc;
+    }
     std::vector<Affine> aff(A);
     rc = zg_msm_dev(ctx, ZG_BASIS_LAGRANGE, (const zg_fr*)pk->adv_values, n, n, A, (zg_g1*)ctx->d_msm_out);
     if (rc) return rc;
@@ -640,8 +707,6 @@ int zg_create_proof(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice, const zg
     ZG_CUDA(cudaMemcpyAsync(pk->rnd_words_dev + 8 * small_draws, pk->rnd_words_host + 8 * small_draws, 64 * rest,
                             cudaMemcpyHostToDevice, st));
     fr_from_u512(pk->rnd_words_dev + 8 * small_draws, pk->rnd + small_draws, rest, st, lc);
-    rc = zg_lagrange_to_coeff_dev(ctx, (const zg_fr*)pk->adv_values, (zg_fr*)pk->adv_polys, pk->k, A, n);
-    if (rc) return rc;
     ZG_CUDA(cudaEventRecord(ev[1], st));
     ZG_CUDA(cudaStreamSynchronize(st));
     batch_normalize(jac.data(), A, aff.data());
@@ -687,21 +752,30 @@ int zg_create_proof(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice, const zg
         ZG_CUDA(blind_rows(pk->ps + l * n, usable, bf + 1));
         draw += 2;
       }
+      {
+        AuxScope aux(ctx);
+        if (aux.err != cudaSuccess) return ctx->cuda_fail(aux.err, "fork to aux stream");
+        rc = zg_lagrange_to_coeff_dev(ctx, (const zg_fr*)pk->pa, (zg_fr*)pk->pa_poly, pk->k, 2 * Lk, n);
+        if (rc) return rc;
+        rc = coset_lookup_permuted(ctx, pk);
+        if (rc) return rc;
+      }
       rc = zg_msm_dev(ctx, ZG_BASIS_LAGRANGE, (const zg_fr*)pk->pa, n, n, 2 * Lk, (zg_g1*)ctx->d_msm_out);
       if (rc) return rc;
       std::vector<G1Jac> jac(2 * Lk);
       std::vector<uint32_t> status(2 * Lk);
       ZG_CUDA(cudaMemcpyAsync(jac.data(), ctx->d_msm_out, sizeof(G1Jac) * 2 * Lk, cudaMemcpyDeviceToHost, st));
       ZG_CUDA(cudaMemcpyAsync(status.data(), pk->d_status, 4 * 2 * Lk, cudaMemcpyDeviceToHost, st));
-      rc = zg_lagrange_to_coeff_dev(ctx, (const zg_fr*)pk->pa, (zg_fr*)pk->pa_poly, pk->k, 2 * Lk, n);
-      if (rc) return rc;
       ZG_CUDA(cudaEventRecord(ev[2], st));
       ZG_CUDA(cudaStreamSynchronize(st));
       bool retry = false;
       for (uint32_t l = 0; l < Lk; l++) {
         if (status[2 * l] && !full[l] && pk->tab_count[l] != 1) { full[l] = 1; retry = true; }
       }
-      if (retry && attempt == 0) continue;
+      if (retry && attempt == 0) {
+        ZG_CUDA(join_aux(ctx));   // the transforms of the failed attempt still read pa / ps
+        continue;
+      }
       for (uint32_t l = 0; l < Lk; l++)
         if (status[2 * l + 1]) return ctx->fail(ZG_E_SYNTH, "create_proof: lookup input not in table (ConstraintSystemFailure)");
       batch_normalize(jac.data(), 2 * Lk, aff.data());
@@ -773,16 +847,20 @@ int zg_create_proof(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice, const zg
     const uint32_t cnt = S + Lk;
     std::vector<G1Jac> jac(cnt + 1);
     if (cnt) {
+      {
+        AuxScope aux(ctx);
+        if (aux.err != cudaSuccess) return ctx->cuda_fail(aux.err, "fork to aux stream");
+        rc = zg_lagrange_to_coeff_dev(ctx, (const zg_fr*)pk->pz, (zg_fr*)pk->pz_poly, pk->k, cnt, n);
+        if (rc) return rc;
+        rc = coset_products(ctx, pk);
+        if (rc) return rc;
+      }
       rc = zg_msm_dev(ctx, ZG_BASIS_LAGRANGE, (const zg_fr*)pk->pz, n, n, cnt, (zg_g1*)ctx->d_msm_out);
       if (rc) return rc;
     }
     rc = zg_msm_dev(ctx, ZG_BASIS_MONOMIAL, (const zg_fr*)pk->random_poly, n, n, 1, (zg_g1*)(ctx->d_msm_out + cnt));
     if (rc) return rc;
     ZG_CUDA(cudaMemcpyAsync(jac.data(), ctx->d_msm_out, sizeof(G1Jac) * (cnt + 1), cudaMemcpyDeviceToHost, st));
-    if (cnt) {
-      rc = zg_lagrange_to_coeff_dev(ctx, (const zg_fr*)pk->pz, (zg_fr*)pk->pz_poly, pk->k, cnt, n);
-      if (rc) return rc;
-    }
     ZG_CUDA(cudaEventRecord(ev[3], st));
     ZG_CUDA(cudaStreamSynchronize(st));
     std::vector<Affine> aff(cnt + 1);
@@ -793,7 +871,8 @@ int zg_create_proof(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice, const zg
   const Fr y = tr.squeeze();
 
   // ---- 7. quotient numerator on the extended coset ----------------------------------------------------------------------
-  rc = quotient_numerator(ctx, pk, theta, beta, gamma, y);
+  ZG_CUDA(join_aux(ctx));   // every coset form is ready
+  rc = quotient_numerator(ctx, pk, theta, beta, gamma, y, /*transform=*/false);
   if (rc) return rc;
   ZG_CUDA(cudaEventRecord(ev[4], st));
   // ---- 8. vanishing::construct: divide, back to coefficients, commit the pieces ---------------------------------------------
@@ -932,6 +1011,8 @@ int zg_create_proof(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice, const zg
   return ZG_OK;
 }
 
+extern "C" {
+
 // plonk::evaluation::Evaluator::evaluate_h for one circuit: polynomials in coefficient form (host), result on the
 // extended coset (host).  divide != 0 also applies EvaluationDomain::divide_by_vanishing_poly.
 int zg_evaluate_h(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice_polys, const zg_fr* const* instance_polys,
@@ -963,7 +1044,7 @@ int zg_evaluate_h(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice_polys, cons
   ZG_CUDA(up(pk->lz_poly, lookup_product_polys, Lk));
   Fr ch[4];
   memcpy(ch, challenges, sizeof(ch));   // theta, beta, gamma, y
-  int rc = quotient_numerator(ctx, pk, ch[0], ch[1], ch[2], ch[3]);
+  int rc = quotient_numerator(ctx, pk, ch[0], ch[1], ch[2], ch[3], /*transform=*/true);
   if (rc) return rc;
   if (divide) fr_mul_periodic(pk->h, pk->t_inv, pk->rot_scale, N, st, lc);
   ZG_CUDA(cudaMemcpyAsync(h_out, pk->h, sizeof(Fr) * N, cudaMemcpyDeviceToHost, st));
