@@ -10,6 +10,8 @@ Workloads:
                    k = 15) on benches/example_image_7.png.  Witness synthesis is host work outside the
                    replaced path (BASELINE north_star) and is done once, untimed, for both arms.
   msm              one 2^LOGN-point BN254 G1 MSM per step (uniform scalars)      -> points/s
+  msm_sharded      ONE 2^LOGN-point MSM split by point range over the ranks, partial sums all-gathered (NCCL)
+                   and added (strong scaling, BASELINE configs[3])                -> points/s
   ntt              one 2^LOGN-point BN254 Fr NTT per step                        -> GB/s (algorithmic)
 `value` is timed with inputs resident in HBM (CUDA events on the launching stream, L2 flushed between
 steps); `e2e` goes through the host-pointer C-ABI call (pinned host buffers in, result bytes out).
@@ -178,7 +180,7 @@ def run_reference(args, rank, world):
             seed[0] += 1
             return H.create_proof(srs, pk, asm.advice, [out], H.XorShiftRng(bytes([seed[0] % 256] * 16)), real_msm=True)
         metric, unit, units = "proofs_per_s", "proofs/s", 1
-    elif args.workload == "msm":
+    elif args.workload in ("msm", "msm_sharded"):
         n = 1 << args.logn
         bases, sc = synth_bases(n), rand_fr(n, 7)
         fn = lambda: cpu_ref.best_multiexp(sc, bases)
@@ -223,7 +225,9 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=120))
     # a non-default torch stream: the context enqueues on it, so torch CUDA events time our kernels
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
@@ -318,6 +322,53 @@ def main():
         if not args.no_cpu_baseline and rank == 0:
             import cpu_ref
             cpu_fn = lambda: cpu_ref.best_multiexp(sc_host, bases)
+    elif args.workload == "msm_sharded":
+        # BASELINE configs[3]: ONE 2^logn MSM split by point range; rank g keeps bases [g n/G, (g+1) n/G) resident, gets
+        # the matching scalar slice, and the G partial sums (96 B each) are all-gathered over NCCL and added (strong scaling)
+        from zg_b200 import farm
+        assert n % world == 0 and (n // world) & (n // world - 1) == 0, "world size must divide 2^logn into powers of two"
+        lo, hi = farm.point_range(n, rank, world)
+        bases = synth_bases(n)
+        logn_loc = (hi - lo).bit_length() - 1
+        ctx.srs_load(logn_loc, np.ascontiguousarray(bases[lo:hi]), None)
+        sc_full = rand_fr(n, 7)
+        sc_host_t = torch.from_numpy(np.ascontiguousarray(sc_full[lo:hi]).view(np.int64)).pin_memory()
+        sc_host = sc_host_t.numpy().view(np.uint64)
+        sc_dev = sc_host_t.cuda()
+        out_dev = torch.zeros(12, dtype=torch.int64, device="cuda")
+        gathered = [torch.zeros(12, dtype=torch.int64, device="cuda") for _ in range(world)]
+        result = [None]
+
+        def gather_and_add():
+            if world > 1:
+                dist.all_gather(gathered, out_dev)
+                parts = torch.stack(gathered).cpu().numpy().view(np.uint64)
+            else:
+                parts = out_dev.cpu().numpy().view(np.uint64)[None]
+            result[0] = farm.combine_partials(parts)
+
+        def step_dev():
+            ctx.msm_dev(0, sc_dev.data_ptr(), hi - lo, hi - lo, 1, out_dev.data_ptr())
+            gather_and_add()
+
+        def step_e2e():
+            out_dev.copy_(torch.from_numpy(ctx.msm(0, sc_host).view(np.int64)))
+            gather_and_add()
+        metric, unit, units = "msm_points_per_s", "points/s", n / world      # value = n / time (units * world below)
+        h2d, d2h = (hi - lo) * 32, 96 * world
+        dom_kernel = "msm_accumulate_kernel"
+        extra["scaling_override"] = "strong"
+        if logn <= 20:
+            step_dev()                                 # a collective: every rank takes part, rank 0 checks
+        if rank == 0 and logn <= 20:
+            import cpu_ref
+            exp = cpu_ref.g1_to_affine(cpu_ref.best_multiexp(sc_full, bases))[0]
+            got = bn254.g1_affine_to_limbs([result[0]])[0] if result[0] is not None else np.zeros(8, dtype=np.uint64)
+            assert (np.asarray(got).reshape(-1) == np.asarray(exp).reshape(-1)).all(), "sharded MSM differs from the oracle"
+        if not args.no_cpu_baseline and rank == 0:
+            import cpu_ref
+            cpu_fn = lambda: cpu_ref.best_multiexp(sc_full, bases)
+            cpu_units = n
     elif args.workload == "ntt":
         a_host_t = torch.from_numpy(rand_fr(n, 11 + rank).view(np.int64)).pin_memory()
         a_host = a_host_t.numpy().view(np.uint64)
@@ -411,9 +462,11 @@ def main():
                 "traffic": None, "peak_source": peak_src, "kernel": dom_kernel,
                 "note": "254-bit Montgomery butterflies make this kernel integer-pipe bound; see int_pipe"}
         int_pipe["kernel_mulmod_gops"] = (n // 2) * logn / 1e9 / (ms_per_step * 1e-3)
-    elif args.workload == "msm":
-        c = int(os.environ.get("ZG_MSM_C", "0")) or max(8, min(16, logn - 2))
-        ach = msm_imad(n, c) / 1e9 / (ms_per_step * 1e-3)
+    elif args.workload in ("msm", "msm_sharded"):
+        nl = n // world if args.workload == "msm_sharded" else n           # points per GPU
+        ll = nl.bit_length() - 1
+        c = int(os.environ.get("ZG_MSM_C", "0")) or max(8, min(16, ll - 2))
+        ach = msm_imad(nl, c) / 1e9 / (ms_per_step * 1e-3)
         roof = {"bound": "int", "achieved": ach, "peak": imad_peak, "unit": "GIMAD/s", "frac": ach / imad_peak,
                 "traffic": None, "peak_source": "measured in this run (zg_bench_int_pipe kind 0)",
                 "kernel": dom_kernel, "window_c": c}
@@ -436,6 +489,8 @@ def main():
         "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches), "clocks": clocks,
     }
+    if "scaling_override" in extra:
+        out["scaling"] = extra.pop("scaling_override")
     out.update(extra)
     if cpu_fn is not None:
         import cpu_ref
@@ -446,7 +501,7 @@ def main():
             cpu_fn()
             reps += 1
         dt = (time.perf_counter() - t0) / reps
-        out["cpu_baseline"] = {"value": (cpu_units if args.workload == "proof" else units) / dt, "unit": unit, "cores": cores, "kind": "port",
+        out["cpu_baseline"] = {"value": (cpu_units if args.workload in ("proof", "msm_sharded") else units) / dt, "unit": unit, "cores": cores, "kind": "port",
                                "sample": "same workload, %d repetitions on host cores (oracle restatement of the upstream "
                                          "CPU prover, OpenMP; witness synthesis excluded)" % reps}
     print(json.dumps(out))
