@@ -162,6 +162,8 @@ void zg_ctx_destroy(zg_ctx* ctx) {
   if (ctx->ws_ntt.p) cudaFree(ctx->ws_ntt.p);
   if (ctx->ws_stage.p) cudaFree(ctx->ws_stage.p);
   if (ctx->d_msm_out) cudaFree(ctx->d_msm_out);
+  for (auto e : ctx->probe.ev) cudaEventDestroy(e);
+  if (ctx->probe.counts) cudaFreeHost(ctx->probe.counts);
   if (ctx->hp) { cudaStreamSynchronize(ctx->hp); cudaStreamDestroy(ctx->hp); }
   if (ctx->aux) { cudaStreamSynchronize(ctx->aux); cudaStreamDestroy(ctx->aux); }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -200,6 +202,41 @@ int zg_d2h(zg_ctx* ctx, void* dst, const void* src, size_t bytes) {
   ZG_ENTER(ctx);
   ZG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   ZG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return ZG_OK;
+}
+
+// ---- live kernel timing for bench.py's roofline -----------------------------------------------------
+int zg_probe_enable(zg_ctx* ctx, int on) {
+  ZG_ENTER(ctx);
+  MsmProbe& p = ctx->probe;
+  if (on && !p.counts) {
+    p.cap = 8192;
+    ZG_CUDA(cudaMallocHost(&p.counts, p.cap * sizeof(uint32_t)));
+  }
+  p.used = 0;
+  p.on = on != 0;
+  return ZG_OK;
+}
+int zg_probe_read(zg_ctx* ctx, double* kernel_ms, uint64_t* launches, uint64_t* point_additions) {
+  ZG_ENTER(ctx);
+  MsmProbe& p = ctx->probe;
+  double ms = 0;
+  uint64_t adds = 0;
+  for (size_t i = 0; i < p.used; i++) {
+    ZG_CUDA(cudaEventSynchronize(p.ev[2 * i + 1]));
+    float t = 0;
+    ZG_CUDA(cudaEventElapsedTime(&t, p.ev[2 * i], p.ev[2 * i + 1]));
+    ms += t;
+    adds += p.counts[i];
+  }
+  // the count copies were enqueued after the stop events on the same streams
+  cudaDeviceSynchronize();
+  adds = 0;
+  for (size_t i = 0; i < p.used; i++) adds += p.counts[i];
+  if (kernel_ms) *kernel_ms = ms;
+  if (launches) *launches = p.used;
+  if (point_additions) *point_additions = adds;
+  p.used = 0;
   return ZG_OK;
 }
 
@@ -250,7 +287,7 @@ int zg_msm_dev(zg_ctx* ctx, int basis, const zg_fr* scalars_dev, size_t stride, 
   int rc = ws_reserve(ctx, ctx->ws_msm, lay.bytes);
   if (rc) return rc;
   cudaError_t e = msm_run(t, (const Fr*)scalars_dev, stride, (uint32_t)n, (uint32_t)count, (G1Jac*)out_dev,
-                          ctx->ws_msm.p, lay, ctx->stream, &ctx->launches);
+                          ctx->ws_msm.p, lay, ctx->stream, &ctx->launches, &ctx->probe);
   if (e != cudaSuccess) return ctx->cuda_fail(e, "msm_run");
   return ZG_OK;
 }

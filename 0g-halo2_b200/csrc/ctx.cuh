@@ -53,6 +53,7 @@ struct zg_ctx {
 
   zg::Workspace ws_msm, ws_ntt, ws_stage;
   zg::G1Jac* d_msm_out = nullptr;  // small result staging (64 results)
+  zg::MsmProbe probe;              // zg_probe_enable / zg_probe_read
 
   int fail(int code, const std::string& msg) {
     err = msg;

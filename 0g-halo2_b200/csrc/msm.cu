@@ -286,7 +286,7 @@ cudaError_t msm_precompute_table(const G1Affine* base, uint32_t n, uint32_t c, u
 }
 
 cudaError_t msm_run(const MsmTable& tb, const Fr* scalars, size_t stride, uint32_t n_used, uint32_t M,
-                    G1Jac* out, uint8_t* ws, const MsmWorkspaceLayout& l, cudaStream_t st, uint64_t* nl) {
+                    G1Jac* out, uint8_t* ws, const MsmWorkspaceLayout& l, cudaStream_t st, uint64_t* nl, MsmProbe* probe) {
   uint64_t launches = 0;
   {
     // up to 2^15 bucket counters (c = 16) in shared memory: opt in once per device
@@ -331,7 +331,21 @@ cudaError_t msm_run(const MsmTable& tb, const Fr* scalars, size_t stride, uint32
   // level 0: serial chunks over the sorted list (length offsets[cnt], read on device)
   uint32_t T0 = l.T0;
   launches++;
+  const bool probing = probe && probe->on && probe->used < probe->cap;
+  if (probing) {
+    while (probe->ev.size() < 2 * (probe->used + 1)) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      probe->ev.push_back(e);
+    }
+    cudaEventRecord(probe->ev[2 * probe->used], st);
+  }
   msm_accumulate_kernel<<<(T0 + 127) / 128, 128, 0, st>>>(entries, offsets + cnt, tb.pts, l.K0, buckets, pk[0], pp[0], T0);
+  if (probing) {
+    cudaEventRecord(probe->ev[2 * probe->used + 1], st);
+    cudaMemcpyAsync(probe->counts + probe->used, offsets + cnt, 4, cudaMemcpyDeviceToHost, st);
+    probe->used++;
+  }
   uint32_t slots = 2 * T0;
   int cur = 0;
   if (slots > 8192) {

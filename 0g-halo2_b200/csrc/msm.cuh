@@ -1,6 +1,7 @@
 // MSM descriptors shared by msm.cu and the context layer.
 #pragma once
 #include <cuda_runtime.h>
+#include <vector>
 #include "curve.cuh"
 
 namespace zg {
@@ -26,6 +27,15 @@ struct MsmWorkspaceLayout {
 };
 MsmWorkspaceLayout msm_workspace_layout(uint32_t n, uint32_t c, uint32_t W, uint32_t M);
 
+// Optional live timing of the level-0 accumulation kernel (the dominant kernel of the path): every launch is bracketed
+// by CUDA events on the launching stream and its entry count (= mixed point additions) is copied back.
+struct MsmProbe {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;      // 2 per launch
+  uint32_t* counts = nullptr;       // pinned host, one per launch
+  size_t cap = 0, used = 0;
+};
+
 cudaError_t msm_precompute_table(const G1Affine* base, uint32_t n, uint32_t c, uint32_t W,
                                  G1Affine* table, cudaStream_t stream);
 
@@ -34,6 +44,6 @@ cudaError_t msm_precompute_table(const G1Affine* base, uint32_t n, uint32_t c, u
 // out[m] is Jacobian.  `ws` must hold msm_workspace_layout(...).bytes.
 cudaError_t msm_run(const MsmTable& table, const Fr* scalars, size_t scalar_stride, uint32_t n_used,
                     uint32_t M, G1Jac* out, uint8_t* ws, const MsmWorkspaceLayout& lay,
-                    cudaStream_t stream, uint64_t* launch_counter);
+                    cudaStream_t stream, uint64_t* launch_counter, MsmProbe* probe = nullptr);
 
 }  // namespace zg

@@ -28,7 +28,7 @@ EXPORTS = [
     "zg_srs_load", "zg_msm", "zg_msm_batch", "zg_msm_dev",
     "zg_ntt", "zg_ntt_dev", "zg_lagrange_to_coeff", "zg_lagrange_to_coeff_dev",
     "zg_coeff_to_extended", "zg_coeff_to_extended_dev", "zg_extended_to_coeff", "zg_extended_to_coeff_dev",
-    "zg_bench_int_pipe", "zg_debug_field_op",
+    "zg_bench_int_pipe", "zg_debug_field_op", "zg_probe_enable", "zg_probe_read",
     "zg_xorshift_seed", "zg_xorshift_fill", "zg_pk_load", "zg_pk_free", "zg_pk_commitments", "zg_create_proof",
     "zg_pk_last_stage_ms",
     "zg_lookup_permute", "zg_grand_product", "zg_batch_invert", "zg_eval_poly_batch", "zg_kate_division", "zg_evaluate_h",
@@ -82,6 +82,8 @@ def load_library() -> ctypes.CDLL:
     L.zg_extended_to_coeff_dev.argtypes = [vp, vp, u32, u32, sz, vp]
     L.zg_bench_int_pipe.argtypes = [vp, ci, u32, ctypes.POINTER(ctypes.c_double)]
     L.zg_debug_field_op.argtypes = [vp, ci, ci, vp, vp, vp, sz]
+    L.zg_probe_enable.argtypes = [vp, ci]
+    L.zg_probe_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u64), ctypes.POINTER(u64)]
     L.zg_xorshift_seed.argtypes = [vp, vp]
     L.zg_xorshift_seed.restype = None
     L.zg_xorshift_fill.argtypes = [vp, vp, sz]
@@ -183,6 +185,13 @@ class Context:
         self._ck(self._L.zg_ntt(self._h, _ptr(a), log_n, _ptr(w)))
         return a
 
+    def ntt_inplace(self, a: np.ndarray, log_n: int, omega):
+        """zg_ntt on the caller's buffer (no copy; pass pinned memory for full PCIe speed)"""
+        assert a.dtype == np.uint64 and a.flags.c_contiguous and a.shape[-1] == 4
+        w = _np(omega, 4)
+        self._ck(self._L.zg_ntt(self._h, _ptr(a), log_n, _ptr(w)))
+        return a
+
     def ntt_dev(self, in_ptr: int, out_ptr: int, log_n: int, omega, batch: int = 1, stride: int | None = None):
         w = _np(omega, 4)
         self._ck(self._L.zg_ntt_dev(self._h, in_ptr, out_ptr, log_n, _ptr(w), batch, stride or (1 << log_n)))
@@ -269,6 +278,15 @@ class Context:
         v = ctypes.c_double()
         self._ck(self._L.zg_bench_int_pipe(self._h, kind, iters, ctypes.byref(v)))
         return v.value
+
+    def probe_enable(self, on: bool = True):
+        self._ck(self._L.zg_probe_enable(self._h, int(on)))
+
+    def probe_read(self):
+        """(kernel ms, launches, point additions) of msm_accumulate_kernel since probe_enable / the last read"""
+        ms, ln, adds = ctypes.c_double(), ctypes.c_uint64(), ctypes.c_uint64()
+        self._ck(self._L.zg_probe_read(self._h, ctypes.byref(ms), ctypes.byref(ln), ctypes.byref(adds)))
+        return ms.value, int(ln.value), int(adds.value)
 
     def debug_field_op(self, field: int, op: int, a, b=None) -> np.ndarray:
         a = _np(a, 4)

@@ -135,6 +135,29 @@ def msm_imad(n, c):
     return ((254 + c - 1) // c) * (10 * n + 2 * (1 << (c - 1)) * 14) * 264
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of msm_accumulate_kernel, from the `ncu --set full` captures
+# summarised in profiles/ (see profiles/README.md); keyed by workload
+NCU_TRAFFIC = {}
+_traffic_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+if os.path.exists(_traffic_path):
+    NCU_TRAFFIC = json.load(open(_traffic_path))
+
+
+def kernel_roofline(probe, imad_peak, region_ms, peak_src, traffic=None):
+    """msm_accumulate_kernel alone, timed live with CUDA events around every launch (zg_probe_*): algorithmic work =
+    one mixed XYZZ addition (10 Montgomery products = 2640 IMAD) per sorted (bucket, point) entry."""
+    if not probe or not probe[1]:
+        return None
+    kms, launches, adds = probe
+    ach = adds * 10 * 264 / 1e9 / (kms * 1e-3)
+    return {"bound": "int", "achieved": ach, "peak": imad_peak, "unit": "GIMAD/s", "frac": ach / imad_peak,
+            "traffic": traffic, "peak_source": peak_src, "kernel": "msm_accumulate_kernel", "launches": launches,
+            "avg_launch_ms": kms / launches, "point_additions_per_launch": adds / launches,
+            "algorithmic_gimad_per_launch": adds / launches * 2640 / 1e9, "share_of_timed_region": kms / region_ms,
+            "note": "bound is the integer (IMAD) pipe, not HBM or tensor: 254-bit Montgomery arithmetic; traffic = ncu dram bytes "
+                    "per launch (profiles/ncu_traffic.json) when captured for this workload"}
+
+
 def proof_msm_imad(n, k):
     """30 MSMs per proof at the window the backend uses for 2^k points."""
     c = max(8, min(16, k - 2))
@@ -376,7 +399,7 @@ def main():
         b_dev = torch.empty_like(a_dev)
         w = bn254.fr_to_limbs([bn254.omega(logn)])
         step_dev = lambda: ctx.ntt_dev(a_dev.data_ptr(), b_dev.data_ptr(), logn, w)
-        step_e2e = lambda: ctx.ntt(a_host, logn, w)
+        step_e2e = lambda: ctx.ntt_inplace(a_host, logn, w)     # pinned buffer, transformed in place
         metric, unit, units = "ntt_algorithmic_gbs", "GB/s", ntt_bytes(logn) / 1e9
         h2d = d2h = n * 32
         dom_kernel = "ntt_pass_kernel"
@@ -414,14 +437,23 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    probe = None
+    if args.workload in ("msm", "msm_sharded"):
+        ctx.probe_enable(True)
     barrier()
     ms = timed(step_dev, args.steps)
     barrier()
+    if args.workload in ("msm", "msm_sharded"):
+        probe = ctx.probe_read()
+        ctx.probe_enable(False)
     launches = sum(c.launch_count for c in all_ctx) - l0
     stage = None
     if args.workload == "proof":
         # single-proof latency (one lane alone), the other half of BASELINE's "proofs/s & proof latency"
+        ctx.probe_enable(True)
         lat_ms = timed(lambda: lanes[0].prove_dev(), args.steps) / args.steps
+        probe = ctx.probe_read()
+        ctx.probe_enable(False)
         stage = pk.stage_ms()
         extra["latency_ms_single_proof"] = lat_ms
     # e2e: host buffers through the plain C-ABI call (H2D + compute + D2H of the result)
@@ -467,17 +499,20 @@ def main():
         ll = nl.bit_length() - 1
         c = int(os.environ.get("ZG_MSM_C", "0")) or max(8, min(16, ll - 2))
         ach = msm_imad(nl, c) / 1e9 / (ms_per_step * 1e-3)
-        roof = {"bound": "int", "achieved": ach, "peak": imad_peak, "unit": "GIMAD/s", "frac": ach / imad_peak,
-                "traffic": None, "peak_source": "measured in this run (zg_bench_int_pipe kind 0)",
-                "kernel": dom_kernel, "window_c": c}
+        step_roof = {"bound": "int", "achieved": ach, "peak": imad_peak, "unit": "GIMAD/s", "frac": ach / imad_peak,
+                     "window_c": c, "note": "whole MSM: SURVEY 8(d) algorithmic IMAD(N, c) / step time"}
+        roof = kernel_roofline(probe, imad_peak, ms, peak_src="measured in this run (zg_bench_int_pipe kind 0)",
+                               traffic=NCU_TRAFFIC.get("%s_%d" % (args.workload, logn)))
+        extra["step_roofline"] = step_roof
     else:
         imad, c = proof_msm_imad(n, k)
         # MSM share of the step: stages that are MSM-dominated are reported by the library per proof
         ach = units * imad / 1e9 / (ms_per_step * 1e-3)
-        roof = {"bound": "int", "achieved": ach, "peak": imad_peak, "unit": "GIMAD/s", "frac": ach / imad_peak,
-                "traffic": None, "peak_source": "measured in this run (zg_bench_int_pipe kind 0)",
-                "kernel": dom_kernel, "window_c": c,
-                "note": "algorithmic IMAD of the 30 MSMs of one proof / whole-proof time (lower bound on the kernel's own fraction)"}
+        step_roof = {"bound": "int", "achieved": ach, "peak": imad_peak, "unit": "GIMAD/s", "frac": ach / imad_peak, "window_c": c,
+                     "note": "algorithmic IMAD of the 30 MSMs of every proof of the step / whole step time (all stages)"}
+        roof = kernel_roofline(probe, imad_peak, lat_ms * args.steps, peak_src="measured in this run (zg_bench_int_pipe kind 0)",
+                               traffic=NCU_TRAFFIC.get("proof_" + args.model))
+        extra["step_roofline"] = step_roof
         extra["stage_ms_last_proof"] = stage
     out = {
         "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,

@@ -179,6 +179,12 @@ int zg_evaluate_h(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice_polys, cons
  * carry-chain body, 4 = same, even/odd carry-chain body (the one the kernels use) */
 int zg_bench_int_pipe(zg_ctx* ctx, int kind, uint32_t iters, double* giga_per_s);
 
+/* live timing of the dominant kernel (msm_accumulate_kernel, the level-0 bucket accumulation of every MSM): while
+ * enabled, each launch is bracketed by CUDA events on the launching stream and its entry count (= mixed point
+ * additions) is copied back.  zg_probe_read returns the totals since the last enable / read and resets them. */
+int zg_probe_enable(zg_ctx* ctx, int on);
+int zg_probe_read(zg_ctx* ctx, double* kernel_ms, uint64_t* launches, uint64_t* point_additions);
+
 /* ---- diagnostics (parity tests) --------------------------------------------------------- */
 /* element-wise device field op on host arrays of n elements; field 0 = Fr, 1 = Fq;
  * op 0 mul, 1 mul (portable body), 2 mul (row-wise PTX body), 3 add, 4 sub, 5 inverse(a), 6 from_mont(a),
