@@ -192,3 +192,77 @@ def synthetic_image(index: int, shape=(28, 28)) -> np.ndarray:
     mask = rng.random(shape) < 0.15
     img[mask] = rng.integers(1, 256, size=int(mask.sum()), dtype=np.uint8)
     return img
+
+
+# ---- wire formats shared with the Rust CLI (src/io.rs:137-207) -------------------------------------------------
+# proof.json and circuit_params.json are serde_json renderings of structs defined IN the reference, so their
+# layout is certain.  The SRS file is written by halo2_proofs' ParamsKZG::write (un-vendored): the layout below is
+# the one of tag v2023_04_20 as recalled (SerdeFormat::RawBytes) and must be re-checked against a file written by
+# the Rust CLI as soon as one is available.
+def write_circuit_params(params: dict, path: str) -> None:
+    """src/io.rs:150-152: serde_json of WnnCircuitParams (src/gadgets/wnn.rs:245-253), field order preserved."""
+    import json
+    keys = ["p", "l", "n_hashes", "bits_per_hash", "bits_per_filter", "n_classes"]
+    with open(path, "w") as f:
+        json.dump({k: int(params[k]) for k in keys}, f, separators=(",", ":"))
+
+
+def read_circuit_params(path: str) -> dict:
+    """src/io.rs:155-157"""
+    import json
+    with open(path) as f:
+        d = json.load(f)
+    return {k: int(d[k]) for k in ["p", "l", "n_hashes", "bits_per_hash", "bits_per_filter", "n_classes"]}
+
+
+def write_proof_with_output(proof: bytes, output, path: str) -> None:
+    """ProofWithOutput::write (src/io.rs:178-207): {"proof":[u8...],"output":[Fr...]}.  halo2curves 0.3.3 derives
+    Serialize on `struct Fr([u64; 4])` (feature derive_serde, Cargo.toml:26-28), i.e. an Fr is the JSON array of its
+    four little-endian Montgomery limbs -- the same limbs the C ABI uses."""
+    import json
+    from .bn254_host import to_limbs
+    limbs = to_limbs([int(v) for v in output])
+    with open(path, "w") as f:
+        json.dump({"proof": list(proof), "output": [[int(x) for x in row] for row in limbs]}, f, separators=(",", ":"))
+
+
+def read_proof_with_output(path: str):
+    """ProofWithOutput::read: returns (proof bytes, [canonical ints])."""
+    import json
+    from .bn254_host import R_MOD, from_limbs
+    with open(path) as f:
+        d = json.load(f)
+    out = np.array(d["output"], dtype=np.uint64).reshape(-1, 4)
+    return bytes(d["proof"]), [int(v) for v in from_limbs(out, R_MOD)]
+
+
+def write_srs(k: int, g: np.ndarray, g_lagrange: np.ndarray, g2_raw: bytes, s_g2_raw: bytes, path: str) -> None:
+    """ParamsKZG::<Bn256>::write as used by src/io.rs:138-140 [UPSTREAM-RECALLED layout, RawBytes]:
+    k (u32 LE) | g[0..n) | g_lagrange[0..n) | g2 | s_g2, G1Affine = x | y as 4 x u64 LE Montgomery limbs each (64 B),
+    G2Affine = 128 B.  g / g_lagrange are the (n, 8) uint64 arrays the C ABI takes, so they are written verbatim."""
+    n = 1 << k
+    g = np.ascontiguousarray(g, dtype="<u8")
+    gl = np.ascontiguousarray(g_lagrange, dtype="<u8")
+    assert g.shape == (n, 8) and gl.shape == (n, 8) and len(g2_raw) == 128 and len(s_g2_raw) == 128
+    with open(path, "wb") as f:
+        f.write(int(k).to_bytes(4, "little"))
+        f.write(g.tobytes())
+        f.write(gl.tobytes())
+        f.write(g2_raw)
+        f.write(s_g2_raw)
+
+
+def read_srs(path: str):
+    """ParamsKZG::<Bn256>::read (src/io.rs:143-145), same layout: returns (k, g, g_lagrange, g2_raw, s_g2_raw).
+    The prover needs g and g_lagrange only; the G2 points are carried through for the verifier."""
+    with open(path, "rb") as f:
+        k = int.from_bytes(f.read(4), "little")
+        if not 1 <= k <= 28:
+            raise ValueError("SRS file: k = %d out of range (not a RawBytes ParamsKZG file?)" % k)
+        n = 1 << k
+        g = np.frombuffer(f.read(64 * n), dtype="<u8").reshape(n, 8).astype(np.uint64)
+        gl = np.frombuffer(f.read(64 * n), dtype="<u8").reshape(n, 8).astype(np.uint64)
+        g2, s_g2 = f.read(128), f.read(128)
+        if len(s_g2) != 128 or f.read(1):
+            raise ValueError("SRS file: unexpected length for k = %d" % k)
+    return k, g, gl, g2, s_g2

@@ -1,0 +1,42 @@
+"""Round trips of the files exchanged with the Rust CLI (zg_b200/io.py mirrors /root/reference/src/io.rs:137-207)."""
+import json
+
+import numpy as np
+
+from zg_b200 import io as zio
+from zg_b200.bn254_host import R_MOD, to_limbs
+
+
+def test_circuit_params_json(tmp_path):
+    p = {"p": (1 << 21) - 9, "l": 20, "n_hashes": 2, "bits_per_hash": 10, "bits_per_filter": 28, "n_classes": 10}
+    path = str(tmp_path / "circuit_params.json")
+    zio.write_circuit_params(p, path)
+    assert zio.read_circuit_params(path) == p
+    # serde_json keeps the struct's field order (src/gadgets/wnn.rs:245-253)
+    assert list(json.load(open(path)).keys()) == ["p", "l", "n_hashes", "bits_per_hash", "bits_per_filter", "n_classes"]
+
+
+def test_proof_with_output_json(tmp_path):
+    proof = bytes(range(256)) * 15
+    outputs = [17, 13, 25, 27, 29, 21, 15, 55, 27, 32]            # tests/integration_test.rs:30-37
+    path = str(tmp_path / "proof.json")
+    zio.write_proof_with_output(proof, outputs, path)
+    d = json.load(open(path))
+    assert list(d.keys()) == ["proof", "output"] and d["proof"][:4] == [0, 1, 2, 3]
+    # an Fr is the array of its 4 Montgomery limbs: 17 * R mod r
+    assert d["output"][0] == [int(x) for x in to_limbs([17])[0]]
+    p2, o2 = zio.read_proof_with_output(path)
+    assert p2 == proof and o2 == outputs
+
+
+def test_srs_raw_bytes_round_trip(tmp_path):
+    k = 4
+    rng = np.random.default_rng(1)
+    g = rng.integers(0, 1 << 62, size=(16, 8), dtype=np.uint64)
+    gl = rng.integers(0, 1 << 62, size=(16, 8), dtype=np.uint64)
+    g2, sg2 = bytes(range(128)), bytes(reversed(range(128)))
+    path = str(tmp_path / "kzg.srs")
+    zio.write_srs(k, g, gl, g2, sg2, path)
+    assert (tmp_path / "kzg.srs").stat().st_size == 4 + 2 * 16 * 64 + 256
+    k2, g_, gl_, g2_, sg2_ = zio.read_srs(path)
+    assert k2 == k and (g_ == g).all() and (gl_ == gl).all() and g2_ == g2 and sg2_ == sg2
