@@ -111,6 +111,26 @@ static int ntt_generic_dev(zg_ctx* ctx, const Fr* in, size_t in_stride, Fr* out,
   return ZG_OK;
 }
 
+int msm_dev_mixed(zg_ctx* ctx, int basis, const Fr* scalars_dev, size_t stride, size_t n, size_t count, uint32_t other_mask,
+                  G1Jac* out_dev) {
+  ZG_ENTER(ctx);
+  if (!ctx->srs_loaded) return ctx->fail(ZG_E_STATE, "msm: no SRS loaded");
+  if (basis < 0 || basis > 1 || !ctx->table[basis].pts) return ctx->fail(ZG_E_STATE, "msm: basis not loaded");
+  if (other_mask && (!ctx->table[basis ^ 1].pts || count > 32)) return ctx->fail(ZG_E_STATE, "msm: other basis not loaded");
+  const MsmTable& t = ctx->table[basis];
+  if (n == 0 || n > t.n) return ctx->fail(ZG_E_INVALID, "msm: n must be in [1, 2^k]");
+  if (count == 0) return ZG_OK;
+  if ((uint64_t)n * t.W * count >= (1ull << 32) || count > 65535)
+    return ctx->fail(ZG_E_INVALID, "msm: batch too large for 32-bit entry indices");
+  MsmWorkspaceLayout lay = msm_workspace_layout((uint32_t)n, t.c, t.W, (uint32_t)count);
+  int rc = ws_reserve(ctx, ctx->ws_msm, lay.bytes);
+  if (rc) return rc;
+  cudaError_t e = msm_run(t, scalars_dev, stride, (uint32_t)n, (uint32_t)count, out_dev, ctx->ws_msm.p, lay, ctx->stream,
+                          &ctx->launches, &ctx->probe, other_mask ? ctx->table[basis ^ 1].pts : nullptr, other_mask);
+  if (e != cudaSuccess) return ctx->cuda_fail(e, "msm_run");
+  return ZG_OK;
+}
+
 }  // namespace zg
 
 extern "C" {
@@ -275,21 +295,7 @@ int zg_srs_load(zg_ctx* ctx, uint32_t k, const zg_g1_affine* g, const zg_g1_affi
 // ---- MSM -------------------------------------------------------------------------------------
 int zg_msm_dev(zg_ctx* ctx, int basis, const zg_fr* scalars_dev, size_t stride, size_t n, size_t count,
                zg_g1* out_dev) {
-  ZG_ENTER(ctx);
-  if (!ctx->srs_loaded) return ctx->fail(ZG_E_STATE, "msm: no SRS loaded");
-  if (basis < 0 || basis > 1 || !ctx->table[basis].pts) return ctx->fail(ZG_E_STATE, "msm: basis not loaded");
-  const MsmTable& t = ctx->table[basis];
-  if (n == 0 || n > t.n) return ctx->fail(ZG_E_INVALID, "msm: n must be in [1, 2^k]");
-  if (count == 0) return ZG_OK;
-  if ((uint64_t)n * t.W * count >= (1ull << 32) || count > 65535)
-    return ctx->fail(ZG_E_INVALID, "msm: batch too large for 32-bit entry indices");
-  MsmWorkspaceLayout lay = msm_workspace_layout((uint32_t)n, t.c, t.W, (uint32_t)count);
-  int rc = ws_reserve(ctx, ctx->ws_msm, lay.bytes);
-  if (rc) return rc;
-  cudaError_t e = msm_run(t, (const Fr*)scalars_dev, stride, (uint32_t)n, (uint32_t)count, (G1Jac*)out_dev,
-                          ctx->ws_msm.p, lay, ctx->stream, &ctx->launches, &ctx->probe);
-  if (e != cudaSuccess) return ctx->cuda_fail(e, "msm_run");
-  return ZG_OK;
+  return msm_dev_mixed(ctx, basis, (const Fr*)scalars_dev, stride, n, count, 0, (G1Jac*)out_dev);
 }
 
 int zg_msm_batch(zg_ctx* ctx, int basis, const zg_fr* const* scalars, size_t n, size_t count, zg_g1* out) {

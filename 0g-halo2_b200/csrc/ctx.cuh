@@ -68,6 +68,9 @@ struct zg_ctx {
 namespace zg {
 int ws_reserve(zg_ctx* ctx, Workspace& w, size_t bytes);
 int get_domain(zg_ctx* ctx, uint32_t logn, const Fr& omega, Domain** out);
+// zg_msm_dev with MSM m on the OTHER basis when bit m of other_mask is set (count <= 32)
+int msm_dev_mixed(zg_ctx* ctx, int basis, const Fr* scalars_dev, size_t stride, size_t n, size_t count, uint32_t other_mask,
+                  G1Jac* out_dev);
 }  // namespace zg
 
 // CUDA's current device is per host thread: every entry point selects the context's device first

@@ -265,7 +265,7 @@ int lookup_sort_table(const Fr* s_mont, uint32_t usable, const LookupTable& out,
   k_canonical_iota<<<nb(n), 256, 0, st>>>(s_mont, Tcan, idx0, n); lc++;
   uint32_t* in = idx0;
   uint32_t* o = idx1;
-  for (uint32_t byte = full_sort ? 0 : 24; byte < 32; byte++) {
+  for (uint32_t byte = full_sort ? 0 : 26; byte < 32; byte++) {   // partial sort: the top 48 bits, then checked
     k_rs_hist<<<nblocks, RS_THREADS, 0, st>>>(Tcan, in, n, byte, hist); lc++;
     {
       ScanJobs sj{};

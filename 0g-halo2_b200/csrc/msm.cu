@@ -168,6 +168,7 @@ __global__ void msm_hist_offsets_kernel(uint32_t* __restrict__ H, uint32_t J, ui
 // (nobody else holds that key); the first and last runs go to partial slots 2t, 2t+1.
 __global__ void __launch_bounds__(128) msm_accumulate_kernel(
     const uint2* __restrict__ entries, const uint32_t* __restrict__ count_ptr, const G1Affine* __restrict__ table,
+    const G1Affine* __restrict__ alt_table, uint32_t alt_mask, uint32_t log_nb,
     uint32_t K, G1Xyzz* __restrict__ buckets, uint32_t* __restrict__ pkeys, G1Xyzz* __restrict__ ppts, uint32_t nthreads) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nthreads) return;
@@ -198,7 +199,8 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(
       acc = xyzz_identity();
     }
     Fq x, y;
-    ld_fq2(table + (ent.y & 0x7fffffffu), x, y);
+    const G1Affine* tb = ((alt_mask >> (ent.x >> log_nb)) & 1u) ? alt_table : table;
+    ld_fq2(tb + (ent.y & 0x7fffffffu), x, y);
     if (!(fp_is_zero(x) && fp_is_zero(y))) {
       if (ent.y >> 31) y = fp_neg(y);
       xyzz_madd(acc, x, y);
@@ -247,7 +249,7 @@ MsmWorkspaceLayout msm_workspace_layout(uint32_t n, uint32_t c, uint32_t W, uint
   l.T0 = (uint32_t)((lmax + l.K0 - 1) / l.K0);
   l.slots_a = 2 * l.T0;
   // level 1 (serial, K = 16) or first warp level consumes slots_a
-  uint32_t t1s = (l.slots_a + 15) / 16, t1w = (l.slots_a + 31) / 32;
+  uint32_t t1s = (l.slots_a + MSM_LEVEL1_K - 1) / MSM_LEVEL1_K, t1w = (l.slots_a + 31) / 32;
   l.slots_b = 2 * (t1s > t1w ? t1s : t1w);
   size_t o = 0;
   size_t cnt = (size_t)M * l.NB;
@@ -286,7 +288,8 @@ cudaError_t msm_precompute_table(const G1Affine* base, uint32_t n, uint32_t c, u
 }
 
 cudaError_t msm_run(const MsmTable& tb, const Fr* scalars, size_t stride, uint32_t n_used, uint32_t M,
-                    G1Jac* out, uint8_t* ws, const MsmWorkspaceLayout& l, cudaStream_t st, uint64_t* nl, MsmProbe* probe) {
+                    G1Jac* out, uint8_t* ws, const MsmWorkspaceLayout& l, cudaStream_t st, uint64_t* nl, MsmProbe* probe,
+                    const G1Affine* alt_pts, uint32_t alt_mask) {
   uint64_t launches = 0;
   {
     // up to 2^15 bucket counters (c = 16) in shared memory: opt in once per device
@@ -340,7 +343,8 @@ cudaError_t msm_run(const MsmTable& tb, const Fr* scalars, size_t stride, uint32
     }
     cudaEventRecord(probe->ev[2 * probe->used], st);
   }
-  msm_accumulate_kernel<<<(T0 + 127) / 128, 128, 0, st>>>(entries, offsets + cnt, tb.pts, l.K0, buckets, pk[0], pp[0], T0);
+  msm_accumulate_kernel<<<(T0 + 127) / 128, 128, 0, st>>>(entries, offsets + cnt, tb.pts, alt_pts ? alt_pts : tb.pts,
+                                                          alt_pts ? alt_mask : 0u, tb.c - 1, l.K0, buckets, pk[0], pp[0], T0);
   if (probing) {
     cudaEventRecord(probe->ev[2 * probe->used + 1], st);
     cudaMemcpyAsync(probe->counts + probe->used, offsets + cnt, 4, cudaMemcpyDeviceToHost, st);
@@ -349,7 +353,7 @@ cudaError_t msm_run(const MsmTable& tb, const Fr* scalars, size_t stride, uint32
   uint32_t slots = 2 * T0;
   int cur = 0;
   if (slots > 8192) {
-    uint32_t T1 = (slots + 15) / 16;
+    uint32_t T1 = (slots + MSM_LEVEL1_K - 1) / MSM_LEVEL1_K;
     launches++;
     msm_tail_serial_level(pk[0], pp[0], slots, buckets, pk[1], pp[1], T1, st);
     slots = 2 * T1;

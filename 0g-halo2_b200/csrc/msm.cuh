@@ -13,6 +13,8 @@ struct MsmTable {
 };
 
 constexpr uint32_t MSM_INVALID_KEY = 0xffffffffu;
+// entries per thread of the second serial level: a chain of this many dependent additions per batch, so kept short
+constexpr uint32_t MSM_LEVEL1_K = 8;
 
 inline uint32_t msm_windows(uint32_t c) { return (255 + c - 1) / c; }
 // window width used for a 2^k-point fixed-base MSM (overridable with ZG_MSM_C)
@@ -44,6 +46,9 @@ cudaError_t msm_precompute_table(const G1Affine* base, uint32_t n, uint32_t c, u
 // out[m] is Jacobian.  `ws` must hold msm_workspace_layout(...).bytes.
 cudaError_t msm_run(const MsmTable& table, const Fr* scalars, size_t scalar_stride, uint32_t n_used,
                     uint32_t M, G1Jac* out, uint8_t* ws, const MsmWorkspaceLayout& lay,
-                    cudaStream_t stream, uint64_t* launch_counter, MsmProbe* probe = nullptr);
+                    cudaStream_t stream, uint64_t* launch_counter, MsmProbe* probe = nullptr,
+                    const G1Affine* alt_pts = nullptr, uint32_t alt_mask = 0);
+// (alt_pts / alt_mask: MSM m of the batch reads the window table `alt_pts` instead when bit m of alt_mask is set --
+//  one Fiat-Shamir round can mix commit_lagrange and commit columns in a single pipeline; both tables share n, c, W)
 
 }  // namespace zg

@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(96) msm_finish_kernel(const G1Xyzz* __restrict
 // ---- launchers called from msm_run (msm.cu) -------------------------------------------------------------
 void msm_tail_serial_level(const uint32_t* keys, const G1Xyzz* pts, uint32_t slots, G1Xyzz* buckets, uint32_t* pkeys_out,
                            G1Xyzz* ppts_out, uint32_t T1, cudaStream_t st) {
-  msm_serial_reduce_kernel<false><<<(T1 + 127) / 128, 128, 0, st>>>(keys, nullptr, pts, nullptr, slots, nullptr, 16, buckets,
+  msm_serial_reduce_kernel<false><<<(T1 + 127) / 128, 128, 0, st>>>(keys, nullptr, pts, nullptr, slots, nullptr, MSM_LEVEL1_K, buckets,
                                                                      pkeys_out, ppts_out, T1);
 }
 void msm_tail_warp_level(const uint32_t* keys, const G1Xyzz* pts, uint32_t slots, G1Xyzz* buckets, uint32_t* pkeys_out,

@@ -59,10 +59,29 @@ __global__ void ntt_twiddle_stage_kernel(Fr* tab, const Fr* flat, uint32_t logn)
   st_fr(tab + e, ld_fr(flat + ((size_t)j << (logn - 1 - t))));
 }
 
+struct SmTile {
+  uint4* lo;
+  uint4* hi;
+  __device__ __forceinline__ Fr get(uint32_t e) const {
+    uint4 a = lo[e], b = hi[e];
+    Fr r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+  }
+  __device__ __forceinline__ void put(uint32_t e, const Fr& r) const {
+    lo[e] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    hi[e] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+  }
+};
+
 // ---- one pass ----------------------------------------------------------------------------
 __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(NttPassArgs A) {
+  // The tile is kept as two planes of 16-byte halves (low limbs | high limbs): consecutive elements are 16 B apart in
+  // each plane, so the 128-bit shared accesses of a warp hit 32 distinct banks per quarter-warp.  (Whole 32-byte
+  // elements gave a 2-way conflict on every access: ncu l1tex__data_bank_conflicts 4.2 M of 8.4 M wavefronts.)
   extern __shared__ uint4 ntt_smem_raw[];
-  Fr* sm = reinterpret_cast<Fr*>(ntt_smem_raw);
+  SmTile sm{ntt_smem_raw, ntt_smem_raw + ((1u << A.S) << A.logc)};
   const uint32_t S = A.S, logc = A.logc, lo = A.lo, logn = A.logn;
   const uint32_t R = 1u << S, C = 1u << logc;
   const Fr* in = A.in + (size_t)blockIdx.y * A.in_stride;
@@ -90,7 +109,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(NttPassArgs A) {
       } else {
         v = fp_zero<FrParams>();
       }
-      sm[e] = v;  // e = j*C + c
+      sm.put(e, v);  // e = j*C + c
     }
   } else {
     base = tile << S;  // `rest` field sits above the S active bits
@@ -108,7 +127,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(NttPassArgs A) {
       } else {
         v = fp_zero<FrParams>();
       }
-      sm[e] = v;  // e = c*R + j
+      sm.put(e, v);  // e = c*R + j
     }
   }
   __syncthreads();
@@ -139,12 +158,12 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(NttPassArgs A) {
         eb = ea + half;
         widx = jl;
       }
-      Fr x = sm[ea], y = sm[eb];
+      Fr x = sm.get(ea), y = sm.get(eb);
       Fr s = fp_add(x, y);
       Fr d = fp_sub(x, y);
       if (widx != 0) d = fp_mul(d, ld_fr(T + widx));
-      sm[ea] = s;
-      sm[eb] = d;
+      sm.put(ea, s);
+      sm.put(eb, d);
     }
     __syncthreads();
   }
@@ -153,7 +172,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(NttPassArgs A) {
     for (uint32_t e = tid; e < total; e += NTT_THREADS) {
       uint32_t c = e & (C - 1), j = e >> logc;
       uint32_t idx = base | (j << lo) | c;
-      st_fr(out + idx, sm[e]);
+      st_fr(out + idx, sm.get(e));
     }
   } else {
     const uint32_t restbits = logn - S - logc;
@@ -164,7 +183,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(NttPassArgs A) {
       uint32_t c = logc ? (__brev(cr) >> (32 - logc)) : 0;
       uint32_t pos = (jr << (logn - S)) | (rest_rev << logc) | cr;
       if (pos >= A.n_out) continue;
-      Fr v = sm[(c << S) | j];
+      Fr v = sm.get((c << S) | j);
       if (A.flags & NTT_OUT_SCALE) v = fp_mul(v, A.out_scale[(A.flags & NTT_OUT_MOD3) ? pos % 3 : 0]);
       st_fr(out + pos, v);
     }

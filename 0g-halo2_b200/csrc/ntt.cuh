@@ -5,9 +5,18 @@
 
 namespace zg {
 
-constexpr int NTT_THREADS = 256;
-constexpr uint32_t NTT_MAX_S = 8;  // index bits per pass (tile = 2^S rows)
-constexpr uint32_t NTT_LOGC = 2;   // columns per tile (4 x 32 B = one 128-B line)
+#ifndef ZG_NTT_THREADS
+#define ZG_NTT_THREADS 128
+#endif
+#ifndef ZG_NTT_LOGC
+#define ZG_NTT_LOGC 2
+#endif
+constexpr int NTT_THREADS = ZG_NTT_THREADS;
+#ifndef ZG_NTT_MAX_S
+#define ZG_NTT_MAX_S 8
+#endif
+constexpr uint32_t NTT_MAX_S = ZG_NTT_MAX_S;  // index bits per pass (tile = 2^S rows)
+constexpr uint32_t NTT_LOGC = ZG_NTT_LOGC;   // columns per tile (4 x 32 B = one 128-B line)
 
 enum : uint32_t {
   NTT_IN_COSET = 1,   // multiply input i by in_scale[i % 3]   (distribute_powers_zeta)

@@ -469,7 +469,7 @@ int zg_pk_load(zg_ctx* ctx, const zg_pk_desc* d, zg_pk** out) {
     pk->ci = b.take<Fr>(Lk * n); pk->ct = b.take<Fr>(Lk * n);
     pk->pa = b.take<Fr>(2 * Lk * n); pk->ps = pk->pa ? pk->pa + (size_t)Lk * n : nullptr;   // pa | ps contiguous: one MSM batch
     pk->pa_poly = b.take<Fr>(2 * Lk * n); pk->ps_poly = pk->pa_poly ? pk->pa_poly + (size_t)Lk * n : nullptr;
-    pk->pz = b.take<Fr>((S + Lk) * n); pk->lz = pk->pz ? pk->pz + (size_t)S * n : nullptr;     // pz | lz contiguous
+    pk->pz = b.take<Fr>((S + Lk + 1) * n); pk->lz = pk->pz ? pk->pz + (size_t)S * n : nullptr;   // pz | lz | (random poly) contiguous
     pk->pz_poly = b.take<Fr>((S + Lk) * n); pk->lz_poly = pk->pz_poly ? pk->pz_poly + (size_t)S * n : nullptr;
     pk->pz_coset = b.take<Fr>(S * N); pk->lk_cosets = b.take<Fr>(3 * (size_t)Lk * N);
     pk->frac = b.take<Fr>(n); pk->rnd = b.take<Fr>(pk->n_draws); pk->random_poly = pk->rnd;  // set per proof
@@ -847,18 +847,17 @@ static int create_proof_impl(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice,
     const uint32_t cnt = S + Lk;
     std::vector<G1Jac> jac(cnt + 1);
     if (cnt) {
-      {
-        AuxScope aux(ctx);
-        if (aux.err != cudaSuccess) return ctx->cuda_fail(aux.err, "fork to aux stream");
-        rc = zg_lagrange_to_coeff_dev(ctx, (const zg_fr*)pk->pz, (zg_fr*)pk->pz_poly, pk->k, cnt, n);
-        if (rc) return rc;
-        rc = coset_products(ctx, pk);
-        if (rc) return rc;
-      }
-      rc = zg_msm_dev(ctx, ZG_BASIS_LAGRANGE, (const zg_fr*)pk->pz, n, n, cnt, (zg_g1*)ctx->d_msm_out);
+      AuxScope aux(ctx);
+      if (aux.err != cudaSuccess) return ctx->cuda_fail(aux.err, "fork to aux stream");
+      rc = zg_lagrange_to_coeff_dev(ctx, (const zg_fr*)pk->pz, (zg_fr*)pk->pz_poly, pk->k, cnt, n);
+      if (rc) return rc;
+      rc = coset_products(ctx, pk);
       if (rc) return rc;
     }
-    rc = zg_msm_dev(ctx, ZG_BASIS_MONOMIAL, (const zg_fr*)pk->random_poly, n, n, 1, (zg_g1*)(ctx->d_msm_out + cnt));
+    // one pipeline for the whole round: the product columns on the Lagrange basis and, as MSM number `cnt`, the random
+    // polynomial on the monomial basis (copied behind the product columns so the batch is one strided array)
+    ZG_CUDA(cudaMemcpyAsync(pk->pz + (size_t)cnt * n, pk->random_poly, sizeof(Fr) * n, cudaMemcpyDeviceToDevice, st));
+    rc = msm_dev_mixed(ctx, ZG_BASIS_LAGRANGE, pk->pz, n, n, cnt + 1, 1u << cnt, ctx->d_msm_out);
     if (rc) return rc;
     ZG_CUDA(cudaMemcpyAsync(jac.data(), ctx->d_msm_out, sizeof(G1Jac) * (cnt + 1), cudaMemcpyDeviceToHost, st));
     ZG_CUDA(cudaEventRecord(ev[3], st));
