@@ -248,23 +248,27 @@ __device__ __forceinline__ G1Xyzz xyzz_mul32(G1Xyzz p) {
   return p;
 }
 
-// level 2: warp w of MSM m folds s1[32w..32w+32) -> (S2, T2) and sums t1[32w..32w+32) -> U
-__global__ void __launch_bounds__(32) msm_bucket_l2_kernel(const G1Xyzz* __restrict__ s1,
+// level 2: CTA w of MSM m folds s1[32w..32w+32) -> (S2, T2) (warp 0) and sums t1[32w..32w+32) -> U (warp 1); the two
+// chains (10 and 5 dependent additions) run side by side instead of back to back
+__global__ void __launch_bounds__(64) msm_bucket_l2_kernel(const G1Xyzz* __restrict__ s1,
                                                            const G1Xyzz* __restrict__ t1, uint32_t n1,
                                                            G1Xyzz* __restrict__ l2out) {
-  const uint32_t w = blockIdx.x, m = blockIdx.y, lane = threadIdx.x;
+  const uint32_t w = blockIdx.x, m = blockIdx.y, lane = threadIdx.x & 31, role = threadIdx.x >> 5;
   const uint32_t nw = gridDim.x;
   uint32_t i = w * 32 + lane;
-  G1Xyzz x = (i < n1) ? s1[(size_t)m * n1 + i] : xyzz_identity();
-  G1Xyzz tt = (i < n1) ? t1[(size_t)m * n1 + i] : xyzz_identity();
-  G1Xyzz s, t;
-  warp_weighted(x, lane, s, t);
-  G1Xyzz u = warp_sum(tt, lane);
-  if (lane == 0) {
-    G1Xyzz* o = l2out + (size_t)m * 3 * nw;
-    o[w] = s;
-    o[nw + w] = t;
-    o[2 * nw + w] = u;
+  G1Xyzz* o = l2out + (size_t)m * 3 * nw;
+  if (role == 0) {
+    G1Xyzz x = (i < n1) ? s1[(size_t)m * n1 + i] : xyzz_identity();
+    G1Xyzz s, t;
+    warp_weighted(x, lane, s, t);
+    if (lane == 0) {
+      o[w] = s;
+      o[nw + w] = t;
+    }
+  } else {
+    G1Xyzz tt = (i < n1) ? t1[(size_t)m * n1 + i] : xyzz_identity();
+    G1Xyzz u = warp_sum(tt, lane);
+    if (lane == 0) o[2 * nw + w] = u;
   }
 }
 
@@ -320,7 +324,7 @@ void msm_tail_buckets(const G1Xyzz* buckets, uint32_t NB, uint32_t M, G1Xyzz* s1
   else
     msm_bucket_l1_kernel<<<dim3((4 * n1 + 127) / 128, M), 128, 0, st>>>(buckets, NB, n1, s1, t1);
   uint32_t nw = (n1 + 31) / 32;
-  msm_bucket_l2_kernel<<<dim3(nw, M), 32, 0, st>>>(s1, t1, n1, l2out);
+  msm_bucket_l2_kernel<<<dim3(nw, M), 64, 0, st>>>(s1, t1, n1, l2out);
   msm_finish_kernel<<<M, 96, 0, st>>>(l2out, nw, out);
 }
 

@@ -161,7 +161,7 @@ __global__ void k_rp_apply(const Fr* __restrict__ f, const Fr* __restrict__ E, u
 }
 
 // Kate division as the forward recurrence b[t] = A[t] + zz * b[t-1], A[t] = a[n-1-t], q[n-2-t] = b[t]
-__global__ void k_kd_chunk(const Fr* __restrict__ a, size_t n, Fr zz, uint32_t len, Fr* __restrict__ Lc) {
+__device__ __forceinline__ void k_kd_chunk_body(const Fr* __restrict__ a, size_t n, const Fr& zz, uint32_t len, Fr* __restrict__ Lc) {
   uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
   size_t m = n - 1;
   size_t b = (size_t)c * len;
@@ -171,8 +171,11 @@ __global__ void k_kd_chunk(const Fr* __restrict__ a, size_t n, Fr zz, uint32_t l
   for (size_t t = b; t < e; t++) acc = fp_add(ldf(a + (n - 1 - t)), fp_mul(zz, acc));
   stf(Lc + c, acc);
 }
+__global__ void k_kd_chunk(const Fr* __restrict__ a, size_t n, Fr zz, uint32_t len, Fr* __restrict__ Lc) {
+  k_kd_chunk_body(a, n, zz, len, Lc);
+}
 // carry[c] = b[c*len - 1] = sum_{c' < c} M^(c-1-c') L[c'], M = zz^len
-__global__ void __launch_bounds__(1024) k_kd_block_scan(const Fr* __restrict__ Lc, uint32_t chunks, Fr M, Fr* __restrict__ carry) {
+__device__ __forceinline__ void k_kd_block_scan_body(const Fr* __restrict__ Lc, uint32_t chunks, const Fr& M, Fr* __restrict__ carry) {
   __shared__ Fr sm[1024];
   const uint32_t t = threadIdx.x;
   Fr zero = fp_zero<FrParams>();
@@ -197,7 +200,11 @@ __global__ void __launch_bounds__(1024) k_kd_block_scan(const Fr* __restrict__ L
   if (2 * t < chunks) stf(carry + 2 * t, excl);
   if (2 * t + 1 < chunks) stf(carry + 2 * t + 1, fp_add(l0, fp_mul(M, excl)));
 }
-__global__ void k_kd_apply(const Fr* __restrict__ a, size_t n, Fr zz, uint32_t len, const Fr* __restrict__ carry, Fr* __restrict__ q) {
+__global__ void __launch_bounds__(1024) k_kd_block_scan(const Fr* __restrict__ Lc, uint32_t chunks, Fr M, Fr* __restrict__ carry) {
+  k_kd_block_scan_body(Lc, chunks, M, carry);
+}
+__device__ __forceinline__ void k_kd_apply_body(const Fr* __restrict__ a, size_t n, const Fr& zz, uint32_t len,
+                                                const Fr* __restrict__ carry, Fr* __restrict__ q) {
   uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
   size_t m = n - 1;
   size_t b = (size_t)c * len;
@@ -208,6 +215,9 @@ __global__ void k_kd_apply(const Fr* __restrict__ a, size_t n, Fr zz, uint32_t l
     acc = fp_add(ldf(a + (n - 1 - t)), fp_mul(zz, acc));
     stf(q + (m - 1 - t), acc);
   }
+}
+__global__ void k_kd_apply(const Fr* __restrict__ a, size_t n, Fr zz, uint32_t len, const Fr* __restrict__ carry, Fr* __restrict__ q) {
+  k_kd_apply_body(a, n, zz, len, carry, q);
 }
 
 // ---- evaluation at points ---------------------------------------------------------------------------
@@ -459,6 +469,46 @@ void fr_eval_many(const Fr* const* polys_dev, const uint32_t* point_idx_dev, con
   k_eval_final<<<blocks_for(count, 64), 64, 0, st>>>(scratch, per, count, out_dev);
   lc++;
 }
+// ---- batched GWC witnesses: sets are grid.y ------------------------------------------------------------
+__global__ void k_gwc_fold(const Fr* const* __restrict__ polys, const Fr* __restrict__ coeff, GwcBatch B, size_t n, Fr* __restrict__ fold) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t g = blockIdx.y;
+  if (i >= n) return;
+  Fr acc = fp_zero<FrParams>();
+  for (uint32_t j = B.off[g]; j < B.off[g + 1]; j++) acc = fp_add(acc, fp_mul(ldf(polys[j] + i), ldf(coeff + j)));
+  if (i == 0) acc = fp_sub(acc, B.sub0[g]);
+  stf(fold + (size_t)g * n + i, acc);
+}
+__global__ void k_gwc_kd_chunk(const Fr* __restrict__ fold, size_t n, GwcBatch B, uint32_t len, Fr* __restrict__ scratch) {
+  const uint32_t g = blockIdx.y;
+  k_kd_chunk_body(fold + (size_t)g * n, n, B.z[g], len, scratch + (size_t)g * 2 * SCAN_MAX_CHUNKS);
+}
+__global__ void __launch_bounds__(1024) k_gwc_kd_block_scan(GwcBatch B, uint32_t chunks, Fr* __restrict__ scratch) {
+  const uint32_t g = blockIdx.x;
+  Fr* Lc = scratch + (size_t)g * 2 * SCAN_MAX_CHUNKS;
+  k_kd_block_scan_body(Lc, chunks, B.M[g], Lc + SCAN_MAX_CHUNKS);
+}
+__global__ void k_gwc_kd_apply(const Fr* __restrict__ fold, size_t n, GwcBatch B, uint32_t len, const Fr* __restrict__ scratch,
+                               Fr* __restrict__ q) {
+  const uint32_t g = blockIdx.y;
+  k_kd_apply_body(fold + (size_t)g * n, n, B.z[g], len, scratch + (size_t)g * 2 * SCAN_MAX_CHUNKS + SCAN_MAX_CHUNKS, q + (size_t)g * n);
+}
+
+void fr_gwc_witness_batch(const Fr* const* polys_dev, const Fr* coeff_dev, GwcBatch B, size_t n, Fr* fold, Fr* q, Fr* scratch,
+                          cudaStream_t st, LaunchCounter lc) {
+  if (!B.nsets || n < 2) return;
+  ScanGeom g = scan_geom(n - 1);
+  for (uint32_t s = 0; s < B.nsets; s++) B.M[s] = fp_pow_var(B.z[s], (uint64_t)g.len);
+  k_gwc_fold<<<dim3(blocks_for(n), B.nsets), EW_THREADS, 0, st>>>(polys_dev, coeff_dev, B, n, fold);
+  lc++;
+  k_gwc_kd_chunk<<<dim3(blocks_for(g.chunks, 128), B.nsets), 128, 0, st>>>(fold, n, B, g.len, scratch);
+  lc++;
+  k_gwc_kd_block_scan<<<B.nsets, 1024, 0, st>>>(B, g.chunks, scratch);
+  lc++;
+  k_gwc_kd_apply<<<dim3(blocks_for(g.chunks, 128), B.nsets), 128, 0, st>>>(fold, n, B, g.len, scratch, q);
+  lc++;
+}
+
 void fr_linear_combination(const Fr* const* polys_dev, const Fr* coeff_dev, uint32_t count, size_t n, const Fr& sub0, Fr* out,
                            cudaStream_t st, LaunchCounter lc) {
   k_linear_combination<<<blocks_for(n), EW_THREADS, 0, st>>>(polys_dev, coeff_dev, count, n, sub0, out);

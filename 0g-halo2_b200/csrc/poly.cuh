@@ -44,6 +44,16 @@ void fr_eval_many(const Fr* const* polys_dev, const uint32_t* point_idx_dev, con
 // out[i] = sum_j coeff[j] * polys[j][i], then out[0] -= sub0   (GWC fold by powers of v; h_poly from pieces)
 void fr_linear_combination(const Fr* const* polys_dev, const Fr* coeff_dev, uint32_t count, size_t n, const Fr& sub0,
                            Fr* out, cudaStream_t st, LaunchCounter lc);
+// ProverGWC witnesses for up to 8 opening points in four launches: set g folds polys[off[g] .. off[g+1]) with the
+// matching coefficients (powers of v), subtracts sub0[g] (the folded evaluation) from the constant term and divides
+// by (X - z[g]).  fold and q hold nsets columns of n; scratch >= nsets * 4096 Fr.  M is filled in by the callee.
+struct GwcBatch {
+  uint32_t nsets;
+  uint32_t off[9];
+  Fr sub0[8], z[8], M[8];
+};
+void fr_gwc_witness_batch(const Fr* const* polys_dev, const Fr* coeff_dev, GwcBatch B, size_t n, Fr* fold, Fr* q, Fr* scratch,
+                          cudaStream_t st, LaunchCounter lc);
 // out[i] = a[i] * b[i]
 void fr_mul_vec(const Fr* a, const Fr* b, Fr* out, size_t n, cudaStream_t st, LaunchCounter lc);
 // permutation argument, one column set: num[i] = prod_j (v_j[i] + delta_start*delta^j * beta * w^i + gamma),

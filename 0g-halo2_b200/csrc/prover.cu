@@ -474,8 +474,8 @@ int zg_pk_load(zg_ctx* ctx, const zg_pk_desc* d, zg_pk** out) {
     pk->pz_coset = b.take<Fr>(S * N); pk->lk_cosets = b.take<Fr>(3 * (size_t)Lk * N);
     pk->frac = b.take<Fr>(n); pk->rnd = b.take<Fr>(pk->n_draws); pk->random_poly = pk->rnd;  // set per proof
     pk->h = b.take<Fr>(N); pk->h_coeff = b.take<Fr>(N); pk->h_poly = b.take<Fr>(n);
-    pk->fold = b.take<Fr>(n); pk->wpoly = b.take<Fr>(8 * n);
-    pk->scratch = b.take<Fr>(8192 + std::max<size_t>(64, (n + 4095) / 4096) * (size_t)n_queries);
+    pk->fold = b.take<Fr>(8 * n); pk->wpoly = b.take<Fr>(8 * n);
+    pk->scratch = b.take<Fr>(8 * 4096 + std::max<size_t>(64, (n + 4095) / 4096) * (size_t)n_queries);
     pk->evals_dev = b.take<Fr>(n_queries + 8); pk->points_dev = b.take<Fr>(16); pk->coeff_dev = b.take<Fr>(n_queries + 8);
     pk->one_dev = b.take<Fr>(8);
     pk->d_polyptrs = b.take<const Fr*>(n_queries + 8); pk->d_pidx = b.take<uint32_t>(n_queries + 8);
@@ -940,7 +940,7 @@ static int create_proof_impl(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice,
   ZG_CUDA(cudaMemcpyAsync(pk->d_polyptrs, qptr.data(), qptr.size() * sizeof(Fr*), cudaMemcpyHostToDevice, st));
   ZG_CUDA(cudaMemcpyAsync(pk->d_pidx, pidx.data(), pidx.size() * 4, cudaMemcpyHostToDevice, st));
   ZG_CUDA(cudaMemcpyAsync(pk->points_dev, points.data(), points.size() * sizeof(Fr), cudaMemcpyHostToDevice, st));
-  fr_eval_many(pk->d_polyptrs, pk->d_pidx, pk->points_dev, (uint32_t)Q.size(), n, pk->evals_dev, pk->scratch + 8192, st, lc);
+  fr_eval_many(pk->d_polyptrs, pk->d_pidx, pk->points_dev, (uint32_t)Q.size(), n, pk->evals_dev, pk->scratch + 8 * 4096, st, lc);
   std::vector<Fr> evals(Q.size());
   ZG_CUDA(cudaMemcpyAsync(evals.data(), pk->evals_dev, sizeof(Fr) * Q.size(), cudaMemcpyDeviceToHost, st));
   ZG_CUDA(cudaEventRecord(ev[6], st));
@@ -986,10 +986,12 @@ static int create_proof_impl(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice,
   }
   ZG_CUDA(cudaMemcpyAsync(pk->d_polyptrs, gp.data(), gp.size() * sizeof(Fr*), cudaMemcpyHostToDevice, st));
   ZG_CUDA(cudaMemcpyAsync(pk->coeff_dev, gc.data(), gc.size() * sizeof(Fr), cudaMemcpyHostToDevice, st));
-  for (uint32_t g = 0; g < nsetsQ; g++) {
-    fr_linear_combination(pk->d_polyptrs + goff[g], pk->coeff_dev + goff[g], (uint32_t)(goff[g + 1] - goff[g]), n, eaccs[g], pk->fold,
-                          st, lc);
-    fr_kate_division(pk->fold, n, points[g], pk->wpoly + g * n, pk->scratch, st, lc);
+  {
+    GwcBatch gb;
+    gb.nsets = nsetsQ;
+    for (uint32_t g = 0; g <= nsetsQ; g++) gb.off[g] = (uint32_t)goff[g];
+    for (uint32_t g = 0; g < nsetsQ; g++) { gb.sub0[g] = eaccs[g]; gb.z[g] = points[g]; }
+    fr_gwc_witness_batch(pk->d_polyptrs, pk->coeff_dev, gb, n, pk->fold, pk->wpoly, pk->scratch, st, lc);
   }
   {
     std::vector<Affine> aff(nsetsQ);
