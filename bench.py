@@ -188,7 +188,7 @@ def run_reference(args, rank, world):
         return
     import bn254
     import cpu_ref
-    cores = cpu_ref.num_threads()
+    cores = cpu_ref.use_all_cores()
     if args.workload == "proof":
         import halo2_ref as H
         wnn, img, k = load_model(args.model)
@@ -529,7 +529,7 @@ def main():
     out.update(extra)
     if cpu_fn is not None:
         import cpu_ref
-        cores = cpu_ref.num_threads()
+        cores = cpu_ref.use_all_cores()
         cpu_fn()
         reps, t0 = 0, time.perf_counter()
         while reps < 2 or (time.perf_counter() - t0 < 10 and reps < 20):

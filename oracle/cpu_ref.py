@@ -62,6 +62,12 @@ def num_threads() -> int:
     return lib().zgo_num_threads()
 
 
+def use_all_cores() -> int:
+    """OpenMP threads = host cores, whatever OMP_NUM_THREADS says (torchrun sets it to 1 in its workers)."""
+    lib().zgo_set_num_threads(ctypes.c_int(os.cpu_count() or 1))
+    return num_threads()
+
+
 def best_multiexp(coeffs: np.ndarray, bases: np.ndarray, threads: int = 0) -> np.ndarray:
     """halo2 best_multiexp; coeffs (n,4) Fr Montgomery, bases (n,8) G1Affine -> (12,) Jacobian."""
     coeffs, bases = _fr(coeffs), np.ascontiguousarray(bases, dtype=np.uint64)

@@ -628,6 +628,8 @@ void zgo_g1_fixed_base_mul_many(const fe* scalars, const g1a* gen, size_t n, g1a
   }
 }
 int zgo_num_threads(void) { return omp_get_max_threads(); }
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline asks for all host cores explicitly */
+void zgo_set_num_threads(int t) { if (t > 0) omp_set_num_threads(t); }
 
 /* Synthetic SRS-shaped bases for benchmarks: out[i] = [start + i + 1] * gen, affine.
  * (A real ParamsKZG basis is [s^i]G; for timing an MSM any distinct curve points do.)
