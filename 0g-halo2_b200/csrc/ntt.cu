@@ -206,6 +206,13 @@ cudaError_t ntt_run(const NttPlan& P, cudaStream_t stream, uint64_t* nl) {
   const uint32_t logn = P.logn;
   uint32_t npass = (logn + NTT_MAX_S - 1) / NTT_MAX_S;
   if (npass == 0) npass = 1;
+  // a lone small transform would run on a handful of CTAs: trade one more pass for a grid that covers the SMs
+  while (npass < 4 && logn >= 5 * (npass + 1)) {
+    uint32_t S0 = (logn + npass - 1) / npass;
+    uint64_t ctas = ((uint64_t)1 << (logn - S0 - (logn - S0 >= NTT_LOGC ? NTT_LOGC : logn - S0))) * P.batch;
+    if (ctas >= 148) break;
+    npass++;
+  }
   uint32_t bits_left = logn;
   uint32_t hi = logn;
   // the attribute is per device; one process may drive several devices / host threads

@@ -39,15 +39,20 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(ScanJobs J, uint32_t n, uin
   const uint32_t* in = J.in[job];
   uint32_t* out = J.out[job];
   uint32_t* out2 = J.out2[job];
-  const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * 4;
-  uint32_t v[4];
+  constexpr int E = (int)SCAN_PER_THREAD;
+  const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * E;
+  uint32_t v[E];
+  uint32_t sum = 0;
 #pragma unroll
-  for (int i = 0; i < 4; i++) v[i] = (base + i < n) ? in[base + i] : 0u;
+  for (int i = 0; i < E; i++) {
+    v[i] = (base + i < n) ? in[base + i] : 0u;
+    sum += v[i];
+  }
   uint32_t total;
-  uint32_t run = block_excl_scan_1024(v[0] + v[1] + v[2] + v[3], warp_sums, total);
+  uint32_t run = block_excl_scan_1024(sum, warp_sums, total);
   const bool final_pass = tiles == 1;
 #pragma unroll
-  for (int i = 0; i < 4; i++) {
+  for (int i = 0; i < E; i++) {
     if (base + i < n) {
       out[base + i] = run;
       if (final_pass && out2) out2[base + i] = run;
@@ -75,9 +80,9 @@ __global__ void __launch_bounds__(1024) k_scan_add_base(ScanJobs J, uint32_t n, 
   for (uint32_t b = threadIdx.x; b < tile; b += 1024) part += ts[b];
   uint32_t total;
   block_excl_scan_1024(part, warp_sums, total);   // total = sum of the tiles before this one
-  const uint32_t base = tile * SCAN_TILE + threadIdx.x * 4;
+  const uint32_t base = tile * SCAN_TILE + threadIdx.x * SCAN_PER_THREAD;
 #pragma unroll
-  for (int i = 0; i < 4; i++) {
+  for (int i = 0; i < (int)SCAN_PER_THREAD; i++) {
     if (base + i < n) {
       uint32_t r = out[base + i] + total;
       out[base + i] = r;

@@ -7,7 +7,8 @@
 
 namespace zg {
 
-constexpr uint32_t SCAN_TILE = 4096;   // counters per CTA (1024 threads x 4)
+constexpr uint32_t SCAN_PER_THREAD = 8;
+constexpr uint32_t SCAN_TILE = 1024 * SCAN_PER_THREAD;   // counters per CTA (a whole radix pass of the k = 15 lookups is one tile)
 constexpr uint32_t SCAN_MAX_JOBS = 4;
 
 struct ScanJobs {
