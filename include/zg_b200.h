@@ -136,7 +136,12 @@ void zg_pk_free(zg_ctx* ctx, zg_pk* pk);
 /* VerifyingKey: fixed_commitments (num_fixed) and permutation commitments (m), affine */
 int zg_pk_commitments(zg_ctx* ctx, const zg_pk* pk, zg_g1_affine* fixed_out, zg_g1_affine* sigma_out);
 /* advice: num_advice columns of 2^k values, host pointers (or device pointers on the context's device: the
- * copy is direction-agnostic); rows >= 2^k - blinding_factors - 1 are replaced by blinding scalars; instances: num_instance host columns with their lengths.  Writes the proof bytes. */
+ * copy is direction-agnostic); rows >= 2^k - blinding_factors - 1 are replaced by blinding scalars; instances:
+ * num_instance host columns with their lengths.  Writes the proof bytes.
+ * Host-synchronous: the proof is ordered after the work already enqueued on the context's stream, runs on two
+ * context-owned streams (critical path at the highest priority, coefficient / extended-coset transforms at the lowest)
+ * and has completed when the call returns.  Contexts are independent: one host thread per context may prove
+ * concurrently on the same GPU (each with its own SRS tables and zg_pk). */
 int zg_create_proof(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice, const zg_fr* const* instances,
                     const size_t* instance_lens, zg_rng_fill_fn rng, void* rng_state, uint8_t* proof_out,
                     size_t proof_cap, size_t* proof_len);
