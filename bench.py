@@ -56,6 +56,10 @@ def parse():
     ap.add_argument("--inflight", type=int, default=int(os.environ.get("ZG_BENCH_INFLIGHT", "4")),
                     help="proof workload: independent proofs in flight per GPU (one context + stream + host thread each); "
                          "a step is one batch of that many proofs")
+    ap.add_argument("--images", type=int, default=int(os.environ.get("ZG_BENCH_IMAGES", "1")),
+                    help="proof workload: 1 = benches/example_image_7.png for every proof (the reference's bench input); "
+                         "K > 1 = K distinct synthetic MNIST-shaped images per rank, proofs cycle through them "
+                         "(BASELINE configs[4]); witnesses are synthesized once, untimed")
     return ap.parse_args()
 
 
@@ -270,9 +274,16 @@ def main():
         wnn, img, k = load_model(args.model)
         n = 1 << k
         srs = H.Srs(k, SRS_SECRET)
-        _, asm = wnn.synthesize(img, k)
-        outputs = wnn.predict(img)
-        inst = [to_limbs(list(outputs))]
+        # the inputs every proof cycles through: (advice columns, public outputs) per image
+        from zg_b200.io import synthetic_image
+        nimg = max(1, args.images)
+        imgs = [img] if nimg == 1 else [synthetic_image(rank * nimg + i, wnn.img_shape()) for i in range(nimg)]
+        witnesses = []
+        for im in imgs:
+            _, a = wnn.synthesize(im, k)
+            o = wnn.predict(im)
+            witnesses.append((a.advice, o, [to_limbs(list(o))]))
+        asm_advice, outputs, inst = witnesses[0]
 
         class DevCol:                              # quacks like a numpy column for create_proof_limbs
             def __init__(self, t):
@@ -287,21 +298,33 @@ def main():
                 params = ParamsKZG(k, srs.g, srs.g_lagrange)
                 circ0, asm0 = wnn.synthesize(np.zeros(wnn.img_shape(), dtype=np.uint8), k)
                 self.pk = keygen(lane_ctx, params, circ0.cs, asm0)
-                self.adv_host_t = [torch.from_numpy(a.view(np.int64)).pin_memory() for a in advice_to_mont(lane_ctx, asm.advice)]
-                self.adv_host = [t.numpy().view(np.uint64) for t in self.adv_host_t]
-                self.adv_dev_t = [t.cuda() for t in self.adv_host_t]
-                self.adv_dev = [DevCol(t) for t in self.adv_dev_t]
+                self.adv_host_t, self.adv_host, self.adv_dev_t, self.adv_dev = [], [], [], []
+                for adv, _, _ in witnesses:
+                    ht = [torch.from_numpy(a.view(np.int64)).pin_memory() for a in advice_to_mont(lane_ctx, adv)]
+                    dt = [t.cuda() for t in ht]
+                    self.adv_host_t.append(ht)
+                    self.adv_host.append([t.numpy().view(np.uint64) for t in ht])
+                    self.adv_dev_t.append(dt)
+                    self.adv_dev.append([DevCol(t) for t in dt])
                 self.seed = rank * 100000 + idx * 1000
+                self.turn = idx                      # which image this lane proves next
 
             def rng(self):
                 self.seed += 1
                 return zg_b200.lib.XorShift.from_seed(int(self.seed).to_bytes(16, "little"))
 
+            def _next(self):
+                w = self.turn % len(witnesses)
+                self.turn += K
+                return w
+
             def prove_dev(self):
-                return create_proof_limbs(self.pk, self.adv_dev, inst, self.rng())
+                w = self._next()
+                return w, create_proof_limbs(self.pk, self.adv_dev[w], witnesses[w][2], self.rng())
 
             def prove_e2e(self):
-                return create_proof_limbs(self.pk, self.adv_host, inst, self.rng())
+                w = self._next()
+                return w, create_proof_limbs(self.pk, self.adv_host[w], witnesses[w][2], self.rng())
 
         K = max(1, args.inflight)
         lane_streams = [stream] + [torch.cuda.Stream() for _ in range(K - 1)]
@@ -321,14 +344,20 @@ def main():
             circ_o, asm_o = wnn.synthesize(np.zeros(wnn.img_shape(), dtype=np.uint8), k)
             opk = H.keygen(srs, circ_o.cs, asm_o)
             assert pk.fixed_commitments == opk.fixed_commitments and pk.perm_commitments == opk.perm_commitments
-            for pr in step_e2e():
-                assert H.verify_proof(srs, opk, [outputs], pr), "GPU proof rejected by the restated verifier"
+            seen = set()
+            for _ in range((len(witnesses) + K - 1) // K + 1):
+                for w, pr in step_e2e():
+                    if w not in seen:
+                        assert H.verify_proof(srs, opk, [witnesses[w][1]], pr), "GPU proof rejected by the restated verifier"
+                        seen.add(w)
+            assert len(seen) == len(witnesses), "not every image was proven during the check"
         metric, unit, units = "proofs_per_s", "proofs/s", K
-        h2d, d2h = K * (len(lanes[0].adv_host) * n * 32 + len(outputs) * 32), K * 3840
+        h2d, d2h = K * (len(lanes[0].adv_host[0]) * n * 32 + len(outputs) * 32), K * 3840
         dom_kernel = "msm_accumulate_kernel"
         extra["inflight"] = K
+        extra["images"] = "example_image_7.png" if nimg == 1 else "%d synthetic MNIST-shaped images per rank" % nimg
         if not args.no_cpu_baseline and rank == 0:
-            cpu_fn = lambda: H.create_proof(srs, opk, asm.advice, [outputs], H.XorShiftRng(bytes(range(16))), real_msm=True)
+            cpu_fn = lambda: H.create_proof(srs, opk, asm_advice, [outputs], H.XorShiftRng(bytes(range(16))), real_msm=True)
             cpu_units = 1
     elif args.workload == "msm":
         bases = synth_bases(n)
