@@ -173,6 +173,10 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nthreads) return;
   const uint32_t L = *count_ptr;
+  // equal shares of the REAL list (its length is only known on the device: zero digits were skipped), never below the
+  // minimum chunk K: the grid is sized to whole waves of resident CTAs, so every SM finishes at the same time
+  const uint32_t share = (uint32_t)(((uint64_t)L + nthreads - 1) / nthreads);
+  if (share > K) K = share;
   const uint64_t start64 = (uint64_t)t * K;
   if (start64 >= L) {
     pkeys[2 * t] = MSM_INVALID_KEY;
@@ -226,6 +230,23 @@ void msm_tail_buckets(const G1Xyzz* buckets, uint32_t NB, uint32_t M, G1Xyzz* s1
                       cudaStream_t st);
 
 // ---- host side ---------------------------------------------------------------------------
+// threads of one full wave of msm_accumulate_kernel on the current device (resident CTAs per SM x SMs x 128)
+static uint32_t msm_accumulate_wave_threads() {
+  static std::atomic<uint32_t> cached[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  uint32_t v = cached[dev & 63].load(std::memory_order_acquire);
+  if (v) return v;
+  int per_sm = 0, sms = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, msm_accumulate_kernel, 128, 0);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (per_sm < 1) per_sm = 3;
+  if (sms < 1) sms = 148;
+  v = (uint32_t)per_sm * (uint32_t)sms * 128u;
+  cached[dev & 63].store(v, std::memory_order_release);
+  return v;
+}
+
 uint32_t msm_pick_c(uint32_t k) {
   if (const char* e = getenv("ZG_MSM_C")) {
     int v = atoi(e);
@@ -245,8 +266,22 @@ MsmWorkspaceLayout msm_workspace_layout(uint32_t n, uint32_t c, uint32_t W, uint
   l.NB = 1u << (c - 1);
   uint64_t lmax = (uint64_t)n * W * M;
   l.L_max = (uint32_t)lmax;
+  // accumulation geometry: K0 entries per thread (32 for long lists: fewer chunk-boundary partials for the tail; measured
+  // best of 8/16/32/64 for the k = 15 and k = 17 proofs, profiles/r01_notes.md).  ZG_MSM_WAVES caps the grid at that many
+  // full waves of resident CTAs instead, the kernel then giving every thread an equal share of the real list -- measured
+  // slower (one wave: 0.75 vs 0.83 of the IMAD peak at 2^20: no back-fill when SMs finish unevenly), kept for tuning.
   l.K0 = lmax >= (2u << 20) ? 32 : 16;
-  l.T0 = (uint32_t)((lmax + l.K0 - 1) / l.K0);
+  if (const char* e = getenv("ZG_MSM_K0")) {          // tuning override: minimum entries per thread
+    int v = atoi(e);
+    if (v >= 4 && v <= 256) l.K0 = (uint32_t)v;
+  }
+  uint64_t t_cap = ~0ull;
+  if (const char* e = getenv("ZG_MSM_WAVES")) {
+    int v = atoi(e);
+    if (v >= 1 && v <= 64) t_cap = (uint64_t)msm_accumulate_wave_threads() * (uint64_t)v;
+  }
+  const uint64_t t_dense = (lmax + l.K0 - 1) / l.K0;
+  l.T0 = (uint32_t)(t_dense < t_cap ? t_dense : t_cap);
   l.slots_a = 2 * l.T0;
   // level 1 (serial, K = 16) or first warp level consumes slots_a
   uint32_t t1s = (l.slots_a + MSM_LEVEL1_K - 1) / MSM_LEVEL1_K, t1w = (l.slots_a + 31) / 32;
