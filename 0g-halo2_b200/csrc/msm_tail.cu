@@ -9,11 +9,6 @@
 
 namespace zg {
 
-__device__ __forceinline__ void ld_fq2(const G1Affine* p, Fq& x, Fq& y) {   // only referenced by the LEVEL0 branch
-  x = p->x;
-  y = p->y;
-}
-
 __device__ __forceinline__ G1Xyzz shfl_down_xyzz(const G1Xyzz& p, int d) {
   G1Xyzz r;
 #pragma unroll
@@ -26,43 +21,29 @@ __device__ __forceinline__ G1Xyzz shfl_down_xyzz(const G1Xyzz& p, int d) {
   return r;
 }
 
-// ---- serial segmented reduction over the sorted list -----------------------------------
-// LEVEL0: entries are (key, table index|sign) and are gathered from the affine window table.
-// !LEVEL0: entries are (key, XYZZ partial sum).
+// ---- serial segmented reduction over a list of (key, XYZZ partial sum) entries -------------------------
+// (level 0, over the packed table-index entries, is msm_accumulate_kernel in msm.cu.)
 // Thread t owns entries [t*K, t*K+K).  Runs strictly inside the chunk go straight to their bucket
 // (nobody else holds that key); the first and last runs go to partial slots 2t, 2t+1.
-template <bool LEVEL0>
 __global__ void __launch_bounds__(128) msm_serial_reduce_kernel(
-    const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
-    const G1Xyzz* __restrict__ pts_in, const uint32_t* __restrict__ count_ptr, uint32_t count_static,
-    const G1Affine* __restrict__ table, uint32_t K, G1Xyzz* __restrict__ buckets,
-    uint32_t* __restrict__ pkeys, G1Xyzz* __restrict__ ppts, uint32_t nthreads) {
+    const uint32_t* __restrict__ keys, const G1Xyzz* __restrict__ pts_in, uint32_t L, uint32_t K,
+    G1Xyzz* __restrict__ buckets, uint32_t* __restrict__ pkeys, G1Xyzz* __restrict__ ppts, uint32_t nthreads) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nthreads) return;
-  const uint32_t L = count_ptr ? *count_ptr : count_static;
   const uint64_t start64 = (uint64_t)t * K;
-  if (start64 >= L) {
+  uint32_t cur = start64 < L ? keys[start64] : MSM_INVALID_KEY;
+  if (cur == MSM_INVALID_KEY) {   // past the end, or the list ends in invalid slots
     pkeys[2 * t] = MSM_INVALID_KEY;
     pkeys[2 * t + 1] = MSM_INVALID_KEY;
     return;
   }
   const uint32_t start = (uint32_t)start64;
   const uint32_t end = (start64 + K < L) ? start + K : L;
-  uint32_t cur = keys[start];
-  uint32_t e = start;
-  if (!LEVEL0) {
-    // the list may end in invalid slots
-    if (cur == MSM_INVALID_KEY) {
-      pkeys[2 * t] = MSM_INVALID_KEY;
-      pkeys[2 * t + 1] = MSM_INVALID_KEY;
-      return;
-    }
-  }
   G1Xyzz acc = xyzz_identity();
   uint32_t nruns = 0;
-  for (; e < end; e++) {
+  for (uint32_t e = start; e < end; e++) {
     uint32_t k = keys[e];
-    if (!LEVEL0 && k == MSM_INVALID_KEY) break;
+    if (k == MSM_INVALID_KEY) break;
     if (k != cur) {
       if (nruns == 0) {
         pkeys[2 * t] = cur;
@@ -74,17 +55,8 @@ __global__ void __launch_bounds__(128) msm_serial_reduce_kernel(
       cur = k;
       acc = xyzz_identity();
     }
-    if (LEVEL0) {
-      uint32_t v = vals[e];
-      Fq x, y;
-      ld_fq2(table + (v & 0x7fffffffu), x, y);
-      if (fp_is_zero(x) && fp_is_zero(y)) continue;
-      if (v >> 31) y = fp_neg(y);
-      xyzz_madd(acc, x, y);
-    } else {
-      G1Xyzz p = pts_in[e];
-      xyzz_add(acc, p);
-    }
+    G1Xyzz p = pts_in[e];
+    xyzz_add(acc, p);
   }
   if (nruns == 0) {
     pkeys[2 * t] = cur;
@@ -307,8 +279,7 @@ __global__ void __launch_bounds__(96) msm_finish_kernel(const G1Xyzz* __restrict
 // ---- launchers called from msm_run (msm.cu) -------------------------------------------------------------
 void msm_tail_serial_level(const uint32_t* keys, const G1Xyzz* pts, uint32_t slots, G1Xyzz* buckets, uint32_t* pkeys_out,
                            G1Xyzz* ppts_out, uint32_t T1, cudaStream_t st) {
-  msm_serial_reduce_kernel<false><<<(T1 + 127) / 128, 128, 0, st>>>(keys, nullptr, pts, nullptr, slots, nullptr, MSM_LEVEL1_K, buckets,
-                                                                     pkeys_out, ppts_out, T1);
+  msm_serial_reduce_kernel<<<(T1 + 127) / 128, 128, 0, st>>>(keys, pts, slots, MSM_LEVEL1_K, buckets, pkeys_out, ppts_out, T1);
 }
 void msm_tail_warp_level(const uint32_t* keys, const G1Xyzz* pts, uint32_t slots, G1Xyzz* buckets, uint32_t* pkeys_out,
                          G1Xyzz* ppts_out, uint32_t nwarps, int fin, cudaStream_t st) {

@@ -266,3 +266,15 @@ def read_srs(path: str):
         if len(s_g2) != 128 or f.read(1):
             raise ValueError("SRS file: unexpected length for k = %d" % k)
     return k, g, gl, g2, s_g2
+
+
+def encode_calldata(instances, proof: bytes) -> bytes:
+    """snark_verifier::loader::evm::encode_calldata as called at src/eth.rs:114 / :211 [UPSTREAM-RECALLED]: every public
+    input as a 32-byte big-endian canonical scalar, instance columns in order, followed by the proof bytes -- the
+    calldata the generated EVM verifier takes."""
+    from .bn254_host import R_MOD
+    out = bytearray()
+    for col in instances:
+        for v in col:
+            out += (int(v) % R_MOD).to_bytes(32, "big")
+    return bytes(out) + bytes(proof)

@@ -10,6 +10,7 @@ Workloads:
                    k = 15) on benches/example_image_7.png.  Witness synthesis is host work outside the
                    replaced path (BASELINE north_star) and is done once, untimed, for both arms.
   msm              one 2^LOGN-point BN254 G1 MSM per step (uniform scalars)      -> points/s
+  keygen           keygen_vk + keygen_pk of `--model` on the device (benches/bench.rs bench_key_generation)  -> keygens/s
   msm_sharded      ONE 2^LOGN-point MSM split by point range over the ranks, partial sums all-gathered (NCCL)
                    and added (strong scaling, BASELINE configs[3])                -> points/s
   ntt              one 2^LOGN-point BN254 Fr NTT per step                        -> GB/s (algorithmic)
@@ -435,6 +436,32 @@ def main():
         if not args.no_cpu_baseline and rank == 0:
             import cpu_ref
             cpu_fn = lambda: cpu_ref.best_fft(a_host, w, logn)
+    elif args.workload == "keygen":
+        # keygen_vk + keygen_pk on the device (benches/bench.rs:24-28 `bench_key_generation`): commitments of the 16 fixed and
+        # 8 sigma columns, their coefficient and extended-coset forms, l_0 / l_last / l_active.  Host circuit synthesis and
+        # selector compression are done once, untimed (they stay on the host in the reference too).
+        import halo2_ref as H
+        from zg_b200.plonk.mock import finalize_fixed
+        from zg_b200.plonk.serialize import serialize_cs
+        from zg_b200.prover import ParamsKZG, _load_pk, ints_to_canonical
+        wnn, img, k = load_model(args.model)
+        n = 1 << k
+        srs = H.Srs(k, SRS_SECRET)
+        params = ParamsKZG(k, srs.g, srs.g_lagrange)
+        params.load(ctx)
+        circ0, asm0 = wnn.synthesize(np.zeros(wnn.img_shape(), dtype=np.uint8), k)
+        fixed_int = finalize_fixed(circ0.cs, asm0)
+        words, constants = serialize_cs(circ0.cs)
+        fixed_mont = [ctx.debug_field_op(0, 7, ints_to_canonical(c)) for c in fixed_int]
+        mapping = np.ascontiguousarray(np.array(asm0.mapping, dtype=np.uint32).reshape(len(asm0.perm_cols), asm0.n, 2))
+
+        def step_dev():
+            h = _load_pk(ctx, params, circ0.cs, words, constants, fixed_mont, mapping, 1)
+            ctx._L.zg_pk_free(ctx._h, h)
+        step_e2e = step_dev                        # zg_pk_load always takes host columns
+        metric, unit, units = "keygens_per_s", "keygens/s", 1
+        h2d, d2h = (len(fixed_mont) + 2 * len(asm0.perm_cols) // 8) * n * 32, (len(fixed_mont) + len(asm0.perm_cols)) * 64
+        dom_kernel = "msm_accumulate_kernel"
     else:
         raise SystemExit("unknown workload %s" % args.workload)
 
@@ -533,6 +560,8 @@ def main():
         roof = kernel_roofline(probe, imad_peak, ms, peak_src="measured in this run (zg_bench_int_pipe kind 0)",
                                traffic=NCU_TRAFFIC.get("%s_%d" % (args.workload, logn)))
         extra["step_roofline"] = step_roof
+    elif args.workload == "keygen":
+        roof = None                                # a secondary number: no roofline claim (24 MSMs + 27 extended NTTs + uploads)
     else:
         imad, c = proof_msm_imad(n, k)
         # MSM share of the step: stages that are MSM-dominated are reported by the library per proof

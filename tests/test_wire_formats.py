@@ -40,3 +40,13 @@ def test_srs_raw_bytes_round_trip(tmp_path):
     assert (tmp_path / "kzg.srs").stat().st_size == 4 + 2 * 16 * 64 + 256
     k2, g_, gl_, g2_, sg2_ = zio.read_srs(path)
     assert k2 == k and (g_ == g).all() and (gl_ == gl).all() and g2_ == g2 and sg2_ == sg2
+
+
+def test_encode_calldata_layout():
+    outputs = [9, 6, 13, 10, 17, 10, 9, 26, 11, 16]               # tests/integration_test.rs:13-20
+    proof = bytes(range(200))
+    cd = zio.encode_calldata([outputs], proof)
+    assert len(cd) == 32 * len(outputs) + len(proof)
+    assert cd[:32] == (9).to_bytes(32, "big") and cd[32 * 9:32 * 10] == (16).to_bytes(32, "big")
+    assert cd[32 * len(outputs):] == proof
+    assert zio.encode_calldata([[R_MOD + 5]], b"")[-1] == 5        # reduced like Fr
