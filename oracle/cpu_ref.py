@@ -247,3 +247,69 @@ def g1_fixed_base_mul_many(scalars, gen_affine) -> np.ndarray:
     lib().zgo_g1_fixed_base_mul_many(_p(scalars), _p(np.ascontiguousarray(gen_affine, dtype=np.uint64)),
                                      ctypes.c_size_t(scalars.shape[0]), _p(out))
     return out
+
+
+# ---- BN254 pairing (oracle/zg_oracle.c, "BN254 optimal-ate pairing") -----------------------------------
+_Q_MOD = 21888242871839275222246405745257275088696311157297823662689037894645226208583
+_R_MOD = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+_FINAL_EXP = None
+
+
+def _final_exp_words() -> np.ndarray:
+    global _FINAL_EXP
+    if _FINAL_EXP is None:
+        e = (_Q_MOD ** 12 - 1) // _R_MOD
+        n = (e.bit_length() + 63) // 64
+        _FINAL_EXP = np.array([(e >> (64 * i)) & ((1 << 64) - 1) for i in range(n)], dtype=np.uint64)
+    return _FINAL_EXP
+
+
+def g2_generator() -> np.ndarray:
+    """(16,) uint64: x.c0 | x.c1 | y.c0 | y.c1 of the alt_bn128 G2 generator, Montgomery limbs (halo2curves G2Affine layout)."""
+    out = np.zeros(16, dtype=np.uint64)
+    lib().zgo_g2_generator(_p(out))
+    return out
+
+
+def g2_mul(point: np.ndarray, scalar_mont) -> np.ndarray:
+    out = np.zeros(16, dtype=np.uint64)
+    lib().zgo_g2_mul(_p(np.ascontiguousarray(point, dtype=np.uint64)), _p(_fr(scalar_mont)), _p(out))
+    return out
+
+
+def g2_on_curve(point: np.ndarray) -> bool:
+    lib().zgo_g2_on_curve.restype = ctypes.c_int
+    return bool(lib().zgo_g2_on_curve(_p(np.ascontiguousarray(point, dtype=np.uint64))))
+
+
+def pairing(p_affine: np.ndarray, q_g2: np.ndarray) -> np.ndarray:
+    """e(P, Q) as 12 x 4 Montgomery limbs of its Fq12 coefficients (basis 1, w, ..., w^11)."""
+    e = _final_exp_words()
+    out = np.zeros((12, 4), dtype=np.uint64)
+    lib().zgo_pairing(_p(np.ascontiguousarray(p_affine, dtype=np.uint64)), _p(np.ascontiguousarray(q_g2, dtype=np.uint64)),
+                      _p(e), ctypes.c_size_t(e.shape[0]), _p(out))
+    return out
+
+
+def pairing_check(ps: np.ndarray, qs: np.ndarray) -> bool:
+    """prod_i e(P_i, Q_i) == 1; ps (n, 8) G1 affine, qs (n, 16) G2 affine"""
+    ps = np.ascontiguousarray(ps, dtype=np.uint64).reshape(-1, 8)
+    qs = np.ascontiguousarray(qs, dtype=np.uint64).reshape(-1, 16)
+    assert ps.shape[0] == qs.shape[0]
+    e = _final_exp_words()
+    lib().zgo_pairing_check.restype = ctypes.c_int
+    return bool(lib().zgo_pairing_check(_p(ps), _p(qs), ctypes.c_size_t(ps.shape[0]), _p(e), ctypes.c_size_t(e.shape[0])))
+
+
+def f12_mul(a, b) -> np.ndarray:
+    out = np.zeros((12, 4), dtype=np.uint64)
+    lib().zgo_f12_mul(_p(np.ascontiguousarray(a, dtype=np.uint64)), _p(np.ascontiguousarray(b, dtype=np.uint64)), _p(out))
+    return out
+
+
+def f12_pow(a, e: int) -> np.ndarray:
+    n = max(1, (e.bit_length() + 63) // 64)
+    w = np.array([(e >> (64 * i)) & ((1 << 64) - 1) for i in range(n)], dtype=np.uint64)
+    out = np.zeros((12, 4), dtype=np.uint64)
+    lib().zgo_f12_pow(_p(np.ascontiguousarray(a, dtype=np.uint64)), _p(w), ctypes.c_size_t(n), _p(out))
+    return out

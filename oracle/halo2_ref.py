@@ -11,8 +11,9 @@ EvmTranscript, one circuit, one instance column).
 
 PARITY UNPINNED against the real crates: the reference has no golden proof / commitment /
 evaluation vectors and no Rust toolchain exists here.  What pins this file:
-(i) the verifier below accepts the proofs (a KZG opening check with the test SRS's known trapdoor,
-equivalent to the pairing check), (ii) h(X) * (X^n - 1) == numerator(X) implied by (i),
+(i) the verifier below accepts the proofs (the KZG opening check is the real pairing equation
+e(W', [s]G2) = e(R, G2), oracle/zg_oracle.c; the test SRS's known trapdoor gives an equivalent G1 identity that is
+cross-checked), (ii) h(X) * (X^n - 1) == numerator(X) implied by (i),
 (iii) the reference's own snapshot vectors pin the public instance.  `vk.transcript_repr` (Rust
 Debug-format dependent) is an INPUT here, derived from a documented stand-in hash.
 
@@ -182,6 +183,9 @@ class Srs:
         den = cpu_ref.fr_batch_invert(cpu_ref.fr_sub_vec(np.tile(L(self.s), (n, 1)), wi))
         li = cpu_ref.fr_mul_vec(den, cpu_ref.fr_scale_vec(wi, L(num)))
         self.g_lagrange = cpu_ref.g1_fixed_base_mul_many(li, gen)
+        # ParamsKZG::{g2, s_g2}: what the verifier pairs against (G2Affine, Montgomery limbs x.c0 | x.c1 | y.c0 | y.c1)
+        self.g2 = cpu_ref.g2_generator()
+        self.s_g2 = cpu_ref.g2_mul(self.g2, L(self.s))
 
 
 class Domain:
@@ -699,9 +703,10 @@ def create_proof(srs: Srs, pk: ProvingKey, advice_int, instances, rng: XorShiftR
 
 
 # ---- verify_proof -----------------------------------------------------------------------------------
-def verify_proof(srs: Srs, pk: ProvingKey, instances, proof: bytes) -> bool:
-    """plonk::verify_proof + VerifierGWC with SingleStrategy.  The final pairing check
-    e(W', [s]G2) == e(R, G2) is done in G1 with the test SRS's known trapdoor: [s]W' == R."""
+def verify_proof(srs: Srs, pk: ProvingKey, instances, proof: bytes, use_trapdoor: bool = False) -> bool:
+    """plonk::verify_proof + VerifierGWC with SingleStrategy.  The final check is the pairing equation
+    e(W', [s]G2) == e(R, G2) on the SRS's G2 points, as in the reference (no secret needed).  `use_trapdoor` swaps it
+    for the equivalent G1 identity [s]W' == R with the test SRS's known secret (tests check that both agree)."""
     cs, dom, n = pk.cs, pk.domain, pk.n
     try:
         tr = EvmTranscript(proof)
@@ -781,6 +786,10 @@ def verify_proof(srs: Srs, pk: ProvingKey, instances, proof: bytes) -> bool:
             rhs = bn254.g1_add(rhs, bn254.g1_mul(term, pu))
             lhs = bn254.g1_add(lhs, bn254.g1_mul(w, pu))
             pu = pu * u % R_MOD
-        return bn254.g1_mul(lhs, srs.s) == rhs
+        if use_trapdoor:
+            return bn254.g1_mul(lhs, srs.s) == rhs
+        # e(lhs, [s]G2) * e(-rhs, G2) == 1
+        pts = bn254.g1_affine_to_limbs([lhs, bn254.g1_neg(rhs) if rhs is not None else None])
+        return cpu_ref.pairing_check(pts, np.stack([srs.s_g2, srs.g2]))
     except (ValueError, IndexError):
         return False

@@ -668,3 +668,275 @@ void zgo_g1_sequence(const g1a* gen, size_t n, g1a* out) {
     free(jac); free(pre);
   }
 }
+
+/* ======================================================================================================
+ * BN254 optimal-ate pairing, for the verifier's final check e(W', [s]G2) = e(R, G2) (halo2_proofs
+ * poly/kzg/strategy.rs SingleStrategy::finalize -> DualMSM::check -> Bn256::multi_miller_loop + final_exponentiation,
+ * reached from /root/reference/src/wnn.rs:271-280).  Written for clarity, not speed: G2 arithmetic in affine
+ * coordinates on the sextic twist E'(Fq2): y^2 = x^3 + 3/(9+i); Fq12 as Fq[w]/(w^12 - 18 w^6 + 82) (w^6 = 9 + i) with
+ * schoolbook products; the final exponentiation is one square-and-multiply with the exponent (p^12 - 1)/r supplied
+ * by the caller.  Pinned by tests/test_oracle.py: G2 generator on the twist and of order r, bilinearity
+ * e(aP, bQ) = e(P, Q)^(ab), non-degeneracy, e(P, Q)^r = 1.
+ * ====================================================================================================== */
+typedef struct { fe a, b; } f2;          /* a + b i, i^2 = -1 */
+typedef struct { f2 x, y; } g2a;         /* affine point on the twist; identity = (0, 0) */
+typedef struct { fe c[12]; } f12;        /* sum c[k] w^k */
+
+static fe fq_small(uint64_t v) {         /* v -> Montgomery */
+  fe t = {{v, 0, 0, 0}}, r;
+  fe_mul(&r, &t, &FQ.r2, &FQ);
+  return r;
+}
+static inline void f2_add(f2* r, const f2* x, const f2* y) { fe_add(&r->a, &x->a, &y->a, &FQ); fe_add(&r->b, &x->b, &y->b, &FQ); }
+static inline void f2_sub(f2* r, const f2* x, const f2* y) { fe_sub(&r->a, &x->a, &y->a, &FQ); fe_sub(&r->b, &x->b, &y->b, &FQ); }
+static inline void f2_neg(f2* r, const f2* x) { fe_neg(&r->a, &x->a, &FQ); fe_neg(&r->b, &x->b, &FQ); }
+static inline void f2_conj(f2* r, const f2* x) { r->a = x->a; fe_neg(&r->b, &x->b, &FQ); }
+static inline int f2_is_zero(const f2* x) { return fe_is_zero(&x->a) && fe_is_zero(&x->b); }
+static inline int f2_eq(const f2* x, const f2* y) { return fe_eq(&x->a, &y->a) && fe_eq(&x->b, &y->b); }
+static void f2_mul(f2* r, const f2* x, const f2* y) {
+  fe ac, bd, ad, bc;
+  fe_mul(&ac, &x->a, &y->a, &FQ); fe_mul(&bd, &x->b, &y->b, &FQ);
+  fe_mul(&ad, &x->a, &y->b, &FQ); fe_mul(&bc, &x->b, &y->a, &FQ);
+  fe_sub(&r->a, &ac, &bd, &FQ);
+  fe_add(&r->b, &ad, &bc, &FQ);
+}
+static void f2_mul_fe(f2* r, const f2* x, const fe* s) { fe_mul(&r->a, &x->a, s, &FQ); fe_mul(&r->b, &x->b, s, &FQ); }
+static void f2_inv(f2* r, const f2* x) {   /* conj(x) / (a^2 + b^2) */
+  fe aa, bb, n, ni;
+  fe_mul(&aa, &x->a, &x->a, &FQ); fe_mul(&bb, &x->b, &x->b, &FQ);
+  fe_add(&n, &aa, &bb, &FQ);
+  fe_inv(&ni, &n, &FQ);
+  fe_mul(&r->a, &x->a, &ni, &FQ);
+  fe nb;
+  fe_neg(&nb, &x->b, &FQ);
+  fe_mul(&r->b, &nb, &ni, &FQ);
+}
+static void f2_pow(f2* r, const f2* x, const uint64_t e[4]) {
+  f2 acc = {FQ.r, {{0, 0, 0, 0}}};
+  for (int i = 3; i >= 0; i--)
+    for (int b = 63; b >= 0; b--) {
+      f2_mul(&acc, &acc, &acc);
+      if ((e[i] >> b) & 1) f2_mul(&acc, &acc, x);
+    }
+  *r = acc;
+}
+static f2 f2_xi(void) { f2 x = {fq_small(9), FQ.r}; return x; }   /* 9 + i */
+static f2 g2_b(void) {                                            /* 3 / (9 + i) */
+  f2 xi = f2_xi(), inv, three = {fq_small(3), {{0, 0, 0, 0}}}, r;
+  f2_inv(&inv, &xi);
+  f2_mul(&r, &three, &inv);
+  return r;
+}
+
+static inline int g2_is_id(const g2a* p) { return f2_is_zero(&p->x) && f2_is_zero(&p->y); }
+/* slope of the chord / tangent through p and q on the twist; returns 0 when the line is vertical */
+static int g2_slope(f2* m, const g2a* p, const g2a* q) {
+  f2 num, den, inv;
+  if (f2_eq(&p->x, &q->x)) {
+    if (!f2_eq(&p->y, &q->y) || f2_is_zero(&p->y)) return 0;
+    f2 xx, three = {fq_small(3), {{0, 0, 0, 0}}};
+    f2_mul(&xx, &p->x, &p->x);
+    f2_mul(&num, &xx, &three);
+    f2_add(&den, &p->y, &p->y);
+  } else {
+    f2_sub(&num, &q->y, &p->y);
+    f2_sub(&den, &q->x, &p->x);
+  }
+  f2_inv(&inv, &den);
+  f2_mul(m, &num, &inv);
+  return 1;
+}
+static void g2_add(g2a* r, const g2a* p, const g2a* q) {
+  if (g2_is_id(p)) { *r = *q; return; }
+  if (g2_is_id(q)) { *r = *p; return; }
+  f2 m;
+  if (!g2_slope(&m, p, q)) { memset(r, 0, sizeof *r); return; }
+  f2 mm, x3, t, y3;
+  f2_mul(&mm, &m, &m);
+  f2_sub(&x3, &mm, &p->x);
+  f2_sub(&x3, &x3, &q->x);
+  f2_sub(&t, &p->x, &x3);
+  f2_mul(&y3, &m, &t);
+  f2_sub(&y3, &y3, &p->y);
+  r->x = x3;
+  r->y = y3;
+}
+static void g2_mul_bits(g2a* r, const g2a* p, const uint64_t e[4]) {
+  g2a acc;
+  memset(&acc, 0, sizeof acc);
+  for (int i = 3; i >= 0; i--)
+    for (int b = 63; b >= 0; b--) {
+      g2_add(&acc, &acc, &acc);
+      if ((e[i] >> b) & 1) g2_add(&acc, &acc, p);
+    }
+  *r = acc;
+}
+
+/* ---- Fq12 ---- */
+static void f12_one(f12* r) { memset(r, 0, sizeof *r); r->c[0] = FQ.r; }
+static int f12_is_one(const f12* x) {
+  if (!fe_eq(&x->c[0], &FQ.r)) return 0;
+  for (int k = 1; k < 12; k++) if (!fe_is_zero(&x->c[k])) return 0;
+  return 1;
+}
+static void f12_mul(f12* r, const f12* x, const f12* y) {
+  static fe c18, c82;
+  static int init = 0;
+  if (!init) { c18 = fq_small(18); c82 = fq_small(82); init = 1; }
+  fe t[23], p;
+  memset(t, 0, sizeof t);
+  for (int i = 0; i < 12; i++) {
+    if (fe_is_zero(&x->c[i])) continue;
+    for (int j = 0; j < 12; j++) {
+      fe_mul(&p, &x->c[i], &y->c[j], &FQ);
+      fe_add(&t[i + j], &t[i + j], &p, &FQ);
+    }
+  }
+  for (int k = 22; k >= 12; k--) {       /* w^k = 18 w^(k-6) - 82 w^(k-12) */
+    fe_mul(&p, &t[k], &c18, &FQ);
+    fe_add(&t[k - 6], &t[k - 6], &p, &FQ);
+    fe_mul(&p, &t[k], &c82, &FQ);
+    fe_sub(&t[k - 12], &t[k - 12], &p, &FQ);
+  }
+  memcpy(r->c, t, sizeof r->c);
+}
+/* embed s * w^k for s = a + b i in Fq2: i = w^6 - 9  =>  s w^k = (a - 9 b) w^k + b w^(k+6)   (k < 6) */
+static void f12_add_f2_wk(f12* r, const f2* s, int k) {
+  fe nine = fq_small(9), t;
+  fe_mul(&t, &s->b, &nine, &FQ);
+  fe_sub(&t, &s->a, &t, &FQ);
+  fe_add(&r->c[k], &r->c[k], &t, &FQ);
+  fe_add(&r->c[k + 6], &r->c[k + 6], &s->b, &FQ);
+}
+/* line through the twisted points t1, t2 (tangent if equal), evaluated at P = (xp, yp) in G1:
+ * with X = x' w^2, Y = y' w^3 and slope m' w:   l(P) = -yp + (m' xp) w + (y1' - m' x1') w^3 */
+static void line_eval(f12* l, const g2a* t1, const g2a* t2, const g1a* P) {
+  memset(l, 0, sizeof *l);
+  f2 m;
+  if (!g2_slope(&m, t1, t2)) {           /* vertical: xp - x1' w^2 */
+    l->c[0] = P->x;
+    f2 nx;
+    f2_neg(&nx, &t1->x);
+    f12_add_f2_wk(l, &nx, 2);
+    return;
+  }
+  fe_neg(&l->c[0], &P->y, &FQ);
+  f2 c1, c3, mx;
+  f2_mul_fe(&c1, &m, &P->x);
+  f12_add_f2_wk(l, &c1, 1);
+  f2_mul(&mx, &m, &t1->x);
+  f2_sub(&c3, &t1->y, &mx);
+  f12_add_f2_wk(l, &c3, 3);
+}
+static void miller_loop(f12* f, const g1a* P, const g2a* Q) {
+  f12_one(f);
+  if (a_is_id(P) || g2_is_id(Q)) return;
+  /* 6u + 2 = 29793968203157093288 (65 bits), u = 4965661367192848881 */
+  const uint64_t lo = 0x9d797039be763ba8ull;   /* low 64 bits; bit 64 is the implicit leading one */
+  g2a R = *Q;
+  f12 l;
+  for (int i = 63; i >= 0; i--) {
+    f12_mul(f, f, f);
+    line_eval(&l, &R, &R, P);
+    f12_mul(f, f, &l);
+    g2_add(&R, &R, &R);
+    if ((lo >> i) & 1) {
+      line_eval(&l, &R, Q, P);
+      f12_mul(f, f, &l);
+      g2_add(&R, &R, Q);
+    }
+  }
+  /* Q1 = pi_p(Q), Q2 = pi_p^2(Q) on the twist: (conj(x') g2, conj(y') g3), g2 = xi^((p-1)/3), g3 = xi^((p-1)/2) */
+  static f2 g2c, g3c;
+  static fe n2, n3;
+  static int init = 0;
+  if (!init) {
+    uint64_t pm1[4], e3[4], e2[4];
+    memcpy(pm1, FQ.p, 32);
+    pm1[0] -= 1;
+    /* (p-1)/2 */
+    for (int k = 0; k < 4; k++) e2[k] = (pm1[k] >> 1) | (k < 3 ? pm1[k + 1] << 63 : 0);
+    /* (p-1)/3 by long division */
+    u128 rem = 0;
+    for (int k = 3; k >= 0; k--) { u128 cur = (rem << 64) | pm1[k]; e3[k] = (uint64_t)(cur / 3); rem = cur % 3; }
+    f2 xi = f2_xi();
+    f2_pow(&g2c, &xi, e3);
+    f2_pow(&g3c, &xi, e2);
+    /* xi^((p^2-1)/3) = g2 * conj(g2) = norm(g2) in Fq, likewise for g3 */
+    fe aa, bb;
+    fe_mul(&aa, &g2c.a, &g2c.a, &FQ); fe_mul(&bb, &g2c.b, &g2c.b, &FQ); fe_add(&n2, &aa, &bb, &FQ);
+    fe_mul(&aa, &g3c.a, &g3c.a, &FQ); fe_mul(&bb, &g3c.b, &g3c.b, &FQ); fe_add(&n3, &aa, &bb, &FQ);
+    init = 1;
+  }
+  g2a Q1, nQ2;
+  f2 cx, cy;
+  f2_conj(&cx, &Q->x); f2_conj(&cy, &Q->y);
+  f2_mul(&Q1.x, &cx, &g2c);
+  f2_mul(&Q1.y, &cy, &g3c);
+  f2_mul_fe(&nQ2.x, &Q->x, &n2);
+  f2_mul_fe(&nQ2.y, &Q->y, &n3);
+  f2_neg(&nQ2.y, &nQ2.y);
+  line_eval(&l, &R, &Q1, P);
+  f12_mul(f, f, &l);
+  g2_add(&R, &R, &Q1);
+  line_eval(&l, &R, &nQ2, P);
+  f12_mul(f, f, &l);
+}
+static void f12_pow_words(f12* r, const f12* x, const uint64_t* e, size_t nwords) {
+  f12 acc;
+  f12_one(&acc);
+  int started = 0;
+  for (size_t i = nwords; i-- > 0;)
+    for (int b = 63; b >= 0; b--) {
+      if (started) f12_mul(&acc, &acc, &acc);
+      if ((e[i] >> b) & 1) { f12_mul(&acc, &acc, x); started = 1; }
+    }
+  *r = acc;
+}
+
+/* G2 generator of alt_bn128 (EIP-197), canonical little-endian limbs: x.c0, x.c1, y.c0, y.c1 */
+static const uint64_t G2_GEN_CANON[16] = {
+  0x46debd5cd992f6edull, 0x674322d4f75edaddull, 0x426a00665e5c4479ull, 0x1800deef121f1e76ull,
+  0x97e485b7aef312c2ull, 0xf1aa493335a9e712ull, 0x7260bfb731fb5d25ull, 0x198e9393920d483aull,
+  0x4ce6cc0166fa7daaull, 0xe3d1e7690c43d37bull, 0x4aab71808dcb408full, 0x12c85ea5db8c6debull,
+  0x55acdadcd122975bull, 0xbc4b313370b38ef3ull, 0xec9e99ad690c3395ull, 0x090689d0585ff075ull};
+
+void zgo_g2_generator(g2a* out) {
+  const fe* w = (const fe*)G2_GEN_CANON;
+  fe_mul(&out->x.a, &w[0], &FQ.r2, &FQ); fe_mul(&out->x.b, &w[1], &FQ.r2, &FQ);
+  fe_mul(&out->y.a, &w[2], &FQ.r2, &FQ); fe_mul(&out->y.b, &w[3], &FQ.r2, &FQ);
+}
+int zgo_g2_on_curve(const g2a* p) {
+  if (g2_is_id(p)) return 1;
+  f2 yy, xx, xxx, b = g2_b(), rhs;
+  f2_mul(&yy, &p->y, &p->y);
+  f2_mul(&xx, &p->x, &p->x);
+  f2_mul(&xxx, &xx, &p->x);
+  f2_add(&rhs, &xxx, &b);
+  return f2_eq(&yy, &rhs);
+}
+/* out = [scalar] p, scalar an Fr element in Montgomery form */
+void zgo_g2_mul(const g2a* p, const fe* scalar, g2a* out) {
+  uint64_t e[4];
+  fe_from_mont(e, scalar, &FR);
+  g2_mul_bits(out, p, e);
+}
+/* f = final_exponentiation(miller(P, Q)); exp = (p^12 - 1) / r as little-endian 64-bit words */
+void zgo_pairing(const g1a* P, const g2a* Q, const uint64_t* exp, size_t nwords, f12* out) {
+  f12 f;
+  miller_loop(&f, P, Q);
+  f12_pow_words(out, &f, exp, nwords);
+}
+/* 1 iff prod_i e(P_i, Q_i) == 1 */
+int zgo_pairing_check(const g1a* P, const g2a* Q, size_t n, const uint64_t* exp, size_t nwords) {
+  f12 acc, f;
+  f12_one(&acc);
+  for (size_t i = 0; i < n; i++) {
+    miller_loop(&f, &P[i], &Q[i]);
+    f12_mul(&acc, &acc, &f);
+  }
+  f12_pow_words(&f, &acc, exp, nwords);
+  return f12_is_one(&f);
+}
+void zgo_f12_mul(const f12* a, const f12* b, f12* out) { f12_mul(out, a, b); }
+void zgo_f12_pow(const f12* a, const uint64_t* exp, size_t nwords, f12* out) { f12_pow_words(out, a, exp, nwords); }

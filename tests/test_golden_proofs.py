@@ -35,8 +35,12 @@ def test_oracle_reproduces_tiny_fixture():
     _, asm = wnn.synthesize(img, e["k"])
     proof = H.create_proof(srs, pk, asm.advice, [e["outputs"]], H.XorShiftRng(SEED))
     assert len(proof) == e["proof_len"] and hashlib.sha256(proof).hexdigest() == e["proof_sha256"]
-    assert H.verify_proof(srs, pk, [e["outputs"]], proof)
+    assert H.verify_proof(srs, pk, [e["outputs"]], proof)                               # pairing check, no secret used
+    assert H.verify_proof(srs, pk, [e["outputs"]], proof, use_trapdoor=True)           # the G1 shortcut agrees
     assert not H.verify_proof(srs, pk, [[o + 1 for o in e["outputs"]]], proof)          # wrong public outputs
+    bad = bytearray(proof)
+    bad[-1] ^= 1                                                                         # a bit of the last opening witness
+    assert not H.verify_proof(srs, pk, [e["outputs"]], bytes(bad))
 
 
 @pytest.mark.gpu

@@ -85,3 +85,28 @@ def test_srs_monomial_is_powers_of_s():
     seq = cpu_ref.g1_sequence(bn254.g1_affine_to_limbs([bn254.G1_GEN])[0], 5000)
     got = bn254.g1_affine_from_limbs(seq[[0, 1, 4095, 4096, 4999]].copy())
     assert got == [bn254.g1_mul(bn254.G1_GEN, k) for k in (1, 2, 4096, 4097, 5000)]
+
+
+def test_pairing_bilinear_nondegenerate_order_r():
+    """pins the verifier's pairing (oracle/zg_oracle.c): generator on the twist and of order r, e(aP, bQ) = e(P, Q)^(ab),
+    e(P, Q) != 1, e(P, Q)^r = 1, and the product check used for e(W', [s]G2) = e(R, G2)."""
+    L = lambda x: bn254.fr_to_limbs([x])[0]
+    g2 = cpu_ref.g2_generator()
+    assert cpu_ref.g2_on_curve(g2)
+    assert (cpu_ref.g2_mul(g2, L(0)) == 0).all()
+    minus = cpu_ref.g2_mul(g2, L(R_MOD - 1))
+    assert (minus[:8] == g2[:8]).all() and (minus[8:] != g2[8:]).any()       # [r-1]G2 = -G2
+    G1 = bn254.g1_affine_to_limbs([bn254.G1_GEN])[0]
+    e = cpu_ref.pairing(G1, g2)
+    one = cpu_ref.f12_pow(e, 0)
+    assert not (e == one).all()
+    assert (cpu_ref.f12_pow(e, R_MOD) == one).all()
+    a, b = 0x1F3C5A7B9D2E4F60718293A4B5C6D7E8, 987654321987654321
+    aP = bn254.g1_affine_to_limbs([bn254.g1_mul(bn254.G1_GEN, a)])[0]
+    bQ = cpu_ref.g2_mul(g2, L(b))
+    assert (cpu_ref.pairing(aP, bQ) == cpu_ref.f12_pow(e, a * b % R_MOD)).all()
+    negP = bn254.g1_affine_to_limbs([bn254.g1_neg(bn254.G1_GEN)])[0]
+    assert cpu_ref.pairing_check(np.stack([aP, negP]), np.stack([g2, cpu_ref.g2_mul(g2, L(a))]))
+    assert not cpu_ref.pairing_check(np.stack([aP, negP]), np.stack([g2, cpu_ref.g2_mul(g2, L(a + 1))]))
+    zero = np.zeros(8, dtype=np.uint64)
+    assert (cpu_ref.pairing(zero, g2) == one).all()                          # identity maps to 1
