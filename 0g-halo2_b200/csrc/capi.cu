@@ -165,6 +165,13 @@ int zg_ctx_create(int device, void* stream, zg_ctx** out) {
     delete ctx;
     return ZG_E_CUDA;
   }
+  for (int i = 0; i < zg_ctx::N_SIDE; i++) {
+    if (cudaStreamCreateWithPriority(&ctx->side[i], cudaStreamNonBlocking, greatest) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_side[i], cudaEventDisableTiming) != cudaSuccess) {
+      delete ctx;
+      return ZG_E_CUDA;
+    }
+  }
   *out = ctx;
   return ZG_OK;
 }
@@ -186,6 +193,10 @@ void zg_ctx_destroy(zg_ctx* ctx) {
   if (ctx->probe.counts) cudaFreeHost(ctx->probe.counts);
   if (ctx->hp) { cudaStreamSynchronize(ctx->hp); cudaStreamDestroy(ctx->hp); }
   if (ctx->aux) { cudaStreamSynchronize(ctx->aux); cudaStreamDestroy(ctx->aux); }
+  for (int i = 0; i < zg_ctx::N_SIDE; i++) {
+    if (ctx->side[i]) { cudaStreamSynchronize(ctx->side[i]); cudaStreamDestroy(ctx->side[i]); }
+    if (ctx->ev_side[i]) cudaEventDestroy(ctx->ev_side[i]);
+  }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);

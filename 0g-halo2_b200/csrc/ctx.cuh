@@ -39,6 +39,10 @@ struct zg_ctx {
   // for until the quotient stage on `aux` (lowest priority); both are forked from / joined to `stream` with events
   cudaStream_t hp = nullptr, aux = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // independent latency-bound chains of one stage (the per-lookup sort + permutation) run side by side on these
+  static constexpr int N_SIDE = 4;
+  cudaStream_t side[N_SIDE] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_side[N_SIDE] = {nullptr, nullptr, nullptr, nullptr};
   std::string err;
   uint64_t launches = 0;
 

@@ -200,6 +200,7 @@ struct zg_pk {
   uint32_t* d_pidx;
   uint32_t* d_status;
   uint8_t* lookup_ws;
+  size_t lookup_ws_stride = 0;
   uint8_t* table_cache;
   size_t table_cache_stride = 0;
   std::vector<char> table_cached;
@@ -480,7 +481,8 @@ int zg_pk_load(zg_ctx* ctx, const zg_pk_desc* d, zg_pk** out) {
     pk->one_dev = b.take<Fr>(8);
     pk->d_polyptrs = b.take<const Fr*>(n_queries + 8); pk->d_pidx = b.take<uint32_t>(n_queries + 8);
     pk->d_status = b.take<uint32_t>(64);
-    pk->lookup_ws = b.take<uint8_t>(lookup_workspace_bytes(pk->usable));
+    pk->lookup_ws_stride = (lookup_workspace_bytes(pk->usable) + 255) & ~(size_t)255;
+    pk->lookup_ws = b.take<uint8_t>(pk->lookup_ws_stride * zg_ctx::N_SIDE);
     pk->table_cache_stride = (lookup_table_bytes(pk->usable) + 255) & ~(size_t)255;
     pk->table_cache = b.take<uint8_t>(pk->table_cache_stride * (Lk + 1));
     pk->rnd_words_dev = b.take<uint64_t>(8 * pk->n_draws);
@@ -632,6 +634,7 @@ int zg_create_proof(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice, const zg
   ctx->stream = caller;
   // leave nothing in flight, also on the error paths (the workspace is reused by the next proof)
   cudaError_t e1 = cudaStreamSynchronize(ctx->hp), e2 = cudaStreamSynchronize(ctx->aux);
+  for (int i = 0; i < zg_ctx::N_SIDE; i++) cudaStreamSynchronize(ctx->side[i]);
   if (rc == ZG_OK && (e1 != cudaSuccess || e2 != cudaSuccess)) return ctx->cuda_fail(e1 != cudaSuccess ? e1 : e2, "create_proof");
   return rc;
 }
@@ -729,22 +732,33 @@ static int create_proof_impl(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice,
     for (int attempt = 0;; attempt++) {
       draw = draw_mark;
       ZG_CUDA(cudaMemsetAsync(pk->d_status, 0, 4 * 2 * Lk, st));
+      // the lookups are independent chains of ~40 small kernels each (radix passes, scans, ranking, placement): lookup l
+      // runs on side stream l mod 4 with its own workspace, forked from and joined to the proof's stream by events
+      ZG_CUDA(cudaEventRecord(ctx->ev_fork, st));
       for (uint32_t l = 0; l < Lk; l++) {
+        const int sidx = (int)(l % zg_ctx::N_SIDE);
+        cudaStream_t ss = ctx->side[sidx];
+        uint8_t* ws = pk->lookup_ws + (size_t)sidx * pk->lookup_ws_stride;
+        if (l < (uint32_t)zg_ctx::N_SIDE) ZG_CUDA(cudaStreamWaitEvent(ss, ctx->ev_fork, 0));
         LookupTable tab;
         if (pk->tab_count[l] == 1) {
           tab = lookup_table_carve(pk->table_cache + (size_t)l * pk->table_cache_stride, usable);
           if (!pk->table_cached[l]) {
-            if (lookup_sort_table(pk->ct + l * n, usable, tab, pk->lookup_ws, pk->d_status + 2 * l, true, st, lc))
+            if (lookup_sort_table(pk->ct + l * n, usable, tab, ws, pk->d_status + 2 * l, true, ss, lc))
               return ctx->cuda_fail(cudaGetLastError(), "lookup_sort_table");
             pk->table_cached[l] = 1;
           }
         } else {
-          tab = lookup_workspace_table(pk->lookup_ws, usable);
-          if (lookup_sort_table(pk->ct + l * n, usable, tab, pk->lookup_ws, pk->d_status + 2 * l, full[l] != 0, st, lc))
+          tab = lookup_workspace_table(ws, usable);
+          if (lookup_sort_table(pk->ct + l * n, usable, tab, ws, pk->d_status + 2 * l, full[l] != 0, ss, lc))
             return ctx->cuda_fail(cudaGetLastError(), "lookup_sort_table");
         }
-        if (lookup_permute(pk->ci + l * n, usable, tab, pk->pa + l * n, pk->ps + l * n, pk->lookup_ws, pk->d_status + 2 * l + 1, st, lc))
+        if (lookup_permute(pk->ci + l * n, usable, tab, pk->pa + l * n, pk->ps + l * n, ws, pk->d_status + 2 * l + 1, ss, lc))
           return ctx->cuda_fail(cudaGetLastError(), "lookup_permute");
+      }
+      for (int i = 0; i < zg_ctx::N_SIDE && (uint32_t)i < Lk; i++) {
+        ZG_CUDA(cudaEventRecord(ctx->ev_side[i], ctx->side[i]));
+        ZG_CUDA(cudaStreamWaitEvent(st, ctx->ev_side[i], 0));
       }
       // blinding rows: per lookup input rows, table rows, then two blinds
       for (uint32_t l = 0; l < Lk; l++) {
