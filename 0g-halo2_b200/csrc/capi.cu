@@ -251,19 +251,16 @@ int zg_probe_enable(zg_ctx* ctx, int on) {
 int zg_probe_read(zg_ctx* ctx, double* kernel_ms, uint64_t* launches, uint64_t* point_additions) {
   ZG_ENTER(ctx);
   MsmProbe& p = ctx->probe;
+  // the entry-count copies were enqueued after the stop events on the same streams: drain everything first
+  ZG_CUDA(cudaDeviceSynchronize());
   double ms = 0;
   uint64_t adds = 0;
   for (size_t i = 0; i < p.used; i++) {
-    ZG_CUDA(cudaEventSynchronize(p.ev[2 * i + 1]));
     float t = 0;
     ZG_CUDA(cudaEventElapsedTime(&t, p.ev[2 * i], p.ev[2 * i + 1]));
     ms += t;
     adds += p.counts[i];
   }
-  // the count copies were enqueued after the stop events on the same streams
-  cudaDeviceSynchronize();
-  adds = 0;
-  for (size_t i = 0; i < p.used; i++) adds += p.counts[i];
   if (kernel_ms) *kernel_ms = ms;
   if (launches) *launches = p.used;
   if (point_additions) *point_additions = adds;

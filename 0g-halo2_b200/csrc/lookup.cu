@@ -8,7 +8,7 @@
 //
 // B200-first restatement that yields the same two columns without sorting the inputs:
 //   1. block-parallel LSD radix sort (8-bit digits, warp match_any ranking) of the canonical table
-//      values only -- top 64 bits first, checked, full 256-bit passes as the fallback -- then the
+//      values only -- top 48 bits first, checked, full 256-bit passes as the fallback -- then the
 //      unique values U with their multiplicities.  Tables that do not depend on theta (one table
 //      expression) are sorted once per proving key and cached by the caller;
 //   2. every input is ranked by binary search in U (an input that is not in the table raises the

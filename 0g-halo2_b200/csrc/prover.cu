@@ -650,8 +650,12 @@ static int create_proof_impl(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice,
   cudaStream_t st = ctx->stream;
   LaunchCounter lc{&ctx->launches};
   int rc;
-  cudaEvent_t ev[9];
-  for (auto& e : ev) ZG_CUDA(cudaEventCreate(&e));
+  struct StageEvents {                       // destroyed on every return path
+    cudaEvent_t e[9] = {};
+    ~StageEvents() { for (auto x : e) if (x) cudaEventDestroy(x); }
+  } stage_events;
+  cudaEvent_t* ev = stage_events.e;
+  for (int i = 0; i < 9; i++) ZG_CUDA(cudaEventCreate(&ev[i]));
   ZG_CUDA(cudaEventRecord(ev[0], st));
   Transcript tr;
   tr.common_scalar(pk->transcript_repr);
@@ -724,7 +728,7 @@ static int create_proof_impl(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice,
   if (Lk) {
     expr_compress_lookups(base_env, lp, Lk, theta, pk->ci, pk->ct, n, st, lc);
     // Tables with a single expression do not depend on theta: sorted once per proving key (full 256-bit
-    // sort) and cached.  The others are sorted per proof on their top 64 bits; the device flags the rare
+    // sort) and cached.  The others are sorted per proof on their top 48 bits; the device flags the rare
     // case where that left distinct keys out of order and the round is redone with the full sort.
     const size_t draw_mark = draw;
     std::vector<char> full(Lk, 0);
@@ -1018,7 +1022,6 @@ static int create_proof_impl(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice,
   ZG_CUDA(cudaEventSynchronize(ev[7]));
   for (int i = 0; i < 7; i++) cudaEventElapsedTime(&pk->stage_ms[i], ev[i], ev[i + 1]);
   cudaEventElapsedTime(&pk->stage_ms[7], ev[0], ev[7]);
-  for (auto& e : ev) cudaEventDestroy(e);
   if (draw != pk->n_draws) return ctx->fail(ZG_E_STATE, "create_proof: RNG draw accounting mismatch");
   if (tr.out.size() > proof_cap) return ctx->fail(ZG_E_INVALID, "create_proof: proof buffer too small");
   memcpy(proof_out, tr.out.data(), tr.out.size());
