@@ -31,6 +31,7 @@ EXPORTS = [
     "zg_bench_int_pipe", "zg_debug_field_op", "zg_probe_enable", "zg_probe_read",
     "zg_xorshift_seed", "zg_xorshift_fill", "zg_pk_load", "zg_pk_free", "zg_pk_commitments", "zg_create_proof",
     "zg_pk_last_stage_ms",
+    "zg_wnn_create", "zg_wnn_free", "zg_wnn_last_error", "zg_wnn_synthesize",
     "zg_lookup_permute", "zg_grand_product", "zg_batch_invert", "zg_eval_poly_batch", "zg_kate_division", "zg_evaluate_h",
 ]
 
@@ -94,6 +95,12 @@ def load_library() -> ctypes.CDLL:
     L.zg_pk_commitments.argtypes = [vp, vp, vp, vp]
     L.zg_create_proof.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, sz, ctypes.POINTER(sz)]
     L.zg_pk_last_stage_ms.argtypes = [vp, vp]
+    L.zg_wnn_create.argtypes = [vp, ctypes.POINTER(vp)]
+    L.zg_wnn_free.argtypes = [vp]
+    L.zg_wnn_free.restype = None
+    L.zg_wnn_last_error.argtypes = [vp]
+    L.zg_wnn_last_error.restype = ctypes.c_char_p
+    L.zg_wnn_synthesize.argtypes = [vp, vp, u32, u32, vp, vp]
     L.zg_lookup_permute.argtypes = [vp, vp, vp, sz, vp, vp]
     L.zg_grand_product.argtypes = [vp, vp, vp, sz, vp]
     L.zg_batch_invert.argtypes = [vp, vp, sz]
@@ -313,3 +320,58 @@ class XorShift(ctypes.Structure):
         r = cls()
         load_library().zg_xorshift_seed(ctypes.byref(r), seed)
         return r
+
+
+class WnnDesc(ctypes.Structure):
+    """zg_wnn_desc (include/zg_b200.h)."""
+    _fields_ = [("p", ctypes.c_uint64), ("n_hashes", ctypes.c_uint32), ("bits_per_hash", ctypes.c_uint32),
+                ("bits_per_filter", ctypes.c_uint32), ("n_classes", ctypes.c_uint32), ("n_filters", ctypes.c_uint32),
+                ("width", ctypes.c_uint32), ("height", ctypes.c_uint32), ("bits_per_input", ctypes.c_uint32),
+                ("thresholds", ctypes.c_void_p), ("input_permutation", ctypes.c_void_p), ("bloom_bits", ctypes.c_void_p)]
+
+
+class NativeSynthesizer:
+    """zg_wnn_*: native witness synthesis of the WNN circuit (host code; usable without a GPU).  Built from a
+    zg_b200.wnn.Wnn; `synthesize(image, k, usable_rows)` returns (six (n,4) uint64 Montgomery columns, class scores)."""
+
+    def __init__(self, wnn):
+        self._L = load_library()
+        cp = wnn.get_circuit_params()
+        thr = np.ascontiguousarray(wnn.binarization_thresholds, dtype=np.uint16)
+        perm = np.ascontiguousarray(wnn.input_permutation, dtype=np.uint64)
+        bloom = np.ascontiguousarray(wnn.bloom_filters, dtype=np.uint8)
+        self._keep = (thr, perm, bloom)
+        d = WnnDesc()
+        d.p, d.n_hashes, d.bits_per_hash, d.bits_per_filter = cp["p"], cp["n_hashes"], cp["bits_per_hash"], cp["bits_per_filter"]
+        d.n_classes, d.n_filters = bloom.shape[0], bloom.shape[1]
+        d.width, d.height, d.bits_per_input = thr.shape
+        d.thresholds, d.input_permutation, d.bloom_bits = thr.ctypes.data, perm.ctypes.data, bloom.ctypes.data
+        assert bloom.shape[2] == 1 << cp["bits_per_hash"]
+        h = ctypes.c_void_p()
+        rc = self._L.zg_wnn_create(ctypes.byref(d), ctypes.byref(h))
+        if rc != ZG_OK:
+            raise ZgError(rc, "zg_wnn_create: unsupported model parameters")
+        self._h, self.n_classes, self.shape = h, int(d.n_classes), (int(d.width), int(d.height))
+
+    def synthesize(self, image, k: int, usable_rows: int, out=None):
+        img = np.ascontiguousarray(image, dtype=np.uint8)
+        assert img.shape == self.shape
+        n = 1 << k
+        cols = out if out is not None else [np.empty((n, 4), dtype=np.uint64) for _ in range(6)]
+        ptrs = (ctypes.c_void_p * 6)(*[c.ctypes.data for c in cols])
+        scores = (ctypes.c_uint64 * self.n_classes)()
+        rc = self._L.zg_wnn_synthesize(self._h, img.ctypes.data, k, usable_rows, ptrs, scores)
+        if rc != ZG_OK:
+            raise ZgError(rc, self._L.zg_wnn_last_error(self._h).decode())
+        return cols, [int(x) for x in scores]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.zg_wnn_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -57,6 +57,10 @@ def parse():
     ap.add_argument("--inflight", type=int, default=int(os.environ.get("ZG_BENCH_INFLIGHT", "4")),
                     help="proof workload: independent proofs in flight per GPU (one context + stream + host thread each); "
                          "a step is one batch of that many proofs")
+    ap.add_argument("--synth", default=os.environ.get("ZG_BENCH_SYNTH", "cached"), choices=["cached", "native"],
+                    help="proof workload, e2e leg: `cached` = witnesses synthesized once, untimed (the default: synthesis is "
+                         "outside the replaced path); `native` = every e2e proof starts from the IMAGE: zg_wnn_synthesize "
+                         "(C++ host code) fills the lane's pinned advice buffers inside the timed region")
     ap.add_argument("--images", type=int, default=int(os.environ.get("ZG_BENCH_IMAGES", "1")),
                     help="proof workload: 1 = benches/example_image_7.png for every proof (the reference's bench input); "
                          "K > 1 = K distinct synthetic MNIST-shaped images per rank, proofs cycle through them "
@@ -280,10 +284,13 @@ def main():
         nimg = max(1, args.images)
         imgs = [img] if nimg == 1 else [synthetic_image(rank * nimg + i, wnn.img_shape()) for i in range(nimg)]
         witnesses = []
+        usable_rows = None
         for im in imgs:
             _, a = wnn.synthesize(im, k)
+            usable_rows = a.usable_rows
             o = wnn.predict(im)
             witnesses.append((a.advice, o, [to_limbs(list(o))]))
+        native = zg_b200.lib.NativeSynthesizer(wnn) if args.synth == "native" else None
         asm_advice, outputs, inst = witnesses[0]
 
         class DevCol:                              # quacks like a numpy column for create_proof_limbs
@@ -325,6 +332,9 @@ def main():
 
             def prove_e2e(self):
                 w = self._next()
+                if native is not None:             # image -> witness (host, C++) -> proof: nothing is precomputed
+                    cols, scores = native.synthesize(imgs[w], k, usable_rows, out=self.adv_host[w])
+                    return w, create_proof_limbs(self.pk, cols, [to_limbs(scores)], self.rng())
                 return w, create_proof_limbs(self.pk, self.adv_host[w], witnesses[w][2], self.rng())
 
         K = max(1, args.inflight)
@@ -357,6 +367,7 @@ def main():
         dom_kernel = "msm_accumulate_kernel"
         extra["inflight"] = K
         extra["images"] = "example_image_7.png" if nimg == 1 else "%d synthetic MNIST-shaped images per rank" % nimg
+        extra["e2e_starts_from"] = "image (native witness synthesis timed)" if native is not None else "synthesized advice columns"
         if not args.no_cpu_baseline and rank == 0:
             cpu_fn = lambda: H.create_proof(srs, opk, asm_advice, [outputs], H.XorShiftRng(bytes(range(16))), real_msm=True)
             cpu_units = 1

@@ -177,6 +177,32 @@ int zg_evaluate_h(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice_polys, cons
                   const zg_fr* const* lookup_product_polys, const zg_fr* const* perm_product_polys,
                   const zg_fr challenges[4], int divide, zg_fr* h_out);
 
+/* ---- native witness synthesis of the WNN circuit (host code, no GPU) ----------------------------------------
+ * The assignment half of `WnnCircuit::synthesize` -> `WnnChip::predict` (/root/reference/src/gadgets/wnn.rs:180-237,
+ * 372-393) and every sub-chip, under halo2's SimpleFloorPlanner: produces the six advice columns zg_create_proof takes.
+ * In the reference this is Rust on the host; here it is the native counterpart of zg_b200/plonk/gadgets.py, checked
+ * cell for cell against it (tests/test_wnn_synth.py).  A zg_wnn is immutable after creation and may be shared by
+ * threads; each zg_wnn_synthesize call writes only its own output buffers (the error string is per model). */
+typedef struct zg_wnn zg_wnn;
+typedef struct {
+  uint64_t p;                        /* hash modulus (Wnn::p) */
+  uint32_t n_hashes, bits_per_hash;  /* WnnCircuitParams::{n_hashes, bits_per_hash}; l = n_hashes * bits_per_hash */
+  uint32_t bits_per_filter;          /* inputs per bloom filter */
+  uint32_t n_classes, n_filters;     /* bloom_filters.shape[0..2] */
+  uint32_t width, height, bits_per_input;
+  const uint16_t* thresholds;        /* [width][height][bits_per_input], 0..256 (src/io.rs:59-73) */
+  const uint64_t* input_permutation; /* width*height*bits_per_input entries */
+  const uint8_t* bloom_bits;         /* [n_classes][n_filters][2^bits_per_hash], 0 / 1 */
+} zg_wnn_desc;
+int zg_wnn_create(const zg_wnn_desc* desc, zg_wnn** out);
+void zg_wnn_free(zg_wnn* w);
+const char* zg_wnn_last_error(const zg_wnn* w);
+/* image: width*height bytes; advice: 6 columns of 2^k elements (zeroed, then filled below `usable_rows` = 2^k -
+ * blinding_factors - 1); outputs: n_classes class scores (the public instance).  ZG_E_SYNTH when the circuit does
+ * not fit in `usable_rows` rows (plonk::Error::NotEnoughRowsAvailable). */
+int zg_wnn_synthesize(zg_wnn* w, const uint8_t* image, uint32_t k, uint32_t usable_rows, zg_fr* const* advice,
+                      uint64_t* outputs);
+
 /* ---- micro-benchmarks used for the integer-pipe roofline (bench.py) ---------------------- */
 /* runs `iters` dependent-free IMAD-class instructions per thread on every SM and returns the
  * achieved rate in 1e9 thread-instructions per second; kind 0 = IMAD (32-bit), 1 = IMAD.WIDE,

@@ -59,3 +59,21 @@ def test_gpu_reproduces_fixture(ctx, fname):
     proof = create_proof(params, pk, asm.advice, [wnn.predict(img)], zg_b200.lib.XorShift.from_seed(SEED))
     assert len(proof) == e["proof_len"] and hashlib.sha256(proof).hexdigest() == e["proof_sha256"]
     pk.close()
+
+
+@pytest.mark.gpu
+def test_wnn_proof_native_and_python_witness_agree(ctx):
+    """Wnn::proof mirror (src/wnn.rs:232-262): image in, proof out, with the C++ witness synthesis and with the Python
+    front-end -- both must hit the committed digest."""
+    import zg_b200
+    from zg_b200.prover import ParamsKZG
+    fname = "model_28input_256entry_1hash_1bpi.hdf5"
+    e = FIX["models"][fname]
+    wnn, img, srs = _inputs(fname, e["k"])
+    params = ParamsKZG(e["k"], srs.g, srs.g_lagrange)
+    pk = wnn.generate_proving_key(ctx, params)
+    for native in (True, False):
+        proof, outputs = wnn.proof(pk, params, img, zg_b200.lib.XorShift.from_seed(SEED), native=native)
+        assert outputs == e["outputs"]
+        assert hashlib.sha256(proof).hexdigest() == e["proof_sha256"], "native=%s" % native
+    pk.close()
