@@ -32,12 +32,19 @@ def point_range(n: int, rank: int, world: int):
     return lo, hi
 
 
-def prove_many(images: Sequence, prove_one: Callable[[int, object], bytes], dist=None) -> List[bytes] | None:
+def prove_many(images: Sequence, prove_one: Callable[[int, object], bytes] = None, dist=None,
+               prove_batch: Callable[[List[int], List[object]], List[bytes]] = None) -> List[bytes] | None:
     """Every rank proves its share; rank 0 returns the proofs in image order (others return None).
-    `prove_one(index, image)` is the per-GPU prover (Wnn.proof bound to this rank's context)."""
+    `prove_one(index, image)` is the per-GPU prover (Wnn.proof bound to this rank's context).  For throughput give
+    every rank a `service.ProofService` (several proofs in flight per GPU) and pass `prove_batch` instead: it receives
+    this rank's (index, image) pairs at once and returns their proofs in that order."""
     rank = dist.get_rank() if dist is not None and dist.is_initialized() else 0
     world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
-    mine = [(i, prove_one(i, images[i])) for i in shard_indices(len(images), rank, world)]
+    idx = shard_indices(len(images), rank, world)
+    if prove_batch is not None:
+        mine = list(zip(idx, prove_batch(idx, [images[i] for i in idx])))
+    else:
+        mine = [(i, prove_one(i, images[i])) for i in idx]
     if world == 1:
         return [p for _, p in mine]
     gathered = [None] * world if rank == 0 else None

@@ -1,0 +1,119 @@
+"""Throughput front-end: several proofs in flight on one GPU.
+
+`Wnn::proof` (/root/reference/src/wnn.rs:232-262) proves one image at a time; a proof of this size leaves a B200 idle
+during its latency-bound stretches (MSM tails, sorts, host round trips for the Fiat-Shamir challenges).  Contexts of the
+backend are independent, so `ProofService` keeps `lanes` of them per GPU -- each with its own streams, SRS window
+tables, proving key and pinned witness buffers -- and drives every lane from its own host thread (the ctypes calls
+release the GIL).  Image in, proof bytes out: witness synthesis is the native `zg_wnn_synthesize`.
+
+This is what `bench.py --inflight K --synth native` measures (profiles/README.md: 115 -> 183 proofs/s from 1 to 4 lanes
+on the 1024-entry MNIST model) and what `farm.prove_many` runs on every rank of a multi-GPU job.  No CPU fallback.
+"""
+from __future__ import annotations
+
+import queue
+import threading
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import lib as zl
+from .bn254_host import to_limbs
+from .prover import ParamsKZG, create_proof_limbs
+
+
+class _Lane:
+    def __init__(self, service: "ProofService", index: int, ctx: zl.Context):
+        self.ctx = ctx
+        self.params = ParamsKZG(service.params.k, service.params.g, service.params.g_lagrange)
+        self.pk = service.wnn.generate_proving_key(ctx, self.params)
+        n = 1 << self.pk.k
+        try:
+            import torch
+            self._pinned = [torch.empty((n, 4), dtype=torch.int64).pin_memory() for _ in range(6)]
+            self.cols = [t.numpy().view(np.uint64) for t in self._pinned]
+        except Exception:                      # torch is only used for pinned host memory here
+            self.cols = [np.empty((n, 4), dtype=np.uint64) for _ in range(6)]
+        self.usable = n - (self.pk.cs.blinding_factors() + 1)
+
+    def close(self):
+        self.pk.close()
+
+
+class ProofService:
+    """`lanes` independent provers for one model on one GPU.
+
+    rng_factory(job_index) -> zl.XorShift (or any object zg_create_proof's RNG callback accepts through
+    `create_proof_limbs`); the default draws a fresh OS-random seed per proof, as the reference's OsRng does."""
+
+    def __init__(self, wnn, params: ParamsKZG, device: int = 0, lanes: int = 4,
+                 rng_factory: Optional[Callable[[int], zl.XorShift]] = None, streams: Optional[Sequence[int]] = None):
+        assert lanes >= 1
+        self.wnn, self.params, self.device = wnn, params, device
+        self.synth = wnn.native_synthesizer()
+        self.rng_factory = rng_factory or self._os_rng
+        self._owned_ctx = []
+        self.lanes: List[_Lane] = []
+        for i in range(lanes):
+            ctx = zl.Context(device, None if streams is None else streams[i])
+            self._owned_ctx.append(ctx)
+            self.lanes.append(_Lane(self, i, ctx))
+
+    @staticmethod
+    def _os_rng(_job: int) -> zl.XorShift:
+        import os
+        return zl.XorShift.from_seed(os.urandom(16))
+
+    @property
+    def vk(self):
+        """fixed / permutation commitments and transcript_repr (identical on every lane)"""
+        return self.lanes[0].pk
+
+    def _prove_on(self, lane: _Lane, job: int, image) -> Tuple[bytes, List[int]]:
+        cols, scores = self.synth.synthesize(image, lane.pk.k, lane.usable, out=lane.cols)
+        return create_proof_limbs(lane.pk, cols, [to_limbs(scores)], self.rng_factory(job)), scores
+
+    def prove(self, image) -> Tuple[bytes, List[int]]:
+        """one proof on lane 0 (the latency path)"""
+        return self._prove_on(self.lanes[0], 0, image)
+
+    def prove_many(self, images: Sequence) -> List[Tuple[bytes, List[int]]]:
+        """All images, `lanes` at a time; results in input order.  The first error of any lane is re-raised."""
+        jobs: "queue.Queue[int]" = queue.Queue()
+        for i in range(len(images)):
+            jobs.put(i)
+        out: List[Optional[Tuple[bytes, List[int]]]] = [None] * len(images)
+        errors: List[BaseException] = []
+
+        def work(lane: _Lane):
+            while not errors:
+                try:
+                    i = jobs.get_nowait()
+                except queue.Empty:
+                    return
+                try:
+                    out[i] = self._prove_on(lane, i, images[i])
+                except BaseException as e:      # surfaced to the caller below
+                    errors.append(e)
+                    return
+        threads = [threading.Thread(target=work, args=(l,), daemon=True) for l in self.lanes[:max(1, min(len(self.lanes), len(images)))]]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        return out  # type: ignore[return-value]
+
+    def close(self):
+        for l in self.lanes:
+            l.close()
+        for c in self._owned_ctx:
+            c.close()
+        self.lanes, self._owned_ctx = [], []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()

@@ -58,3 +58,34 @@ def test_three_lanes_prove_concurrently(ctx):
         pk.close()
     for c, _, _ in lanes[1:]:
         c.close()
+
+
+def test_proof_service_image_to_proof():
+    """ProofService (zg_b200/service.py): lanes of independent provers, image in -> proof out with the native witness
+    synthesis; job 0 must reproduce the committed digest, every other proof must verify."""
+    import hashlib
+    import json
+    import zg_b200
+    from zg_b200.io import load_wnn, load_grayscale_image, synthetic_image
+    from zg_b200.prover import ParamsKZG
+    from zg_b200.service import ProofService
+    fix = json.load(open(os.path.join(GOLD, "proofs.json")))
+    fname = "model_28input_256entry_1hash_1bpi.hdf5"
+    e = fix["models"][fname]
+    wnn = load_wnn(os.path.join(GOLD, fname))
+    srs = H.Srs(e["k"], int(fix["srs_secret"], 16))
+    images = [load_grayscale_image(os.path.join(GOLD, "example_image_7.png"))] + [synthetic_image(i) for i in range(5)]
+    seed = bytes(range(16))
+    with ProofService(wnn, ParamsKZG(e["k"], srs.g, srs.g_lagrange), device=0, lanes=3,
+                      rng_factory=lambda job: zg_b200.lib.XorShift.from_seed(seed)) as svc:
+        results = svc.prove_many(images)
+        assert hashlib.sha256(results[0][0]).hexdigest() == e["proof_sha256"] and results[0][1] == e["outputs"]
+        zero = np.zeros((28, 28), dtype=np.uint8)
+        circ0, asm0 = wnn.synthesize(zero, e["k"])
+        opk = H.keygen(srs, circ0.cs, asm0)
+        assert svc.vk.fixed_commitments == opk.fixed_commitments
+        for img, (proof, outputs) in zip(images, results):
+            assert outputs == wnn.predict(img)
+            assert H.verify_proof(srs, opk, [outputs], proof)
+        single = svc.prove(images[0])
+        assert single[0] == results[0][0]
