@@ -130,6 +130,17 @@ def test_msm_pipeline_model():
         check(n, c, M, adv)
         check(n, c, M, uni, K0=4, serial_l1_threshold=64)
         check(n, c, M, adv, K0=4, serial_l1_threshold=64)
+    # chunked digit sort with several chunks, both bucket level-1 forms, level-1 serial fold
+    check(300, 7, 3, adv, J=5, l1_serial=True)
+    check(300, 7, 3, uni, J=7, l1_serial=False, K0=4, serial_l1_threshold=64)
+    check(1024, 9, 2, uni, J=3, l1_serial=True)
+    # mixed-basis batch (the product round: MSM 1 reads the other basis)
+    n, c = 200, 7
+    g = [rnd.randrange(1, R_MOD) for _ in range(n)]
+    g2 = [rnd.randrange(1, R_MOD) for _ in range(n)]
+    sl = [[uni() for _ in range(n)] for _ in range(3)]
+    exp = [sum(s * x for s, x in zip(sc, (g2 if m == 1 else g))) % R_MOD for m, sc in enumerate(sl)]
+    assert msm_model(sl, g, c, alt=g2, alt_mask=0b010, J=4) == exp
     check(128, 6, 1, lambda: R_MOD - 1)
     check(128, 6, 2, lambda: 1)
     check(128, 8, 1, lambda: 0)
