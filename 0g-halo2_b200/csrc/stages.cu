@@ -53,12 +53,19 @@ int zg_lookup_permute(zg_ctx* ctx, const zg_fr* a, const zg_fr* s, size_t usable
   uint8_t* ws = c.take<uint8_t>(lookup_workspace_bytes(n));
   ZG_CUDA(cudaMemcpyAsync(da, a, sizeof(Fr) * usable, cudaMemcpyHostToDevice, st));
   ZG_CUDA(cudaMemcpyAsync(ds, s, sizeof(Fr) * usable, cudaMemcpyHostToDevice, st));
-  ZG_CUDA(cudaMemsetAsync(flags, 0, 8, st));
   LookupTable tab = lookup_workspace_table(ws, n);
-  if (lookup_sort_table(ds, n, tab, ws, flags, /*full_sort=*/true, st, lc)) return ctx->cuda_fail(cudaGetLastError(), "lookup_sort_table");
-  if (lookup_permute(da, n, tab, dpa, dps, ws, flags + 1, st, lc)) return ctx->cuda_fail(cudaGetLastError(), "lookup_permute");
-  uint32_t hflags[2];
-  ZG_CUDA(cudaMemcpyAsync(hflags, flags, 8, cudaMemcpyDeviceToHost, st));
+  // as in zg_create_proof: sort on the top 48 bits first; the device flags distinct keys left out of order (values that
+  // agree in their top 48 bits, e.g. small integers) and the sort is redone on all 256 bits
+  uint32_t hflags[2] = {0, 0};
+  for (int attempt = 0; attempt < 2; attempt++) {
+    ZG_CUDA(cudaMemsetAsync(flags, 0, 8, st));
+    if (lookup_sort_table(ds, n, tab, ws, flags, /*full_sort=*/attempt == 1, st, lc))
+      return ctx->cuda_fail(cudaGetLastError(), "lookup_sort_table");
+    if (lookup_permute(da, n, tab, dpa, dps, ws, flags + 1, st, lc)) return ctx->cuda_fail(cudaGetLastError(), "lookup_permute");
+    ZG_CUDA(cudaMemcpyAsync(hflags, flags, 8, cudaMemcpyDeviceToHost, st));
+    ZG_CUDA(cudaStreamSynchronize(st));
+    if (!hflags[0]) break;
+  }
   ZG_CUDA(cudaMemcpyAsync(a_perm, dpa, sizeof(Fr) * usable, cudaMemcpyDeviceToHost, st));
   ZG_CUDA(cudaMemcpyAsync(s_perm, dps, sizeof(Fr) * usable, cudaMemcpyDeviceToHost, st));
   ZG_CUDA(cudaStreamSynchronize(st));
