@@ -36,6 +36,48 @@ __global__ void __launch_bounds__(MB_THREADS) mb_imad_wide_kernel(uint64_t* out,
   if (s == 0x12345678u) out[0] = s;
 }
 
+// IMAD.WIDE without any other instruction in the loop: 16 independent 64-bit accumulators, multiplier = own low word
+__global__ void __launch_bounds__(MB_THREADS) mb_imad_wide16_kernel(uint64_t* out, uint32_t b, uint32_t iters) {
+  uint64_t a[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) a[i] = threadIdx.x + i;
+  for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) a[i] = (uint64_t)(uint32_t)a[i] * b + a[i];
+  }
+  uint64_t s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) s ^= a[i];
+  if (s == 0x12345678u) out[0] = s;
+}
+// FP64 pipe (idle on this path today): DFMA alone, and DFMA interleaved 1:1 with IMAD.WIDE to see whether the two
+// pipes issue side by side (the question behind Emmart-style double-precision limb products)
+template <bool WITH_IMAD>
+__global__ void __launch_bounds__(MB_THREADS) mb_dfma_kernel(double* out, double b, double c, uint32_t ib, uint32_t iters) {
+  double d[8];
+  uint64_t a[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    d[i] = 1.0 + threadIdx.x * 1e-9 + i;
+    a[i] = threadIdx.x + i;
+  }
+  for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      d[i] = fma(d[i], b, c);
+      if (WITH_IMAD) a[i] = (uint64_t)(uint32_t)a[i] * ib + a[i];
+    }
+  }
+  double s = 0;
+  uint64_t x = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    s += d[i];
+    x ^= a[i];
+  }
+  if (s == 0.123456789 || x == 0x12345678u) out[0] = s + (double)x;
+}
+
 template <int VARIANT>
 __global__ void __launch_bounds__(MB_THREADS) mb_mulmod_kernel(Fr* out, Fr seed, uint32_t iters) {
   Fr x[4];
@@ -97,6 +139,18 @@ extern "C" int zg_bench_int_pipe(zg_ctx* ctx, int kind, uint32_t iters, double* 
       case 4:
         mb_mulmod_kernel<2><<<blocks, MB_THREADS, 0, ctx->stream>>>((Fr*)scratch, seed, iters);
         ops_per_thread = 4.0 * iters;
+        break;
+      case 5:
+        mb_dfma_kernel<false><<<blocks, MB_THREADS, 0, ctx->stream>>>((double*)scratch, 0.999999, 1e-7, 0x9e3779b1u, iters);
+        ops_per_thread = 8.0 * iters;
+        break;
+      case 6:   // reported rate = DFMA + IMAD.WIDE instructions together
+        mb_dfma_kernel<true><<<blocks, MB_THREADS, 0, ctx->stream>>>((double*)scratch, 0.999999, 1e-7, 0x9e3779b1u, iters);
+        ops_per_thread = 16.0 * iters;
+        break;
+      case 7:
+        mb_imad_wide16_kernel<<<blocks, MB_THREADS, 0, ctx->stream>>>((uint64_t*)scratch, 0x9e3779b1u, iters);
+        ops_per_thread = 16.0 * iters;
         break;
       default:
         return ctx->fail(ZG_E_INVALID, "bench_int_pipe: unknown kind");

@@ -207,7 +207,8 @@ int zg_wnn_synthesize(zg_wnn* w, const uint8_t* image, uint32_t k, uint32_t usab
 /* runs `iters` dependent-free IMAD-class instructions per thread on every SM and returns the
  * achieved rate in 1e9 thread-instructions per second; kind 0 = IMAD (32-bit), 1 = IMAD.WIDE,
  * 2 = Fr Montgomery multiplications, portable body (result in 1e9 mulmod/s), 3 = same, row-wise PTX
- * carry-chain body, 4 = same, even/odd carry-chain body (the one the kernels use) */
+ * carry-chain body, 4 = same, even/odd carry-chain body (the one the kernels use); 5 = DFMA (FP64 pipe), 6 = DFMA and
+ * IMAD.WIDE interleaved 1:1 (rate counts both), 7 = IMAD.WIDE with 16 independent accumulators and nothing else */
 int zg_bench_int_pipe(zg_ctx* ctx, int kind, uint32_t iters, double* giga_per_s);
 
 /* live timing of the dominant kernel (msm_accumulate_kernel, the level-0 bucket accumulation of every MSM): while
