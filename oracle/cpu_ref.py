@@ -31,9 +31,25 @@ _SO = os.path.join(_HERE, "build", "libzg_oracle-%s.so" % _cpu_tag())
 
 
 def build(force: bool = False) -> str:
+    """Compiles oracle/zg_oracle.c for this machine's CPU.  Safe when several processes start at once (one rank per GPU
+    under torchrun): an exclusive file lock serialises them and the library appears under its final name atomically."""
+    import fcntl
     src = os.path.join(_HERE, "zg_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
-        subprocess.check_call(["make", "-C", _HERE, "-s", "OUT=" + _SO])
+
+    def stale():
+        return force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src)
+    if not stale():
+        return _SO
+    os.makedirs(os.path.dirname(_SO), exist_ok=True)
+    with open(_SO + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if stale():                      # another process may have built it while we waited
+                tmp = "%s.tmp.%d" % (_SO, os.getpid())
+                subprocess.check_call(["make", "-C", _HERE, "-s", "OUT=" + tmp])
+                os.replace(tmp, _SO)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return _SO
 
 
