@@ -34,6 +34,9 @@ def _worker(rank, world, port, ret):
         assert proofs == [b"proof-%d-by-%d" % (i, i % world) for i in range(5)]
     else:
         assert proofs is None
+    # 1b. the batch hook (one ProofService call per rank) gives the same placement
+    batched = farm.prove_many(images, dist=dist, prove_batch=lambda idx, imgs: [b"proof-%d-by-%d" % (i, rank) for i in idx])
+    assert batched == proofs
     # 2. point-range MSM: each rank owns half of the bases; partials all-gathered; result identical on all ranks
     n = 64
     gen = bn254.g1_affine_to_limbs([bn254.G1_GEN])[0]
@@ -53,7 +56,7 @@ def _worker(rank, world, port, ret):
 def test_world_size_2_gloo():
     world = 2
     port = _free_port()
-    mgr = mp.Manager()
+    mgr = mp.get_context("spawn").Manager()      # no fork() from a process that already runs OpenMP threads
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     assert dict(ret) == {0: 1, 1: 1}
