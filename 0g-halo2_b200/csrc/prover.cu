@@ -401,6 +401,13 @@ int zg_pk_last_stage_ms(const zg_pk* pk, float out[8]) {
   return ZG_OK;
 }
 
+int zg_pk_set_transcript_repr(zg_ctx* ctx, zg_pk* pk, const zg_fr* transcript_repr) {
+  ZG_ENTER(ctx);
+  if (!pk || !transcript_repr) return ctx->fail(ZG_E_INVALID, "pk_set_transcript_repr: null argument");
+  memcpy(pk->transcript_repr.v, transcript_repr, 32);
+  return ZG_OK;
+}
+
 int zg_pk_commitments(zg_ctx* ctx, const zg_pk* pk, zg_g1_affine* fixed_out, zg_g1_affine* sigma_out) {
   ZG_ENTER(ctx);
   if (!pk) return ctx->fail(ZG_E_INVALID, "pk_commitments: null pk");

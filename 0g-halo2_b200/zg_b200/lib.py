@@ -30,7 +30,7 @@ EXPORTS = [
     "zg_coeff_to_extended", "zg_coeff_to_extended_dev", "zg_extended_to_coeff", "zg_extended_to_coeff_dev",
     "zg_bench_int_pipe", "zg_debug_field_op", "zg_probe_enable", "zg_probe_read",
     "zg_xorshift_seed", "zg_xorshift_fill", "zg_pk_load", "zg_pk_free", "zg_pk_commitments", "zg_create_proof",
-    "zg_pk_last_stage_ms",
+    "zg_pk_last_stage_ms", "zg_pk_set_transcript_repr",
     "zg_wnn_create", "zg_wnn_free", "zg_wnn_last_error", "zg_wnn_synthesize",
     "zg_lookup_permute", "zg_grand_product", "zg_batch_invert", "zg_eval_poly_batch", "zg_kate_division", "zg_evaluate_h",
 ]
@@ -93,6 +93,7 @@ def load_library() -> ctypes.CDLL:
     L.zg_pk_free.argtypes = [vp, vp]
     L.zg_pk_free.restype = None
     L.zg_pk_commitments.argtypes = [vp, vp, vp, vp]
+    L.zg_pk_set_transcript_repr.argtypes = [vp, vp, vp]
     L.zg_create_proof.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, sz, ctypes.POINTER(sz)]
     L.zg_pk_last_stage_ms.argtypes = [vp, vp]
     L.zg_wnn_create.argtypes = [vp, ctypes.POINTER(vp)]

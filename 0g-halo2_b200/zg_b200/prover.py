@@ -122,8 +122,8 @@ def keygen(ctx: zl.Context, params: ParamsKZG, cs, asm, transcript_repr: int | N
     perm_c = _affine_points(pc[:len(asm.perm_cols)])
     if transcript_repr is None:
         transcript_repr = vk_transcript_repr(params.k, cs, fixed_c, perm_c)
-    ctx._L.zg_pk_free(ctx._h, h)
-    h = _load_pk(ctx, params, cs, words, constants, fixed_mont, mapping, transcript_repr)
+    repr_limbs = np.ascontiguousarray(to_limbs([transcript_repr])[0], dtype=np.uint64)
+    ctx._ck(ctx._L.zg_pk_set_transcript_repr(ctx._h, h, repr_limbs.ctypes.data))
     return ProvingKey(ctx, h, params.k, cs, fixed_c, perm_c, transcript_repr)
 
 

@@ -133,6 +133,9 @@ typedef struct {
  * l_active; everything stays resident on the context's device.  Needs the SRS (zg_srs_load, same k). */
 int zg_pk_load(zg_ctx* ctx, const zg_pk_desc* desc, zg_pk** out);
 void zg_pk_free(zg_ctx* ctx, zg_pk* pk);
+/* VerifyingKey::transcript_repr is a hash over the vk, which contains the commitments zg_pk_load has just computed: a
+ * caller that derives it from zg_pk_commitments sets it here instead of loading the key a second time */
+int zg_pk_set_transcript_repr(zg_ctx* ctx, zg_pk* pk, const zg_fr* transcript_repr);
 /* VerifyingKey: fixed_commitments (num_fixed) and permutation commitments (m), affine */
 int zg_pk_commitments(zg_ctx* ctx, const zg_pk* pk, zg_g1_affine* fixed_out, zg_g1_affine* sigma_out);
 /* advice: num_advice columns of 2^k values, host pointers (or device pointers on the context's device: the

@@ -50,6 +50,7 @@ extern "C" {
     pub fn zg_pk_load(ctx: *mut zg_ctx, desc: *const zg_pk_desc, out: *mut *mut zg_pk) -> c_int;
     pub fn zg_pk_free(ctx: *mut zg_ctx, pk: *mut zg_pk);
     pub fn zg_pk_commitments(ctx: *mut zg_ctx, pk: *const zg_pk, fixed: *mut G1Affine, sigma: *mut G1Affine) -> c_int;
+    pub fn zg_pk_set_transcript_repr(ctx: *mut zg_ctx, pk: *mut zg_pk, transcript_repr: *const Fr) -> c_int;
     pub fn zg_evaluate_h(ctx: *mut zg_ctx, pk: *mut zg_pk, advice_polys: *const *const Fr, instance_polys: *const *const Fr,
                          lookup_input_polys: *const *const Fr, lookup_table_polys: *const *const Fr,
                          lookup_product_polys: *const *const Fr, perm_product_polys: *const *const Fr,
