@@ -401,6 +401,9 @@ int zg_pk_last_stage_ms(const zg_pk* pk, float out[8]) {
   return ZG_OK;
 }
 
+// the transcript's hash (host code), exposed so that CPU-only tests can check it against the published keccak256 vectors
+void zg_debug_keccak256(const uint8_t* data, size_t len, uint8_t out[32]) { keccak256(data, len, out); }
+
 int zg_pk_set_transcript_repr(zg_ctx* ctx, zg_pk* pk, const zg_fr* transcript_repr) {
   ZG_ENTER(ctx);
   if (!pk || !transcript_repr) return ctx->fail(ZG_E_INVALID, "pk_set_transcript_repr: null argument");

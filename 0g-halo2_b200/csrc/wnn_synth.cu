@@ -70,8 +70,10 @@ struct zg_wnn {
   uint32_t word_index_bits = 0, bytes_per_word = 0, words_per_filter = 0;
   std::vector<uint64_t> words;   // [bloom index][word], big-endian packed bits (array_lookup.rs from_be_bits)
   Fr inv_pow2[33];               // 1 / 2^k, Montgomery
-  std::string err;
 };
+
+// the model is shared read-only by the threads of a proof service: the last error is kept per calling thread
+static thread_local std::string g_wnn_err;
 
 namespace {
 
@@ -409,9 +411,9 @@ int zg_wnn_create(const zg_wnn_desc* d, zg_wnn** out) {
 
 void zg_wnn_free(zg_wnn* w) { delete w; }
 
-const char* zg_wnn_last_error(const zg_wnn* w) { return w ? w->err.c_str() : "null model"; }
+const char* zg_wnn_last_error(const zg_wnn* w) { return w ? g_wnn_err.c_str() : "null model"; }
 
-int zg_wnn_synthesize(zg_wnn* w, const uint8_t* image, uint32_t k, uint32_t usable_rows, zg_fr* const* advice, uint64_t* outputs) {
+int zg_wnn_synthesize(const zg_wnn* w, const uint8_t* image, uint32_t k, uint32_t usable_rows, zg_fr* const* advice, uint64_t* outputs) {
   if (!w || !image || !advice || k < 1 || k > 28 || usable_rows == 0 || usable_rows > (1u << k)) return ZG_E_INVALID;
   const size_t n = (size_t)1 << k;
   for (int c = 0; c < 6; c++) {
@@ -442,7 +444,7 @@ int zg_wnn_synthesize(zg_wnn* w, const uint8_t* image, uint32_t k, uint32_t usab
     if (outputs) outputs[c] = score.v.l[0];
   }
   if (S.overflow) {
-    w->err = "not enough rows available (k = " + std::to_string(k) + ")";   // plonk::Error::NotEnoughRowsAvailable
+    g_wnn_err = "not enough rows available (k = " + std::to_string(k) + ")";   // plonk::Error::NotEnoughRowsAvailable
     return ZG_E_SYNTH;
   }
   return ZG_OK;

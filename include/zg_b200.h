@@ -185,7 +185,7 @@ int zg_evaluate_h(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice_polys, cons
  * 372-393) and every sub-chip, under halo2's SimpleFloorPlanner: produces the six advice columns zg_create_proof takes.
  * In the reference this is Rust on the host; here it is the native counterpart of zg_b200/plonk/gadgets.py, checked
  * cell for cell against it (tests/test_wnn_synth.py).  A zg_wnn is immutable after creation and may be shared by
- * threads; each zg_wnn_synthesize call writes only its own output buffers (the error string is per model). */
+ * threads; each zg_wnn_synthesize call writes only its own output buffers (zg_wnn_last_error is per calling thread). */
 typedef struct zg_wnn zg_wnn;
 typedef struct {
   uint64_t p;                        /* hash modulus (Wnn::p) */
@@ -203,7 +203,7 @@ const char* zg_wnn_last_error(const zg_wnn* w);
 /* image: width*height bytes; advice: 6 columns of 2^k elements (zeroed, then filled below `usable_rows` = 2^k -
  * blinding_factors - 1); outputs: n_classes class scores (the public instance).  ZG_E_SYNTH when the circuit does
  * not fit in `usable_rows` rows (plonk::Error::NotEnoughRowsAvailable). */
-int zg_wnn_synthesize(zg_wnn* w, const uint8_t* image, uint32_t k, uint32_t usable_rows, zg_fr* const* advice,
+int zg_wnn_synthesize(const zg_wnn* w, const uint8_t* image, uint32_t k, uint32_t usable_rows, zg_fr* const* advice,
                       uint64_t* outputs);
 
 /* ---- micro-benchmarks used for the integer-pipe roofline (bench.py) ---------------------- */
@@ -225,6 +225,8 @@ int zg_probe_read(zg_ctx* ctx, double* kernel_ms, uint64_t* launches, uint64_t* 
  * op 0 mul, 1 mul (portable body), 2 mul (row-wise PTX body), 3 add, 4 sub, 5 inverse(a), 6 from_mont(a),
  * 7 to_mont(a), 8 mul (even/odd carry-chain body) */
 int zg_debug_field_op(zg_ctx* ctx, int field, int op, const void* a, const void* b, void* out, size_t n);
+/* keccak256 as used by the EvmTranscript inside zg_create_proof (host code; needs no context and no GPU) */
+void zg_debug_keccak256(const uint8_t* data, size_t len, uint8_t out[32]);
 
 #ifdef __cplusplus
 }

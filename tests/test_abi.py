@@ -52,3 +52,22 @@ def test_product_never_imports_oracle():
                 if re.search(r"^\s*(from|import)\s+(oracle|cpu_ref|bn254\b)", src, flags=re.M) or "zg_oracle" in src:
                     bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_transcript_keccak256_known_answers():
+    """the product's own keccak256 (host code in csrc/prover.cu, the hash of EvmTranscript): published vectors plus
+    agreement with the oracle's implementation across the 136-byte rate boundary"""
+    import ctypes
+    import zg_b200
+    import halo2_ref as H
+    L = zg_b200.load_library()
+
+    def k(data: bytes) -> bytes:
+        out = (ctypes.c_uint8 * 32)()
+        L.zg_debug_keccak256(data, len(data), out)
+        return bytes(out)
+    assert k(b"").hex() == "c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470"
+    assert k(b"abc").hex() == "4e03657aea45a94fc7d47ba826c8d667c0d1e6e33a64a036ec44f58fa12d6c45"
+    for n in (1, 31, 32, 33, 64, 96, 135, 136, 137, 271, 272, 273, 1000):
+        data = bytes((7 * i + n) & 0xFF for i in range(n))
+        assert k(data) == H.keccak256(data), n
