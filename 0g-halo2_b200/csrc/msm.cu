@@ -10,14 +10,14 @@
 //     removes the per-window bucket reductions and the 254 doublings of the window Horner.
 //   * signed c-bit digits -> 2^(c-1) buckets per MSM; zero digits are skipped, so sparse /
 //     small-valued advice columns cost proportionally less.
-//   * (bucket, point) pairs are counting-sorted; accumulation is a load-balanced SEGMENTED
-//     reduction over the sorted list (fixed-size chunks per thread), so a bucket that receives
-//     20 000 points (value "1" in an advice column) costs the same per point as a uniform one.
-//     Chunk-boundary partial sums are folded by a second serial level and then by warp-shuffle
-//     segmented reductions.
-//   * the weighted bucket sum  sum_b b * B_b  is a warp-shuffle suffix scan (32 buckets per
-//     warp) followed by a one-CTA finish kernel.
-//   * several MSMs over the same basis (one Fiat-Shamir round's commitments) share every launch.
+//   * (bucket, point) pairs are counting-sorted by CTAs that keep the bucket counters in shared memory (no global
+//     atomics; msm_digits_kernel below); accumulation is a load-balanced SEGMENTED reduction over the sorted list
+//     (fixed-size chunks per thread), so a bucket that receives 20 000 points (value "1" in an advice column) costs
+//     the same per point as a uniform one.  Chunk-boundary partial sums are folded by a second serial level and then
+//     by warp-shuffle segmented reductions (msm_tail.cu).
+//   * the weighted bucket sum  sum_b (b + 1) * B_b  has a latency-optimal and a throughput-optimal first level
+//     (msm_tail.cu), a warp-parallel second level and a one-CTA finish kernel.
+//   * several MSMs (one Fiat-Shamir round's commitments) share every launch, and a batch may mix the two bases.
 // The level-0 accumulation is 100 KB of SASS with the multiplier inlined and stalls on instruction fetch
 // (ncu: stalled_no_instruction 3.0 per issue, profiles/r01_ncu_full_msm_accumulate_small_proof.txt):
 // outline it (field.cuh).
