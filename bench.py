@@ -593,6 +593,13 @@ def main():
         "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches), "clocks": clocks,
     }
+    # the same dominant kernel against the HBM roofline (the base contract's vocabulary): algorithmic bytes = 72 B per point
+    # addition (8-B sorted entry + 64-B table point); far from binding, which is the point
+    if roof and roof.get("kernel") == "msm_accumulate_kernel":
+        gbs = roof["point_additions_per_launch"] * 72 / 1e9 / (roof["avg_launch_ms"] * 1e-3)
+        extra["roofline_hbm"] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                                 "traffic": roof.get("traffic"), "peak_source": peak_src, "kernel": roof["kernel"],
+                                 "note": "same launches as `roofline`; this kernel is bound by the integer pipe, not by HBM"}
     if "scaling_override" in extra:
         out["scaling"] = extra.pop("scaling_override")
     out.update(extra)
