@@ -587,8 +587,10 @@ def main():
         "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
         "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u256 (8x32-bit Montgomery limbs)", "data": "synthetic",
-        "config": {"workload": workload_name(args), "l2": "flushed between steps",
-                   "synthesis": "host witness synthesis excluded from both arms"},
+        "config": dict({"workload": workload_name(args), "l2": "flushed between steps",
+                        "synthesis": "host witness synthesis excluded from both arms"},
+                       **({"batch": "%d independent proofs in flight per GPU; one step = one batch" % extra["inflight"]}
+                          if "inflight" in extra else {})),
         "roofline": roof, "int_pipe": int_pipe,
         "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches), "clocks": clocks,
