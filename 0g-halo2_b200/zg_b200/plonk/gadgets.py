@@ -130,6 +130,11 @@ class RangeCheck:
         self.range_check(lay, diff, y.bit_length())
 
 
+def load_bytes_column(lay: SimpleFloorPlanner, table_column: Column):
+    """range_check.rs:128-149: a table column holding 0..255 (only needed when no byte table exists already)."""
+    lay.assign_table("table_idx", [table_column], [(i,) for i in range(1 << K_RANGE)])
+
+
 # ---- greater_than.rs / encode_image.rs -------------------------------------------------------
 class GreaterThan:
     def __init__(self, cs, x, y, diff, is_gt, rc: RangeCheck):
@@ -268,10 +273,13 @@ class Hash:
 
 # ---- bloom_filter/array_lookup.rs --------------------------------------------------------------
 class ArrayLookup:
-    def __init__(self, cs, hash_dec, byte_index, bit_index, bloom_index, bloom_value, n_hashes, bits_per_hash):
+    def __init__(self, cs, hash_dec, byte_index, bit_index, bloom_index, bloom_value, n_hashes, bits_per_hash,
+                 word_index_bits=None):
         assert 7 <= bits_per_hash <= 32
-        byte_index_bits = int((bits_per_hash - 3.0) / 2.0 - math.floor(math.log2(n_hashes)))   # :63-67
-        self.word_index_bits = bits_per_hash - (byte_index_bits + 3)
+        if word_index_bits is None:                     # ArrayLookupConfig::from(BloomFilterConfig), :51-75
+            byte_index_bits = int((bits_per_hash - 3.0) / 2.0 - math.floor(math.log2(n_hashes)))   # :63-67
+            word_index_bits = bits_per_hash - (byte_index_bits + 3)
+        self.word_index_bits = word_index_bits
         self.n_hashes, self.bits_per_hash = n_hashes, bits_per_hash
         self.cols = (hash_dec, byte_index, bit_index, bloom_index, bloom_value)
         self.t_index, self.t_word, self.t_value = (cs.lookup_table_column() for _ in range(3))

@@ -5,10 +5,12 @@
 
 BASELINE.json metric: "WNN MNIST proofs/sec & proof latency; MSM pts/s, NTT GB/s vs roofline".
 Workloads:
-  proof (default)  one zero_g WNN proof per step: create_proof (KZG/BN254, GWC, EvmTranscript) for
-                   `--model` (default small = BASELINE configs[1], model_28input_1024entry_2hash_2bpi,
-                   k = 15) on benches/example_image_7.png.  Witness synthesis is host work outside the
-                   replaced path (BASELINE north_star) and is done once, untimed, for both arms.
+  proof (default)  zero_g WNN proofs, create_proof (KZG/BN254, GWC, EvmTranscript) for `--model` on
+                   benches/example_image_7.png.  Default model = large: the north-star target, the
+                   49input_8192entry_4hash_6bpi shape at k = 17 (synthetic stand-in, the real file is absent upstream;
+                   BASELINE configs[3] on one GPU); small / tiny / medium = configs[1] / [0] / [2].  A step =
+                   `--inflight` lanes x `--proofs-per-lane` proofs.  `value`: advice columns resident in HBM;
+                   `e2e`: image -> native witness synthesis -> proof bytes (what benches/bench.rs:30-36 times).
   msm              one 2^LOGN-point BN254 G1 MSM per step (uniform scalars)      -> points/s
   keygen           keygen_vk + keygen_pk of `--model` on the device (benches/bench.rs bench_key_generation)  -> keygens/s
   msm_sharded      ONE 2^LOGN-point MSM split by point range over the ranks, partial sums all-gathered (NCCL)
@@ -51,16 +53,21 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("ZG_BENCH_WORKLOAD", "proof"))
-    ap.add_argument("--model", default=os.environ.get("ZG_BENCH_MODEL", "small"), choices=list(MODELS))
+    ap.add_argument("--model", default=os.environ.get("ZG_BENCH_MODEL", "large"), choices=list(MODELS),
+                    help="proof / keygen workloads: large (default) = the north-star target, the 49input_8192entry_4hash_6bpi "
+                         "shape at k = 17 (BASELINE configs[3] on one GPU); small = configs[1]; tiny = configs[0]; medium = configs[2]")
     ap.add_argument("--logn", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--inflight", type=int, default=int(os.environ.get("ZG_BENCH_INFLIGHT", "4")),
                     help="proof workload: independent proofs in flight per GPU (one context + stream + host thread each); "
                          "a step is one batch of that many proofs")
-    ap.add_argument("--synth", default=os.environ.get("ZG_BENCH_SYNTH", "cached"), choices=["cached", "native"],
-                    help="proof workload, e2e leg: `cached` = witnesses synthesized once, untimed (the default: synthesis is "
-                         "outside the replaced path); `native` = every e2e proof starts from the IMAGE: zg_wnn_synthesize "
-                         "(C++ host code) fills the lane's pinned advice buffers inside the timed region")
+    ap.add_argument("--synth", default=os.environ.get("ZG_BENCH_SYNTH", "native"), choices=["cached", "native"],
+                    help="proof workload, e2e leg: `native` (default) = every e2e proof starts from the IMAGE, as "
+                         "benches/bench.rs:30-36 `wnn.proof(&pk, &params, &img)` does: zg_wnn_synthesize (C++ host code) fills the "
+                         "lane's pinned advice buffers inside the timed region; `cached` = witnesses synthesized once, untimed")
+    ap.add_argument("--proofs-per-lane", type=int, default=int(os.environ.get("ZG_BENCH_PPL", "2")),
+                    help="proof workload: proofs every lane proves back to back in one step (a step = inflight x this many "
+                         "proofs); 2 keeps the default run's timed region above two seconds")
     ap.add_argument("--images", type=int, default=int(os.environ.get("ZG_BENCH_IMAGES", "1")),
                     help="proof workload: 1 = benches/example_image_7.png for every proof (the reference's bench input); "
                          "K > 1 = K distinct synthetic MNIST-shaped images per rank, proofs cycle through them "
@@ -343,10 +350,15 @@ def main():
         pk = lanes[0].pk
         pool = ThreadPoolExecutor(K) if K > 1 else None
 
+        PPL = max(1, args.proofs_per_lane)
+
+        def lane_run(lane, method):
+            return [getattr(lane, method)() for _ in range(PPL)]
+
         def run_all(method):
             if pool is None:
-                return [getattr(lanes[0], method)()]
-            return [f.result() for f in [pool.submit(getattr(l, method)) for l in lanes]]
+                return lane_run(lanes[0], method)
+            return [r for f in [pool.submit(lane_run, l, method) for l in lanes] for r in f.result()]
         step_dev = lambda: run_all("prove_dev")
         step_e2e = lambda: run_all("prove_e2e")
         # every measured proof is a real proof: check one per lane against the restated verifier (untimed)
@@ -356,16 +368,17 @@ def main():
             opk = H.keygen(srs, circ_o.cs, asm_o)
             assert pk.fixed_commitments == opk.fixed_commitments and pk.perm_commitments == opk.perm_commitments
             seen = set()
-            for _ in range((len(witnesses) + K - 1) // K + 1):
+            for _ in range((len(witnesses) + K * PPL - 1) // (K * PPL) + 1):
                 for w, pr in step_e2e():
                     if w not in seen:
                         assert H.verify_proof(srs, opk, [witnesses[w][1]], pr), "GPU proof rejected by the restated verifier"
                         seen.add(w)
             assert len(seen) == len(witnesses), "not every image was proven during the check"
-        metric, unit, units = "proofs_per_s", "proofs/s", K
-        h2d, d2h = K * (len(lanes[0].adv_host[0]) * n * 32 + len(outputs) * 32), K * 3840
+        metric, unit, units = "proofs_per_s", "proofs/s", K * PPL
+        h2d, d2h = units * (len(lanes[0].adv_host[0]) * n * 32 + len(outputs) * 32), units * 3840
         dom_kernel = "msm_accumulate_kernel"
         extra["inflight"] = K
+        extra["proofs_per_step"] = K * PPL
         extra["images"] = "example_image_7.png" if nimg == 1 else "%d synthetic MNIST-shaped images per rank" % nimg
         extra["e2e_starts_from"] = "image (native witness synthesis timed)" if native is not None else "synthesized advice columns"
         if not args.no_cpu_baseline and rank == 0:
@@ -567,29 +580,24 @@ def main():
         c = int(os.environ.get("ZG_MSM_C", "0")) or max(8, min(16, ll - 2))
         ach = msm_imad(nl, c) / 1e9 / (ms_per_step * 1e-3)
         step_roof = {"bound": "int", "achieved": ach, "peak": imad_peak, "unit": "GIMAD/s", "frac": ach / imad_peak,
-                     "window_c": c, "note": "whole MSM: SURVEY 8(d) algorithmic IMAD(N, c) / step time"}
+                     "window_c": c, "note": "SURVEY 8(d) per-window formula IMAD(N, c) / step time; it OVER-COUNTS for this fixed-base "
+                                            "design (one bucket set instead of one per window) -- not an achieved rate, see `roofline`"}
         roof = kernel_roofline(probe, imad_peak, ms, peak_src="measured in this run (zg_bench_int_pipe kind 0)",
                                traffic=NCU_TRAFFIC.get("%s_%d" % (args.workload, logn)))
-        extra["step_roofline"] = step_roof
+        extra["survey_formula_roofline"] = step_roof
     elif args.workload == "keygen":
         roof = None                                # a secondary number: no roofline claim (24 MSMs + 27 extended NTTs + uploads)
     else:
-        imad, c = proof_msm_imad(n, k)
-        # MSM share of the step: stages that are MSM-dominated are reported by the library per proof
-        ach = units * imad / 1e9 / (ms_per_step * 1e-3)
-        step_roof = {"bound": "int", "achieved": ach, "peak": imad_peak, "unit": "GIMAD/s", "frac": ach / imad_peak, "window_c": c,
-                     "note": "algorithmic IMAD of the 30 MSMs of every proof of the step / whole step time (all stages)"}
         roof = kernel_roofline(probe, imad_peak, lat_ms * args.steps, peak_src="measured in this run (zg_bench_int_pipe kind 0)",
                                traffic=NCU_TRAFFIC.get("proof_" + args.model))
-        extra["step_roofline"] = step_roof
         extra["stage_ms_last_proof"] = stage
     out = {
         "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
         "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u256 (8x32-bit Montgomery limbs)", "data": "synthetic",
-        "config": dict({"workload": workload_name(args), "l2": "flushed between steps",
-                        "synthesis": "host witness synthesis excluded from both arms"},
-                       **({"batch": "%d independent proofs in flight per GPU; one step = one batch" % extra["inflight"]}
+        "config": dict({"workload": workload_name(args), "l2": "flushed between steps"},
+                       **({"batch": "%d independent proofs in flight per GPU, %d proofs per step" % (extra["inflight"], extra["proofs_per_step"]),
+                           "synthesis": "e2e: " + extra["e2e_starts_from"] + "; value: advice columns resident in HBM"}
                           if "inflight" in extra else {})),
         "roofline": roof, "int_pipe": int_pipe,
         "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

@@ -310,14 +310,25 @@ def vk_transcript_repr(k, cs, fixed_commitments, perm_commitments) -> int:
 
 
 def keygen(srs: Srs, cs, asm, real_msm=False) -> ProvingKey:
-    """keygen_vk + keygen_pk.  `asm` is the synthesized Assembly (zero image); selectors are compressed here."""
-    from zg_b200.plonk.mock import finalize_fixed
+    """keygen_vk + keygen_pk.  `cs` is a front-end constraint system BEFORE selector compression (read as data and
+    copied into the oracle's own RefCS, circuit_ref.py) or a RefCS; `asm` carries the synthesized columns of the zero
+    image as plain data (fixed, selector activations, permutation mapping).  Selector compression, degree and blinding
+    factors are the oracle's own restatement -- nothing is imported from the package."""
+    from circuit_ref import RefCS
+    if not isinstance(cs, RefCS):
+        cs = RefCS.from_frontend(cs)
     n, k = asm.n, asm.k
+    n_fixed_before = cs.num_fixed
+    if not cs.compressed:
+        new_cols = cs.compress_selectors([list(a) for a in asm.selectors])
+        fixed_int = [list(c) for c in asm.fixed[:n_fixed_before]] + new_cols
+        cs._fixed_int = fixed_int
+    fixed_int = cs._fixed_int
     dom = Domain(k, cs.degree())
     com = Committer(srs, dom, real_msm)
     pk = ProvingKey()
     pk.k, pk.n, pk.cs, pk.domain = k, n, cs, dom
-    fixed_int = finalize_fixed(cs, asm)
+    pk.fixed_int = fixed_int
     pk.fixed_values = [bn254.fr_to_limbs(c) for c in fixed_int]
     pk.fixed_polys = [dom.lagrange_to_coeff(v) for v in pk.fixed_values]
     pk.fixed_cosets = [dom.coeff_to_extended(c) for c in pk.fixed_polys]
@@ -687,6 +698,17 @@ def create_proof(srs: Srs, pk: ProvingKey, advice_int, instances, rng: XorShiftR
         for i in ref[1:]:
             e = e[i]
         return e
+    # Fold direction (decided here, documented because SURVEY.md B.9 recorded the opposite):
+    # the i-th query of an opening point is weighted by v^i -- the FIRST query gets v^0.  This follows
+    # halo2_proofs v2023_04_20 `poly/kzg/multiopen/gwc/prover.rs`, which folds with
+    #     queries.iter().zip(powers(*v)).map(|(q, power_of_v)| (poly * power_of_v, eval * power_of_v)).reduce(sum)
+    # (`arithmetic::powers` yields 1, v, v^2, ...), and it is what the matching verifier of the reference's
+    # transcript crate does: snark-verifier v2023_04_20 `pcs/kzg/multiopen/gwc19.rs` `QuerySet::msm` zips the
+    # polynomials of a set with `powers_of_v` = v.powers(max_set_len), again first polynomial <-> v^0.
+    # The Horner form `acc = acc * v + poly` (first query <-> highest power) that SURVEY B.9 wrote down is the
+    # older zcash-era multiopen loop and was replaced before this tag.  Prover and verifier only interoperate
+    # if both use the same direction, so a Rust-side run (rust/tools/ref_dump.rs) settles it for good;
+    # until then parity on this point rests on the recollection above.  csrc/prover.cu section 10 follows it.
     v = tr.squeeze()
     for rot, qs in group_by_point(build_queries(cs, dom, x, len(perm_sets))):
         z = dom.rotate_omega(x, rot)

@@ -54,6 +54,18 @@ def test_product_never_imports_oracle():
     assert not bad, bad
 
 
+def test_oracle_never_imports_product():
+    """the checker stands on its own: nothing under oracle/ imports the package (its constraint-system bookkeeping and
+    selector compression are oracle/circuit_ref.py, an independent restatement)"""
+    bad = []
+    for f in os.listdir(os.path.join(ROOT, "oracle")):
+        if f.endswith(".py"):
+            src = open(os.path.join(ROOT, "oracle", f)).read()
+            if re.search(r"^\s*(from|import)\s+zg_b200", src, flags=re.M):
+                bad.append(f)
+    assert not bad, bad
+
+
 def test_transcript_keccak256_known_answers():
     """the product's own keccak256 (host code in csrc/prover.cu, the hash of EvmTranscript): published vectors plus
     agreement with the oracle's implementation across the 136-byte rate boundary"""
