@@ -56,12 +56,17 @@ int get_domain(zg_ctx* ctx, uint32_t logn, const Fr& omega, Domain** out) {
   size_t n = (size_t)1 << logn;
   ZG_CUDA(cudaMalloc(&d.tw, sizeof(Fr) * n));
   Fr* flat = nullptr;
-  ZG_CUDA(cudaMalloc(&flat, sizeof(Fr) * (n / 2 + 1)));
-  cudaError_t e = ntt_build_twiddles(d.tw, flat, omega, logn, ctx->stream);
-  ctx->launches += 2;
-  if (e != cudaSuccess) return ctx->cuda_fail(e, "ntt_build_twiddles");
-  ZG_CUDA(cudaStreamSynchronize(ctx->stream));
-  ZG_CUDA(cudaFree(flat));
+  cudaError_t e = cudaMalloc(&flat, sizeof(Fr) * (n / 2 + 1));
+  if (e == cudaSuccess) {
+    e = ntt_build_twiddles(d.tw, flat, omega, logn, ctx->stream);
+    ctx->launches += 2;
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  }
+  if (flat) cudaFree(flat);
+  if (e != cudaSuccess) {                 // nothing stays allocated when the table could not be built
+    cudaFree(d.tw);
+    return ctx->cuda_fail(e, "ntt_build_twiddles");
+  }
   auto res = ctx->domains.emplace(key, d);
   *out = &res.first->second;
   return ZG_OK;

@@ -7,7 +7,9 @@
 // msm.cu, poly.cu, expr.cu and lookup.cu; the host only sequences rounds, hashes (keccak256) and
 // normalises <= 8 commitments per round.  Witness synthesis is the caller's (BASELINE north_star).
 #include <algorithm>
+#include <cerrno>
 #include <memory>
+#include <sys/random.h>
 #include "ctx.cuh"
 #include "expr.cuh"
 #include "lookup.cuh"
@@ -208,6 +210,14 @@ struct zg_pk {
   uint64_t* rnd_words_host = nullptr;  // pinned
   size_t n_draws = 0;
   float stage_ms[8] = {0};
+  std::vector<char> table_cacheable;   // per lookup: the table reads fixed columns and constants only
+  zg_pk() = default;
+  zg_pk(const zg_pk&) = delete;
+  zg_pk& operator=(const zg_pk&) = delete;
+  ~zg_pk() {                           // every early return of zg_pk_load releases the arena through this
+    if (arena) cudaFree(arena);
+    if (rnd_words_host) cudaFreeHost(rnd_words_host);
+  }
 };
 
 namespace {
@@ -245,6 +255,48 @@ static int parse_cs(zg_ctx* ctx, zg_pk* pk, const zg_pk_desc* d, std::vector<uin
   if (!need(nops)) return ctx->fail(ZG_E_INVALID, "pk_load: truncated blob");
   ops.assign(w + p, w + p + nops);
   if (pk->degree < 3) return ctx->fail(ZG_E_INVALID, "pk_load: constraint degree < 3");
+  // every program: operands in range, stack depth within the interpreter's (expr.cuh EXPR_STACK), one value left
+  for (uint32_t g = 0; g < pk->n_progs; g++) {
+    if (prog_off[g] > prog_off[g + 1] || prog_off[g + 1] > nops) return ctx->fail(ZG_E_INVALID, "pk_load: bad program table");
+    int depth = 0;
+    for (uint32_t pc = prog_off[g]; pc < prog_off[g + 1]; pc++) {
+      const uint32_t op = ops[pc] & 0xff, arg = ops[pc] >> 8;
+      switch (op) {
+        case OP_CONST: if (arg >= d->n_constants) return ctx->fail(ZG_E_INVALID, "pk_load: constant index out of range"); depth++; break;
+        case OP_ADVICE: case OP_FIXED: case OP_INSTANCE:
+          if (arg >= pk->q[op - OP_ADVICE].size()) return ctx->fail(ZG_E_INVALID, "pk_load: query index out of range");
+          depth++; break;
+        case OP_NEG: if (depth < 1) return ctx->fail(ZG_E_INVALID, "pk_load: malformed program"); break;
+        case OP_SCALE:
+          if (depth < 1 || arg >= d->n_constants) return ctx->fail(ZG_E_INVALID, "pk_load: malformed program");
+          break;
+        case OP_ADD: case OP_SUB: case OP_MUL:
+          if (depth < 2) return ctx->fail(ZG_E_INVALID, "pk_load: malformed program");
+          depth--; break;
+        default: return ctx->fail(ZG_E_INVALID, "pk_load: unknown opcode");
+      }
+      if (depth > EXPR_STACK) return ctx->fail(ZG_E_INVALID, "pk_load: expression deeper than the evaluator's stack");
+    }
+    if (depth != 1) return ctx->fail(ZG_E_INVALID, "pk_load: malformed program");
+  }
+  const uint32_t ncols[3] = {pk->A, pk->F, pk->I};
+  for (int kind = 0; kind < 3; kind++)
+    for (auto& qq : pk->q[kind])
+      if (qq.first >= ncols[kind]) return ctx->fail(ZG_E_INVALID, "pk_load: query names a column that does not exist");
+  // a lookup table may be sorted once per key only if nothing in it changes from proof to proof
+  pk->table_cacheable.assign(pk->n_lookups, 0);
+  for (uint32_t l = 0; l < pk->n_lookups; l++) {
+    if ((uint64_t)pk->in_first[l] + pk->in_count[l] > pk->n_progs || (uint64_t)pk->tab_first[l] + pk->tab_count[l] > pk->n_progs ||
+        !pk->in_count[l] || !pk->tab_count[l])
+      return ctx->fail(ZG_E_INVALID, "pk_load: lookup program range out of bounds");
+    bool fixed_only = pk->tab_count[l] == 1;
+    for (uint32_t g = pk->tab_first[l]; fixed_only && g < pk->tab_first[l] + pk->tab_count[l]; g++)
+      for (uint32_t pc = prog_off[g]; pc < prog_off[g + 1]; pc++) {
+        const uint32_t op = ops[pc] & 0xff;
+        if (op == OP_ADVICE || op == OP_INSTANCE) fixed_only = false;
+      }
+    pk->table_cacheable[l] = fixed_only;
+  }
   return ZG_OK;
 }
 
@@ -387,11 +439,68 @@ void zg_xorshift_fill(void* state, uint64_t* out, size_t n) {
   r->x = x; r->y = y; r->z = z; r->w = w;
 }
 
+// ---- ChaCha20 keystream RNG (RFC 8439 block function; 64-bit counter in words 12-13, nonce in 14-15) -----------------
+static inline uint32_t rotl32(uint32_t v, int c) { return (v << c) | (v >> (32 - c)); }
+#define ZG_QR(a, b, c, d) \
+  a += b; d ^= a; d = rotl32(d, 16); c += d; b ^= c; b = rotl32(b, 12); a += b; d ^= a; d = rotl32(d, 8); c += d; b ^= c; b = rotl32(b, 7);
+static void chacha20_block(const zg_chacha20* r, uint64_t counter, uint8_t out[64]) {
+  uint32_t in[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u};
+  for (int i = 0; i < 8; i++) in[4 + i] = r->key[i];
+  in[12] = (uint32_t)counter; in[13] = (uint32_t)(counter >> 32); in[14] = r->nonce[0]; in[15] = r->nonce[1];
+  uint32_t x[16];
+  memcpy(x, in, sizeof(x));
+  for (int round = 0; round < 10; round++) {
+    ZG_QR(x[0], x[4], x[8], x[12]) ZG_QR(x[1], x[5], x[9], x[13]) ZG_QR(x[2], x[6], x[10], x[14]) ZG_QR(x[3], x[7], x[11], x[15])
+    ZG_QR(x[0], x[5], x[10], x[15]) ZG_QR(x[1], x[6], x[11], x[12]) ZG_QR(x[2], x[7], x[8], x[13]) ZG_QR(x[3], x[4], x[9], x[14])
+  }
+  for (int i = 0; i < 16; i++) {
+    const uint32_t v = x[i] + in[i];
+    memcpy(out + 4 * i, &v, 4);            // little-endian hosts only (x86-64 / aarch64)
+  }
+}
+#undef ZG_QR
+void zg_chacha20_seed(zg_chacha20* r, const uint8_t key[32]) {
+  memset(r, 0, sizeof(*r));
+  memcpy(r->key, key, 32);
+}
+int zg_chacha20_seed_os(zg_chacha20* r) {
+  uint8_t key[32];
+  size_t got = 0;
+  while (got < sizeof(key)) {
+    ssize_t k = getrandom(key + got, sizeof(key) - got, 0);
+    if (k < 0) {
+      if (errno == EINTR) continue;
+      return ZG_E_STATE;
+    }
+    got += (size_t)k;
+  }
+  zg_chacha20_seed(r, key);
+  memset(key, 0, sizeof(key));
+  return ZG_OK;
+}
+void zg_chacha20_fill(void* state, uint64_t* out, size_t n) {
+  zg_chacha20* r = (zg_chacha20*)state;
+  uint8_t* dst = (uint8_t*)out;
+  size_t left = n * 8;
+  while (left) {
+    if (!r->have) {
+      if (left >= 64) {                    // whole blocks go straight to the destination
+        chacha20_block(r, r->counter++, dst);
+        dst += 64; left -= 64;
+        continue;
+      }
+      chacha20_block(r, r->counter++, r->buf);
+      r->have = 64;
+    }
+    const size_t take = left < r->have ? left : r->have;
+    memcpy(dst, r->buf + (64 - r->have), take);
+    r->have -= (uint32_t)take; dst += take; left -= take;
+  }
+}
+
 void zg_pk_free(zg_ctx* ctx, zg_pk* pk) {
   if (!pk) return;
   cudaStreamSynchronize(ctx->stream);
-  if (pk->arena) cudaFree(pk->arena);
-  if (pk->rnd_words_host) cudaFreeHost(pk->rnd_words_host);
   delete pk;
 }
 
@@ -489,7 +598,7 @@ int zg_pk_load(zg_ctx* ctx, const zg_pk_desc* d, zg_pk** out) {
     pk->scratch = b.take<Fr>(8 * 4096 + std::max<size_t>(64, (n + 4095) / 4096) * (size_t)n_queries);
     pk->evals_dev = b.take<Fr>(n_queries + 8); pk->points_dev = b.take<Fr>(16); pk->coeff_dev = b.take<Fr>(n_queries + 8);
     pk->one_dev = b.take<Fr>(8);
-    pk->d_polyptrs = b.take<const Fr*>(n_queries + 8); pk->d_pidx = b.take<uint32_t>(n_queries + 8);
+    pk->d_polyptrs = b.take<const Fr*>(std::max<size_t>(n_queries + 8, 2 * (size_t)m + 8)); pk->d_pidx = b.take<uint32_t>(n_queries + 8);
     pk->d_status = b.take<uint32_t>(64);
     pk->lookup_ws_stride = (lookup_workspace_bytes(pk->usable) + 255) & ~(size_t)255;
     pk->lookup_ws = b.take<uint8_t>(pk->lookup_ws_stride * zg_ctx::N_SIDE);
@@ -655,6 +764,14 @@ static int create_proof_impl(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice,
                              const size_t* instance_lens, zg_rng_fill_fn rng, void* rng_state, uint8_t* proof_out, size_t proof_cap,
                              size_t* proof_len) {
   if (!pk || !advice || !rng || !proof_out || !proof_len) return ctx->fail(ZG_E_INVALID, "create_proof: null argument");
+  // the context's SRS may have been replaced since zg_pk_load: the key is only valid on the bases it was built on
+  if (!ctx->srs_loaded || ctx->srs_k != pk->k || !ctx->table[0].pts || !ctx->table[1].pts)
+    return ctx->fail(ZG_E_STATE, "create_proof: the context's SRS does not match the proving key (k or a basis missing)");
+  if (pk->I && (!instances || !instance_lens)) return ctx->fail(ZG_E_INVALID, "create_proof: instance columns missing");
+  for (uint32_t c = 0; c < pk->A; c++)
+    if (!advice[c]) return ctx->fail(ZG_E_INVALID, "create_proof: null advice column");
+  for (uint32_t c = 0; c < pk->I; c++)
+    if (instance_lens[c] && !instances[c]) return ctx->fail(ZG_E_INVALID, "create_proof: null instance column");
   const size_t n = pk->n, N = pk->N;
   const uint32_t A = pk->A, I = pk->I, Lk = pk->n_lookups, S = pk->nsets, bf = pk->bf, usable = pk->usable, m = pk->m;
   cudaStream_t st = ctx->stream;
@@ -741,7 +858,7 @@ static int create_proof_impl(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice,
     // sort) and cached.  The others are sorted per proof on their top 48 bits; the device flags the rare
     // case where that left distinct keys out of order and the round is redone with the full sort.
     const size_t draw_mark = draw;
-    std::vector<char> full(Lk, 0);
+    std::vector<char> full(Lk, 0), sorted_now(Lk, 0);
     std::vector<Affine> aff(2 * Lk);
     for (int attempt = 0;; attempt++) {
       draw = draw_mark;
@@ -755,12 +872,12 @@ static int create_proof_impl(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice,
         uint8_t* ws = pk->lookup_ws + (size_t)sidx * pk->lookup_ws_stride;
         if (l < (uint32_t)zg_ctx::N_SIDE) ZG_CUDA(cudaStreamWaitEvent(ss, ctx->ev_fork, 0));
         LookupTable tab;
-        if (pk->tab_count[l] == 1) {
+        if (pk->table_cacheable[l]) {
           tab = lookup_table_carve(pk->table_cache + (size_t)l * pk->table_cache_stride, usable);
           if (!pk->table_cached[l]) {
             if (lookup_sort_table(pk->ct + l * n, usable, tab, ws, pk->d_status + 2 * l, true, ss, lc))
               return ctx->cuda_fail(cudaGetLastError(), "lookup_sort_table");
-            pk->table_cached[l] = 1;
+            sorted_now[l] = 1;             // marked cached only once this round has completed without error
           }
         } else {
           tab = lookup_workspace_table(ws, usable);
@@ -798,7 +915,7 @@ static int create_proof_impl(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice,
       ZG_CUDA(cudaStreamSynchronize(st));
       bool retry = false;
       for (uint32_t l = 0; l < Lk; l++) {
-        if (status[2 * l] && !full[l] && pk->tab_count[l] != 1) { full[l] = 1; retry = true; }
+        if (status[2 * l] && !full[l] && !pk->table_cacheable[l]) { full[l] = 1; retry = true; }
       }
       if (retry && attempt == 0) {
         ZG_CUDA(join_aux(ctx));   // the transforms of the failed attempt still read pa / ps
@@ -806,6 +923,8 @@ static int create_proof_impl(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice,
       }
       for (uint32_t l = 0; l < Lk; l++)
         if (status[2 * l + 1]) return ctx->fail(ZG_E_SYNTH, "create_proof: lookup input not in table (ConstraintSystemFailure)");
+      for (uint32_t l = 0; l < Lk; l++)
+        if (sorted_now[l]) pk->table_cached[l] = 1;
       batch_normalize(jac.data(), 2 * Lk, aff.data());
       break;
     }

@@ -19,6 +19,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libzg_b200.so")
 
 ZG_OK = 0
+ZG_E_VERIFY = -6
 BASIS_MONOMIAL = 0
 BASIS_LAGRANGE = 1
 
@@ -29,9 +30,10 @@ EXPORTS = [
     "zg_ntt", "zg_ntt_dev", "zg_lagrange_to_coeff", "zg_lagrange_to_coeff_dev",
     "zg_coeff_to_extended", "zg_coeff_to_extended_dev", "zg_extended_to_coeff", "zg_extended_to_coeff_dev",
     "zg_bench_int_pipe", "zg_debug_field_op", "zg_debug_keccak256", "zg_probe_enable", "zg_probe_read",
-    "zg_xorshift_seed", "zg_xorshift_fill", "zg_pk_load", "zg_pk_free", "zg_pk_commitments", "zg_create_proof",
+    "zg_xorshift_seed", "zg_xorshift_fill", "zg_chacha20_seed_os", "zg_chacha20_seed", "zg_chacha20_fill", "zg_pk_load", "zg_pk_free", "zg_pk_commitments", "zg_create_proof",
     "zg_pk_last_stage_ms", "zg_pk_set_transcript_repr",
     "zg_wnn_create", "zg_wnn_free", "zg_wnn_last_error", "zg_wnn_synthesize",
+    "zg_vk_create", "zg_vk_free", "zg_vk_last_error", "zg_verify_proof", "zg_pairing_check",
     "zg_lookup_permute", "zg_grand_product", "zg_batch_invert", "zg_eval_poly_batch", "zg_kate_division", "zg_evaluate_h",
 ]
 
@@ -91,6 +93,11 @@ def load_library() -> ctypes.CDLL:
     L.zg_xorshift_seed.restype = None
     L.zg_xorshift_fill.argtypes = [vp, vp, sz]
     L.zg_xorshift_fill.restype = None
+    L.zg_chacha20_seed_os.argtypes = [vp]
+    L.zg_chacha20_seed.argtypes = [vp, vp]
+    L.zg_chacha20_seed.restype = None
+    L.zg_chacha20_fill.argtypes = [vp, vp, sz]
+    L.zg_chacha20_fill.restype = None
     L.zg_pk_load.argtypes = [vp, vp, ctypes.POINTER(vp)]
     L.zg_pk_free.argtypes = [vp, vp]
     L.zg_pk_free.restype = None
@@ -104,6 +111,13 @@ def load_library() -> ctypes.CDLL:
     L.zg_wnn_last_error.argtypes = [vp]
     L.zg_wnn_last_error.restype = ctypes.c_char_p
     L.zg_wnn_synthesize.argtypes = [vp, vp, u32, u32, vp, vp]
+    L.zg_vk_create.argtypes = [u32, vp, sz, vp, sz, vp, vp, vp, ctypes.POINTER(vp)]
+    L.zg_vk_free.argtypes = [vp]
+    L.zg_vk_free.restype = None
+    L.zg_vk_last_error.argtypes = [vp]
+    L.zg_vk_last_error.restype = ctypes.c_char_p
+    L.zg_verify_proof.argtypes = [vp, vp, vp, vp, vp, vp, vp, sz]
+    L.zg_pairing_check.argtypes = [vp, vp, sz, ctypes.POINTER(ci)]
     L.zg_lookup_permute.argtypes = [vp, vp, vp, sz, vp, vp]
     L.zg_grand_product.argtypes = [vp, vp, vp, sz, vp]
     L.zg_batch_invert.argtypes = [vp, vp, sz]
@@ -323,6 +337,36 @@ class XorShift(ctypes.Structure):
         r = cls()
         load_library().zg_xorshift_seed(ctypes.byref(r), seed)
         return r
+
+
+XorShift.fill_name = "zg_xorshift_fill"
+
+
+class ChaCha20Rng(ctypes.Structure):
+    """zg_chacha20: the production RNG (ChaCha20 keystream keyed from the OS entropy source, the role OsRng plays at
+    src/wnn.rs:256).  `from_os()` for proofs, `from_key(32 bytes)` for known-answer tests."""
+    _fields_ = [("key", ctypes.c_uint32 * 8), ("counter", ctypes.c_uint64), ("nonce", ctypes.c_uint32 * 2),
+                ("have", ctypes.c_uint32), ("buf", ctypes.c_uint8 * 64)]
+    fill_name = "zg_chacha20_fill"
+
+    @classmethod
+    def from_os(cls):
+        r = cls()
+        if load_library().zg_chacha20_seed_os(ctypes.byref(r)) != ZG_OK:
+            raise ZgError(-1, "the operating system returned no entropy (getrandom)")
+        return r
+
+    @classmethod
+    def from_key(cls, key: bytes):
+        assert len(key) == 32
+        r = cls()
+        load_library().zg_chacha20_seed(ctypes.byref(r), key)
+        return r
+
+    def draw(self, n: int) -> np.ndarray:
+        out = np.zeros(n, dtype=np.uint64)
+        load_library().zg_chacha20_fill(ctypes.byref(self), out.ctypes.data, n)
+        return out
 
 
 class WnnDesc(ctypes.Structure):

@@ -36,11 +36,16 @@ class ParamsKZG:
     """ParamsKZG<Bn256>: g = [s^i]G, g_lagrange = [L_i(s)]G as (n,8) uint64 affine limbs.  The SRS is
     an input (ParamsKZG::new / read in the reference, src/main.rs:232, src/io.rs:139-146)."""
 
-    def __init__(self, k: int, g: np.ndarray, g_lagrange: np.ndarray):
+    def __init__(self, k: int, g: np.ndarray, g_lagrange: np.ndarray, g2=None, s_g2=None):
         self.k, self.n = k, 1 << k
         self.g = np.ascontiguousarray(g, dtype=np.uint64)
         self.g_lagrange = np.ascontiguousarray(g_lagrange, dtype=np.uint64)
         assert self.g.shape == (self.n, 8) and self.g_lagrange.shape == (self.n, 8)
+        # ParamsKZG::{g2, s_g2} (G2Affine, 16 uint64 Montgomery limbs x.c0 | x.c1 | y.c0 | y.c1): only the verifier needs them
+        self.g2 = None if g2 is None else np.ascontiguousarray(np.frombuffer(g2, dtype=np.uint64) if isinstance(g2, bytes) else g2,
+                                                               dtype=np.uint64).reshape(16)
+        self.s_g2 = None if s_g2 is None else np.ascontiguousarray(
+            np.frombuffer(s_g2, dtype=np.uint64) if isinstance(s_g2, bytes) else s_g2, dtype=np.uint64).reshape(16)
         self._loaded_on = None
 
     def load(self, ctx: zl.Context):
@@ -62,16 +67,85 @@ def vk_transcript_repr(k, cs, fixed_commitments, perm_commitments) -> int:
     return int.from_bytes(h.digest(), "little") % R_MOD
 
 
+class VerifyingKey:
+    """VerifyingKey<G1Affine>: constraint system + fixed / permutation commitments + transcript_repr, and the host-side
+    verifier bound to them (zg_vk, csrc/verifier.cu).  Needs no GPU and no context."""
+
+    def __init__(self, k, cs_words, constants, fixed_limbs, perm_limbs, transcript_repr: int):
+        self.k, self.transcript_repr = k, transcript_repr
+        self.cs_words = np.ascontiguousarray(cs_words, dtype=np.uint32)
+        self.constants = np.ascontiguousarray(constants, dtype=np.uint64).reshape(-1, 4)
+        self.fixed_limbs = np.ascontiguousarray(fixed_limbs, dtype=np.uint64).reshape(-1, 8)
+        self.perm_limbs = np.ascontiguousarray(perm_limbs, dtype=np.uint64).reshape(-1, 8)
+        self._L = zl.load_library()
+        rl = np.ascontiguousarray(to_limbs([transcript_repr])[0], dtype=np.uint64)
+        h = ctypes.c_void_p()
+        rc = self._L.zg_vk_create(k, self.cs_words.ctypes.data, self.cs_words.shape[0], self.constants.ctypes.data,
+                                  self.constants.shape[0], self.fixed_limbs.ctypes.data, self.perm_limbs.ctypes.data,
+                                  rl.ctypes.data, ctypes.byref(h))
+        if rc != zl.ZG_OK:
+            raise zl.ZgError(rc, "zg_vk_create: malformed verifying key")
+        self._h = h
+
+    def verify(self, params: "ParamsKZG", instances, proof: bytes) -> bool:
+        """verify_proof(params, vk, SingleStrategy, &[&[instances]], transcript).is_ok()"""
+        if params.g2 is None or params.s_g2 is None:
+            raise ValueError("ParamsKZG without g2 / s_g2 cannot verify")
+        inst = [np.ascontiguousarray(to_limbs([int(x) for x in v]), dtype=np.uint64).reshape(-1, 4) for v in instances]
+        iptr = (ctypes.c_void_p * max(len(inst), 1))(*[a.ctypes.data for a in inst])
+        ilen = (ctypes.c_size_t * max(len(inst), 1))(*[a.shape[0] for a in inst])
+        buf = (ctypes.c_uint8 * max(len(proof), 1)).from_buffer_copy(proof or b"\0")
+        g0 = np.ascontiguousarray(params.g[0], dtype=np.uint64)
+        rc = self._L.zg_verify_proof(self._h, g0.ctypes.data, params.g2.ctypes.data, params.s_g2.ctypes.data, iptr, ilen,
+                                     buf, len(proof))
+        if rc == zl.ZG_OK:
+            return True
+        if rc == zl.ZG_E_VERIFY:
+            return False
+        raise zl.ZgError(rc, self._L.zg_vk_last_error(self._h).decode())
+
+    def last_error(self) -> str:
+        return self._L.zg_vk_last_error(self._h).decode()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.zg_vk_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def pairing_check(g1_points, g2_points) -> bool:
+    """prod e(P_i, Q_i) == 1 on the host (zg_pairing_check): (m,8) and (m,16) uint64 limb arrays"""
+    P = np.ascontiguousarray(g1_points, dtype=np.uint64).reshape(-1, 8)
+    Q = np.ascontiguousarray(g2_points, dtype=np.uint64).reshape(-1, 16)
+    assert P.shape[0] == Q.shape[0]
+    out = ctypes.c_int()
+    rc = zl.load_library().zg_pairing_check(P.ctypes.data, Q.ctypes.data, P.shape[0], ctypes.byref(out))
+    if rc != zl.ZG_OK:
+        raise zl.ZgError(rc, "zg_pairing_check: a point is not on its curve")
+    return bool(out.value)
+
+
 class ProvingKey:
     """ProvingKey<G1Affine> resident on one GPU (zg_pk handle) + the VerifyingKey data."""
 
-    def __init__(self, ctx, handle, k, cs, fixed_commitments, perm_commitments, transcript_repr):
+    def __init__(self, ctx, handle, k, cs, fixed_commitments, perm_commitments, transcript_repr, vk_parts=None):
         self.ctx, self._h, self.k, self.cs = ctx, handle, k, cs
         self.fixed_commitments, self.perm_commitments = fixed_commitments, perm_commitments
         self.transcript_repr = transcript_repr
+        self._vk_parts, self._vk = vk_parts, None
 
-    def get_vk(self):
-        return self
+    def get_vk(self) -> VerifyingKey:
+        """ProvingKey::get_vk (src/wnn.rs:271)"""
+        if self._vk is None:
+            words, constants, fc, pc = self._vk_parts
+            self._vk = VerifyingKey(self.k, words, constants, fc, pc, self.transcript_repr)
+        return self._vk
 
     def stage_ms(self):
         out = (ctypes.c_float * 8)()
@@ -124,7 +198,8 @@ def keygen(ctx: zl.Context, params: ParamsKZG, cs, asm, transcript_repr: int | N
         transcript_repr = vk_transcript_repr(params.k, cs, fixed_c, perm_c)
     repr_limbs = np.ascontiguousarray(to_limbs([transcript_repr])[0], dtype=np.uint64)
     ctx._ck(ctx._L.zg_pk_set_transcript_repr(ctx._h, h, repr_limbs.ctypes.data))
-    return ProvingKey(ctx, h, params.k, cs, fixed_c, perm_c, transcript_repr)
+    return ProvingKey(ctx, h, params.k, cs, fixed_c, perm_c, transcript_repr,
+                      vk_parts=(words, constants, fc[:cs.num_fixed].copy(), pc[:len(asm.perm_cols)].copy()))
 
 
 def advice_to_mont(ctx: zl.Context, advice_int) -> list:
@@ -132,8 +207,13 @@ def advice_to_mont(ctx: zl.Context, advice_int) -> list:
     return [ctx.debug_field_op(0, 7, ints_to_canonical(c)) for c in advice_int]
 
 
-def create_proof_limbs(pk: ProvingKey, advice_mont, instance_mont, rng: zl.XorShift) -> bytes:
-    """zg_create_proof on already-marshalled buffers (what bench.py times)."""
+def create_proof_limbs(pk: ProvingKey, advice_mont, instance_mont, rng=None) -> bytes:
+    """zg_create_proof on already-marshalled buffers (what bench.py times).  `rng` is any ctypes object whose class names
+    its bulk-draw callback in `fill_name` (lib.ChaCha20Rng, lib.XorShift) or a (zg_rng_fill_fn pointer, state) pair;
+    None = a fresh OS-seeded ChaCha20 stream per proof, the counterpart of the reference's OsRng (src/wnn.rs:256).
+    XorShift is for seeded, reproducible tests and benches only."""
+    if rng is None:
+        rng = zl.ChaCha20Rng.from_os()
     ctx = pk.ctx
     aptr = (ctypes.c_void_p * len(advice_mont))(*[a.ctypes.data for a in advice_mont])
     iptr = (ctypes.c_void_p * max(len(instance_mont), 1))(*[a.ctypes.data for a in instance_mont])
@@ -141,12 +221,15 @@ def create_proof_limbs(pk: ProvingKey, advice_mont, instance_mont, rng: zl.XorSh
     cap = 1 << 16
     buf = (ctypes.c_uint8 * cap)()
     plen = ctypes.c_size_t()
-    fill = ctypes.cast(ctx._L.zg_xorshift_fill, ctypes.c_void_p)
-    ctx._ck(ctx._L.zg_create_proof(ctx._h, pk._h, aptr, iptr, ilen, fill, ctypes.byref(rng), buf, cap, ctypes.byref(plen)))
+    if isinstance(rng, tuple):
+        fill, state = ctypes.cast(rng[0], ctypes.c_void_p), rng[1]
+    else:
+        fill, state = ctypes.cast(getattr(ctx._L, rng.fill_name), ctypes.c_void_p), ctypes.byref(rng)
+    ctx._ck(ctx._L.zg_create_proof(ctx._h, pk._h, aptr, iptr, ilen, fill, state, buf, cap, ctypes.byref(plen)))
     return bytes(buf[:plen.value])
 
 
-def create_proof(params: ParamsKZG, pk: ProvingKey, advice_int, instances, rng: zl.XorShift) -> bytes:
+def create_proof(params: ParamsKZG, pk: ProvingKey, advice_int, instances, rng=None) -> bytes:
     """create_proof(params, pk, &[circuit], &[&[instances]], rng, transcript) -> proof bytes."""
     ctx = pk.ctx
     params.load(ctx)

@@ -43,11 +43,12 @@ class _Lane:
 class ProofService:
     """`lanes` independent provers for one model on one GPU.
 
-    rng_factory(job_index) -> zl.XorShift (or any object zg_create_proof's RNG callback accepts through
-    `create_proof_limbs`); the default draws a fresh OS-random seed per proof, as the reference's OsRng does."""
+    rng_factory(job_index) -> an RNG `create_proof_limbs` accepts; the default is a fresh ChaCha20 stream keyed from the
+    operating system per proof (lib.ChaCha20Rng.from_os), the counterpart of the reference's OsRng.  Seeded XorShift
+    streams are for reproducible tests only."""
 
     def __init__(self, wnn, params: ParamsKZG, device: int = 0, lanes: int = 4,
-                 rng_factory: Optional[Callable[[int], zl.XorShift]] = None, streams: Optional[Sequence[int]] = None):
+                 rng_factory: Optional[Callable[[int], object]] = None, streams: Optional[Sequence[int]] = None):
         assert lanes >= 1
         self.wnn, self.params, self.device = wnn, params, device
         self.synth = wnn.native_synthesizer()
@@ -60,9 +61,8 @@ class ProofService:
             self.lanes.append(_Lane(self, i, ctx))
 
     @staticmethod
-    def _os_rng(_job: int) -> zl.XorShift:
-        import os
-        return zl.XorShift.from_seed(os.urandom(16))
+    def _os_rng(_job: int) -> zl.ChaCha20Rng:
+        return zl.ChaCha20Rng.from_os()
 
     @property
     def vk(self):

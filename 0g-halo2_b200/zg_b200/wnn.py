@@ -1,7 +1,8 @@
 """`Wnn`: host-side mirror of /root/reference/src/wnn.rs (same method names and argument meaning).
 
-predict / get_circuit_params / get_circuit / mock_proof are host logic; generate_proving_key /
-proof / verify_proof drive the B200 backend through the C ABI (zg_b200.lib) and have no CPU path."""
+predict / get_circuit_params / get_circuit / mock_proof are host logic; generate_proving_key / proof drive the B200
+backend through the C ABI (zg_b200.lib) and have no CPU path; verify_proof is host code in the same library
+(verification is host work in the reference too)."""
 from __future__ import annotations
 
 import numpy as np
@@ -98,9 +99,10 @@ class Wnn:
             self._native = NativeSynthesizer(self)
         return self._native
 
-    def proof(self, pk, params, image, rng, native: bool = True):
+    def proof(self, pk, params, image, rng=None, native: bool = True):
         """create_proof::<KZG<Bn256>, ProverGWC, _, _, EvmTranscript, _>; returns (proof bytes, outputs).
-        `native` selects the C++ witness synthesis (default) or the Python front-end; both give the same columns."""
+        `native` selects the C++ witness synthesis (default) or the Python front-end; both give the same columns.
+        `rng` = None draws from an OS-seeded ChaCha20 stream like the reference's OsRng (src/wnn.rs:256)."""
         from .prover import create_proof, create_proof_limbs
         if native:
             from .bn254_host import to_limbs
@@ -111,3 +113,10 @@ class Wnn:
         outputs = self.predict(image)
         _, asm = self.synthesize(image, pk.k)
         return create_proof(params, pk, asm.advice, [outputs], rng), outputs
+
+    def verify_proof(self, proof: bytes, pk, params, outputs) -> bool:
+        """src/wnn.rs:265-280: verify_proof::<KZG<Bn256>, VerifierGWC, _, EvmTranscript, SingleStrategy> against the
+        claimed class scores.  Host code (csrc/verifier.cu: transcript, expression evaluation, one small MSM, two
+        pairings); `pk` may be a ProvingKey or a VerifyingKey."""
+        vk = pk.get_vk() if hasattr(pk, "get_vk") else pk
+        return vk.verify(params, [list(outputs)], proof)

@@ -38,6 +38,9 @@ typedef struct { uint64_t l[4]; } zg_fr;
 typedef struct { uint64_t l[4]; } zg_fq;
 typedef struct { zg_fq x, y; } zg_g1_affine;
 typedef struct { zg_fq x, y, z; } zg_g1;
+/* G2Affine on the twist y^2 = x^3 + 3/(9+u) over Fq2 = Fq[u]/(u^2+1): x = x_c0 + x_c1 u, y likewise (the in-memory
+ * layout of halo2curves' bn256::G2Affine); identity = all zero */
+typedef struct { zg_fq x_c0, x_c1, y_c0, y_c1; } zg_g2_affine;
 
 enum {
   ZG_OK = 0,
@@ -46,6 +49,7 @@ enum {
   ZG_E_STATE = -3,    /* required object (SRS, pk) not loaded */
   ZG_E_NOMEM = -4,
   ZG_E_SYNTH = -5,    /* prover-level failure, e.g. lookup input not in table (plonk::Error) */
+  ZG_E_VERIFY = -6,   /* zg_verify_proof: the proof was rejected (plonk::Error::ConstraintSystemFailure / Opening) */
 };
 
 enum { ZG_BASIS_MONOMIAL = 0, ZG_BASIS_LAGRANGE = 1 };
@@ -117,6 +121,14 @@ typedef void (*zg_rng_fill_fn)(void* state, uint64_t* out, size_t n);
 typedef struct { uint32_t x, y, z, w; } zg_xorshift;
 void zg_xorshift_seed(zg_xorshift* rng, const uint8_t seed[16]);
 void zg_xorshift_fill(void* state /* zg_xorshift* */, uint64_t* out, size_t n);
+/* The production RNG: ChaCha20 keystream (RFC 8439 block function, 64-bit block counter) keyed from the operating
+ * system's entropy source -- what rand::rngs::OsRng gives the reference at /root/reference/src/wnn.rs:256 (every
+ * blinding row, the random polynomial and the h blinds of a proof come from it).  zg_chacha20_seed_os draws a fresh
+ * 256-bit key with getrandom(2); zg_chacha20_seed takes a caller-supplied key (known-answer tests). */
+typedef struct { uint32_t key[8]; uint64_t counter; uint32_t nonce[2]; uint32_t have; uint8_t buf[64]; } zg_chacha20;
+int  zg_chacha20_seed_os(zg_chacha20* rng);                       /* ZG_OK, or ZG_E_STATE when the OS gives no entropy */
+void zg_chacha20_seed(zg_chacha20* rng, const uint8_t key[32]);
+void zg_chacha20_fill(void* state /* zg_chacha20* */, uint64_t* out, size_t n);
 
 typedef struct {
   uint32_t k;
@@ -179,6 +191,25 @@ int zg_evaluate_h(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice_polys, cons
                   const zg_fr* const* lookup_input_polys, const zg_fr* const* lookup_table_polys,
                   const zg_fr* const* lookup_product_polys, const zg_fr* const* perm_product_polys,
                   const zg_fr challenges[4], int divide, zg_fr* h_out);
+
+/* ---- verifier (host code, no GPU) ------------------------------------------------------------------------------
+ * plonk::verify_proof::<KZGCommitmentScheme<Bn256>, VerifierGWC, _, EvmTranscript, SingleStrategy> as called by
+ * `Wnn::verify_proof` (/root/reference/src/wnn.rs:265-280; `bench_verification`, benches/bench.rs:38-45).  Verification
+ * is host work in the reference too; it needs no context and no device.  A zg_vk holds the VerifyingKey data: the
+ * constraint system (same blob as zg_pk_desc), the fixed / permutation commitments and transcript_repr.
+ * zg_verify_proof returns ZG_OK when the proof is accepted, ZG_E_VERIFY when it is rejected (malformed encoding, a
+ * point off the curve, a failed identity or pairing check), ZG_E_INVALID for bad arguments.  `g1_generator` is
+ * ParamsKZG::get_g()[0]; `g2`, `s_g2` are ParamsKZG::g2() and ::s_g2().  Instances as for zg_create_proof.
+ * zg_pairing_check: is prod_i e(p_i, q_i) the identity of GT (the check behind DualMSM::check)? */
+typedef struct zg_vk zg_vk;
+int zg_vk_create(uint32_t k, const uint32_t* cs_words, size_t cs_nwords, const zg_fr* constants, size_t n_constants,
+                 const zg_g1_affine* fixed_commitments, const zg_g1_affine* permutation_commitments,
+                 const zg_fr* transcript_repr, zg_vk** out);
+void zg_vk_free(zg_vk* vk);
+const char* zg_vk_last_error(const zg_vk* vk);
+int zg_verify_proof(zg_vk* vk, const zg_g1_affine* g1_generator, const zg_g2_affine* g2, const zg_g2_affine* s_g2,
+                    const zg_fr* const* instances, const size_t* instance_lens, const uint8_t* proof, size_t proof_len);
+int zg_pairing_check(const zg_g1_affine* p, const zg_g2_affine* q, size_t n, int* is_one);
 
 /* ---- native witness synthesis of the WNN circuit (host code, no GPU) ----------------------------------------
  * The assignment half of `WnnCircuit::synthesize` -> `WnnChip::predict` (/root/reference/src/gadgets/wnn.rs:180-237,

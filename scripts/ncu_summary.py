@@ -23,8 +23,11 @@ WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
 
 
 def main(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(out.splitlines()))
+    if rep.endswith(".csv"):                 # already exported on the GPU box (ncu -i x.ncu-rep --page raw --csv > x.csv)
+        out = open(rep).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(l for l in out.splitlines() if l.startswith('"')))
     hdr, units, data = rows[0], rows[1], rows[2:]
     idx = {h: i for i, h in enumerate(hdr)}
     for d in data:
@@ -32,6 +35,16 @@ def main(rep):
         for w in WANT:
             if w in idx:
                 print("  %-82s %s %s" % (w, d[idx[w]], units[idx[w]]))
+        # every per-pipe counter the capture holds (names differ between ncu versions: fmaheavy / fma_heavy / imad ...)
+        for h in hdr:
+            if h in WANT:
+                continue
+            hl = h.lower()
+            if ("pipe_" in hl and ("fma" in hl or "alu" in hl or "imad" in hl or "xu" in hl or "lsu" in hl or "uniform" in hl)) or \
+               hl.startswith("launch__occupancy") or hl.startswith("launch__waves") or "registers" in hl or "shared_mem" in hl or \
+               hl.startswith("smsp__average_warps_issue_stalled") or hl.startswith("smsp__warps_eligible") or \
+               hl.startswith("sm__warps_active") or hl.startswith("lts__t_bytes") or hl.startswith("l1tex__data_bank_conflicts"):
+                print("  %-82s %s %s" % (h, d[idx[h]], units[idx[h]]))
         print()
 
 
