@@ -55,15 +55,14 @@ int get_domain(zg_ctx* ctx, uint32_t logn, const Fr& omega, Domain** out) {
   Domain d;
   size_t n = (size_t)1 << logn;
   ZG_CUDA(cudaMalloc(&d.tw, sizeof(Fr) * n));
-  Fr* flat = nullptr;
-  cudaError_t e = cudaMalloc(&flat, sizeof(Fr) * (n / 2 + 1));
+  cudaError_t e = cudaMalloc(&d.flat, sizeof(Fr) * (n / 2 + 1));
   if (e == cudaSuccess) {
-    e = ntt_build_twiddles(d.tw, flat, omega, logn, ctx->stream);
+    e = ntt_build_twiddles(d.tw, d.flat, omega, logn, ctx->stream);
     ctx->launches += 2;
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   }
-  if (flat) cudaFree(flat);
-  if (e != cudaSuccess) {                 // nothing stays allocated when the table could not be built
+  if (e != cudaSuccess) {                 // nothing stays allocated when the tables could not be built
+    if (d.flat) cudaFree(d.flat);
     cudaFree(d.tw);
     return ctx->cuda_fail(e, "ntt_build_twiddles");
   }
@@ -102,6 +101,7 @@ static int ntt_generic_dev(zg_ctx* ctx, const Fr* in, size_t in_stride, Fr* out,
     P.tmp = (Fr*)ctx->ws_ntt.p;
   }
   P.tw = d->tw;
+  P.flat = d->flat;
   P.logn = logn;
   P.batch = (uint32_t)batch;
   P.n_in = n_in;
@@ -134,6 +134,14 @@ int msm_dev_mixed(zg_ctx* ctx, int basis, const Fr* scalars_dev, size_t stride, 
                           &ctx->launches, &ctx->probe, other_mask ? ctx->table[basis ^ 1].pts : nullptr, other_mask);
   if (e != cudaSuccess) return ctx->cuda_fail(e, "msm_run");
   return ZG_OK;
+}
+
+// coefficients (the first n_in of them; the rest read as zero) -> values on halo2's coset zeta * <omega_ext>
+int ntt_halo_coset_dev(zg_ctx* ctx, const Fr* coeff, uint32_t n_in, uint32_t ext_k, Fr* out) {
+  Fr zeta = host_fr_zeta();
+  Fr sc[3] = {fp_one<FrParams>(), zeta, fp_sqr(zeta)};
+  return ntt_generic_dev(ctx, coeff, n_in, out, (size_t)1 << ext_k, ext_k, host_omega(ext_k), 1, n_in, 1u << ext_k, NTT_IN_COSET,
+                         sc, nullptr);
 }
 
 }  // namespace zg
@@ -189,7 +197,7 @@ void zg_ctx_destroy(zg_ctx* ctx) {
     if (ctx->base[b]) cudaFree(ctx->base[b]);
     if (ctx->table[b].pts) cudaFree(ctx->table[b].pts);
   }
-  for (auto& kv : ctx->domains) cudaFree(kv.second.tw);
+  for (auto& kv : ctx->domains) { cudaFree(kv.second.tw); cudaFree(kv.second.flat); }
   if (ctx->ws_msm.p) cudaFree(ctx->ws_msm.p);
   if (ctx->ws_ntt.p) cudaFree(ctx->ws_ntt.p);
   if (ctx->ws_stage.p) cudaFree(ctx->ws_stage.p);

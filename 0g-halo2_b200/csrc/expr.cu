@@ -31,8 +31,9 @@ __device__ __forceinline__ void stf(Fr* p, const Fr& r) {
   q[1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
 }
 
-__device__ __forceinline__ uint32_t rot_idx(uint32_t idx, int32_t rot, uint32_t scale, uint32_t size) {
-  return (uint32_t)((int32_t)idx + rot * (int32_t)scale) & (size - 1);   // size is a power of two
+// row `idx` rotated by `rot` rows of the 2^k domain: a shift by rot * scale inside its block of mask + 1 rows
+__device__ __forceinline__ uint32_t rot_idx(uint32_t idx, int32_t rot, uint32_t scale, uint32_t mask) {
+  return (idx & ~mask) | ((uint32_t)((int32_t)idx + rot * (int32_t)scale) & mask);
 }
 
 __device__ Fr eval_program(const ExprEnv& E, uint32_t begin, uint32_t end, uint32_t idx) {
@@ -50,7 +51,7 @@ __device__ Fr eval_program(const ExprEnv& E, uint32_t begin, uint32_t end, uint3
       case OP_INSTANCE: {
         const int kind = (int)op - (int)OP_ADVICE;
         const Fr* col = E.cols[kind][E.qcol[kind][arg]];
-        st[sp++] = ldf(col + rot_idx(idx, E.qrot[kind][arg], E.rot_scale, E.size));
+        st[sp++] = ldf(col + rot_idx(idx, E.qrot[kind][arg], E.rot_scale, E.wrap_mask));
         break;
       }
       case OP_NEG:
@@ -106,8 +107,8 @@ __global__ void __launch_bounds__(EX_THREADS) k_h_gates(ExprEnv E, const uint32_
 __global__ void __launch_bounds__(EX_THREADS) k_h_permutation(PermEnv P, Fr beta, Fr gamma, Fr y, Fr delta, Fr* h) {
   uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= P.size) return;
-  const uint32_t r_next = rot_idx(idx, 1, P.rot_scale, P.size);
-  const uint32_t r_last = rot_idx(idx, P.last_rot, P.rot_scale, P.size);
+  const uint32_t r_next = rot_idx(idx, 1, P.rot_scale, P.wrap_mask);
+  const uint32_t r_last = rot_idx(idx, P.last_rot, P.rot_scale, P.wrap_mask);
   const Fr one = fp_one<FrParams>();
   Fr acc = ldf(h + idx);
   const Fr l0 = ldf(P.l0 + idx), l_last = ldf(P.l_last + idx), l_active = ldf(P.l_active + idx);
@@ -145,8 +146,8 @@ __global__ void __launch_bounds__(EX_THREADS) k_h_lookup(ExprEnv E, LookupProgs 
                                                          Fr gamma, Fr y, Fr* h) {
   uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= E.size) return;
-  const uint32_t r_next = rot_idx(idx, 1, E.rot_scale, E.size);
-  const uint32_t r_prev = rot_idx(idx, -1, E.rot_scale, E.size);
+  const uint32_t r_next = rot_idx(idx, 1, E.rot_scale, E.wrap_mask);
+  const uint32_t r_prev = rot_idx(idx, -1, E.rot_scale, E.wrap_mask);
   const Fr one = fp_one<FrParams>();
   Fr ci = compress(E, lp.prog_off, lp.in_first[l], lp.in_count[l], theta, idx);
   Fr ct = compress(E, lp.prog_off, lp.tab_first[l], lp.tab_count[l], theta, idx);

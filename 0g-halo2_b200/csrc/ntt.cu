@@ -18,6 +18,7 @@
 //   * 254-bit Montgomery butterflies make this kernel integer-pipe bound (about 10 mulmods per
 //     element at 2^20 against 64 B of traffic per pass), see DESIGN.md.
 #include <atomic>
+#include <cstdlib>
 #include "ntt.cuh"
 
 namespace zg {
@@ -84,8 +85,9 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(NttPassArgs A) {
   SmTile sm{ntt_smem_raw, ntt_smem_raw + ((1u << A.S) << A.logc)};
   const uint32_t S = A.S, logc = A.logc, lo = A.lo, logn = A.logn;
   const uint32_t R = 1u << S, C = 1u << logc;
-  const Fr* in = A.in + (size_t)blockIdx.y * A.in_stride;
-  Fr* out = A.out + (size_t)blockIdx.y * A.out_stride;
+  const uint32_t poly = blockIdx.y / A.cosets, cz = blockIdx.y - poly * A.cosets;
+  const Fr* in = A.in + (size_t)poly * A.in_stride + (size_t)cz * A.in_coset_stride;
+  Fr* out = A.out + (size_t)poly * A.out_stride + (size_t)cz * A.out_coset_stride;
   const uint32_t tile = blockIdx.x;
   const uint32_t tid = threadIdx.x;
   const uint32_t total = R << logc;
@@ -102,7 +104,8 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(NttPassArgs A) {
       Fr v;
       if (idx < A.n_in) {
         v = ld_fr(in + idx);
-        if (A.flags & NTT_IN_COSET) {
+        if (A.in_table) v = fp_mul(v, ld_fr(A.in_table + (size_t)cz * A.in_table_stride + idx));
+        else if (A.flags & NTT_IN_COSET) {
           uint32_t m = idx % 3;
           if (m) v = fp_mul(v, A.in_scale[m]);
         }
@@ -120,7 +123,8 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(NttPassArgs A) {
       Fr v;
       if (idx < A.n_in) {
         v = ld_fr(in + idx);
-        if (A.flags & NTT_IN_COSET) {
+        if (A.in_table) v = fp_mul(v, ld_fr(A.in_table + (size_t)cz * A.in_table_stride + idx));
+        else if (A.flags & NTT_IN_COSET) {
           uint32_t m = idx % 3;
           if (m) v = fp_mul(v, A.in_scale[m]);
         }
@@ -184,7 +188,8 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(NttPassArgs A) {
       uint32_t pos = (jr << (logn - S)) | (rest_rev << logc) | cr;
       if (pos >= A.n_out) continue;
       Fr v = sm.get((c << S) | j);
-      if (A.flags & NTT_OUT_SCALE) v = fp_mul(v, A.out_scale[(A.flags & NTT_OUT_MOD3) ? pos % 3 : 0]);
+      if (A.out_table) v = fp_mul(v, ld_fr(A.out_table + (size_t)cz * A.out_table_stride + pos));
+      else if (A.flags & NTT_OUT_SCALE) v = fp_mul(v, A.out_scale[(A.flags & NTT_OUT_MOD3) ? pos % 3 : 0]);
       st_fr(out + pos, v);
     }
   }
@@ -204,12 +209,16 @@ cudaError_t ntt_build_twiddles(Fr* tab, Fr* scratch_flat, const Fr& w, uint32_t 
 // Passes are planned top-down; every strided pass keeps lo >= NTT_LOGC.
 cudaError_t ntt_run(const NttPlan& P, cudaStream_t stream, uint64_t* nl) {
   const uint32_t logn = P.logn;
+  {
+    static const bool force_stagewise = getenv("ZG_NTT_STAGEWISE") != nullptr;     // A/B switch for profiling
+    if (!force_stagewise && P.flat && ntt_fast_supported(logn)) return ntt_fast_run(P, stream, nl);
+  }
   uint32_t npass = (logn + NTT_MAX_S - 1) / NTT_MAX_S;
   if (npass == 0) npass = 1;
   // a lone small transform would run on a handful of CTAs: trade one more pass for a grid that covers the SMs
   while (npass < 4 && logn >= 5 * (npass + 1)) {
     uint32_t S0 = (logn + npass - 1) / npass;
-    uint64_t ctas = ((uint64_t)1 << (logn - S0 - (logn - S0 >= NTT_LOGC ? NTT_LOGC : logn - S0))) * P.batch;
+    uint64_t ctas = ((uint64_t)1 << (logn - S0 - (logn - S0 >= NTT_LOGC ? NTT_LOGC : logn - S0))) * P.batch * (P.cosets ? P.cosets : 1);
     if (ctas >= 148) break;
     npass++;
   }
@@ -237,14 +246,24 @@ cudaError_t ntt_run(const NttPlan& P, cudaStream_t stream, uint64_t* nl) {
     const bool first = (p == 0), last = (p == npass - 1);
     // buffer routing: first pass reads `in`; last pass writes `out`; between them `tmp`
     // (the last pass permutes across tiles, so it can never run in place unless it is alone).
+    const uint32_t cosets = P.cosets ? P.cosets : 1;
+    A.cosets = cosets;
+    A.in_table = first ? P.in_table : nullptr;
+    A.in_table_stride = P.in_table_stride;
+    A.out_table = nullptr;
+    A.out_table_stride = P.out_table_stride;
     A.in = first ? P.in : P.tmp;
-    A.in_stride = first ? P.in_stride : P.tmp_stride;
+    A.in_stride = first ? P.in_stride : P.tmp_stride * cosets;
+    A.in_coset_stride = first ? P.in_coset_stride : P.tmp_stride;
     if (last) {
       A.out = P.out;
       A.out_stride = P.out_stride;
+      A.out_coset_stride = P.out_coset_stride;
+      A.out_table = P.out_table;
     } else {
       A.out = P.tmp;
-      A.out_stride = P.tmp_stride;
+      A.out_stride = P.tmp_stride * cosets;
+      A.out_coset_stride = P.tmp_stride;
     }
     if (first) {
       A.n_in = P.n_in;
@@ -267,7 +286,7 @@ cudaError_t ntt_run(const NttPlan& P, cudaStream_t stream, uint64_t* nl) {
     }
     uint32_t tiles = 1u << (logn - S - A.logc);
     size_t smem = (sizeof(Fr) << S) << A.logc;
-    dim3 grid(tiles, P.batch);
+    dim3 grid(tiles, P.batch * cosets);
     ntt_pass_kernel<<<grid, NTT_THREADS, smem, stream>>>(A);
     if (nl) ++*nl;
     hi -= S;

@@ -12,6 +12,7 @@
 #include <sys/random.h>
 #include "ctx.cuh"
 #include "expr.cuh"
+#include "extdomain.cuh"
 #include "lookup.cuh"
 #include "poly.cuh"
 
@@ -21,6 +22,9 @@ extern "C" int zg_msm_dev(zg_ctx*, int, const zg_fr*, size_t, size_t, size_t, zg
 extern "C" int zg_lagrange_to_coeff_dev(zg_ctx*, const zg_fr*, zg_fr*, uint32_t, size_t, size_t);
 extern "C" int zg_coeff_to_extended_dev(zg_ctx*, const zg_fr*, size_t, uint32_t, uint32_t, zg_fr*, size_t, size_t);
 extern "C" int zg_extended_to_coeff_dev(zg_ctx*, const zg_fr*, uint32_t, uint32_t, size_t, zg_fr*);
+namespace zg {
+int ntt_halo_coset_dev(zg_ctx* ctx, const Fr* coeff, uint32_t n_in, uint32_t ext_k, Fr* out);
+}
 
 namespace {
 
@@ -171,8 +175,10 @@ struct Bump {
 }  // namespace
 
 struct zg_pk {
-  uint32_t k = 0, ext_k = 0, rot_scale = 0;
-  size_t n = 0, N = 0;
+  uint32_t k = 0, ext_k = 0, rot_scale = 0;   // ext_k: halo2's extended_k (only the C-ABI conversions of zg_evaluate_h use it)
+  size_t n = 0, N = 0;                        // N = ext.N rows of the internal extended domain
+  ExtDomain ext;
+  Fr* ext_mem = nullptr;
   uint32_t A = 0, F = 0, I = 0, degree = 0, bf = 0, usable = 0, qdeg = 0;
   std::vector<std::pair<uint32_t, int32_t>> q[3];
   std::vector<std::pair<uint32_t, uint32_t>> perm;  // (kind, index)
@@ -349,28 +355,27 @@ static ExprEnv make_env(const zg_pk* pk, bool ext) {
   e.ops = pk->ops;
   e.size = (uint32_t)(ext ? pk->N : pk->n);
   e.rot_scale = ext ? pk->rot_scale : 1;
+  e.wrap_mask = (uint32_t)(ext ? pk->ext.B - 1 : pk->n - 1);
   return e;
 }
 
 // extended-coset forms of the per-proof polynomials (coefficient form -> zeta * <omega_ext>), in the batches the prover
 // builds them: advice + instance, lookup permuted [a | s], product polynomials (permutation z, lookup z)
 static int coset_advice_instance(zg_ctx* ctx, zg_pk* pk) {
-  int rc = zg_coeff_to_extended_dev(ctx, (const zg_fr*)pk->adv_polys, pk->n, pk->k, pk->ext_k, (zg_fr*)pk->adv_cosets, pk->N, pk->A);
+  int rc = ext_from_coeff(ctx, pk->ext, pk->adv_polys, pk->n, pk->adv_cosets, pk->N, pk->A);
   if (rc || !pk->I) return rc;
-  return zg_coeff_to_extended_dev(ctx, (const zg_fr*)pk->inst_polys, pk->n, pk->k, pk->ext_k, (zg_fr*)pk->inst_cosets, pk->N, pk->I);
+  return ext_from_coeff(ctx, pk->ext, pk->inst_polys, pk->n, pk->inst_cosets, pk->N, pk->I);
 }
 static int coset_lookup_permuted(zg_ctx* ctx, zg_pk* pk) {
   if (!pk->n_lookups) return ZG_OK;
-  return zg_coeff_to_extended_dev(ctx, (const zg_fr*)pk->pa_poly, pk->n, pk->k, pk->ext_k, (zg_fr*)pk->lk_cosets, pk->N,
-                                  2 * pk->n_lookups);
+  return ext_from_coeff(ctx, pk->ext, pk->pa_poly, pk->n, pk->lk_cosets, pk->N, 2 * pk->n_lookups);
 }
 static int coset_products(zg_ctx* ctx, zg_pk* pk) {
   int rc = ZG_OK;
   if (pk->nsets)
-    rc = zg_coeff_to_extended_dev(ctx, (const zg_fr*)pk->pz_poly, pk->n, pk->k, pk->ext_k, (zg_fr*)pk->pz_coset, pk->N, pk->nsets);
+    rc = ext_from_coeff(ctx, pk->ext, pk->pz_poly, pk->n, pk->pz_coset, pk->N, pk->nsets);
   if (rc || !pk->n_lookups) return rc;
-  return zg_coeff_to_extended_dev(ctx, (const zg_fr*)pk->lz_poly, pk->n, pk->k, pk->ext_k,
-                                  (zg_fr*)(pk->lk_cosets + 2 * (size_t)pk->n_lookups * pk->N), pk->N, pk->n_lookups);
+  return ext_from_coeff(ctx, pk->ext, pk->lz_poly, pk->n, pk->lk_cosets + 2 * (size_t)pk->n_lookups * pk->N, pk->N, pk->n_lookups);
 }
 
 // Evaluator::evaluate_h: reads the coefficient forms in the pk workspace (adv_polys, inst_polys, pz_poly, pa_poly | ps_poly,
@@ -399,6 +404,7 @@ static int quotient_numerator(zg_ctx* ctx, zg_pk* pk, const Fr& theta, const Fr&
     pe.z_cosets = pk->d_z_cosets; pe.col_cosets = pk->d_perm_cosets; pe.sigma_cosets = pk->d_sigma_cosets;
     pe.l0 = pk->l0; pe.l_last = pk->l_last; pe.l_active = pk->l_active; pe.coset_x = pk->coset_x;
     pe.nsets = S; pe.m = m; pe.chunk = pk->chunk; pe.size = (uint32_t)N; pe.rot_scale = pk->rot_scale;
+    pe.wrap_mask = (uint32_t)(pk->ext.B - 1);
     pe.last_rot = -(int32_t)(bf + 1);
     expr_h_permutation(pe, beta, gamma, y, pk->delta, pk->h, st, lc);
   }
@@ -543,8 +549,10 @@ int zg_pk_load(zg_ctx* ctx, const zg_pk_desc* d, zg_pk** out) {
   pk->qdeg = pk->degree - 1;
   pk->ext_k = pk->k;
   while (((size_t)1 << pk->ext_k) < pk->n * pk->qdeg) pk->ext_k++;
-  pk->N = (size_t)1 << pk->ext_k;
-  pk->rot_scale = 1u << (pk->ext_k - pk->k);
+  if (pk->ext_k > 28) return ctx->fail(ZG_E_INVALID, "pk_load: extended domain exceeds the field's 2-adicity");
+  ext_domain_shape(pk->k, pk->qdeg, pk->ext);     // internal domain: 3 cosets of 2n for a degree-6 system (extdomain.cuh)
+  pk->N = pk->ext.N;
+  pk->rot_scale = pk->ext.rot_scale;
   pk->usable = (uint32_t)pk->n - (pk->bf + 1);
   pk->chunk = pk->degree - 2;
   pk->nsets = (pk->m + pk->chunk - 1) / pk->chunk;
@@ -569,7 +577,7 @@ int zg_pk_load(zg_ctx* ctx, const zg_pk_desc* d, zg_pk** out) {
     pk->fixed_values = b.take<Fr>(F * n); pk->fixed_polys = b.take<Fr>(F * n); pk->fixed_cosets = b.take<Fr>(F * N);
     pk->sigma_values = b.take<Fr>(m * n); pk->sigma_polys = b.take<Fr>(m * n); pk->sigma_cosets = b.take<Fr>(m * N);
     pk->l0 = b.take<Fr>(N); pk->l_last = b.take<Fr>(N); pk->l_active = b.take<Fr>(N); pk->coset_x = b.take<Fr>(N);
-    pk->t_inv = b.take<Fr>(pk->rot_scale); pk->constants = b.take<Fr>(d->n_constants + 1); pk->omega_pows = b.take<Fr>(n);
+    pk->t_inv = b.take<Fr>((size_t)1 << (pk->ext_k - pk->k)); pk->ext_mem = b.take<Fr>(ext_domain_table_elems(pk->ext)); pk->constants = b.take<Fr>(d->n_constants + 1); pk->omega_pows = b.take<Fr>(n);
     pk->ops = b.take<uint32_t>(ops.size() + 1); pk->prog_off = b.take<uint32_t>(prog_off.size());
     pk->d_in_first = b.take<uint32_t>(Lk + 1); pk->d_in_count = b.take<uint32_t>(Lk + 1);
     pk->d_tab_first = b.take<uint32_t>(Lk + 1); pk->d_tab_count = b.take<uint32_t>(Lk + 1);
@@ -593,7 +601,8 @@ int zg_pk_load(zg_ctx* ctx, const zg_pk_desc* d, zg_pk** out) {
     pk->pz_poly = b.take<Fr>((S + Lk) * n); pk->lz_poly = pk->pz_poly ? pk->pz_poly + (size_t)S * n : nullptr;
     pk->pz_coset = b.take<Fr>(S * N); pk->lk_cosets = b.take<Fr>(3 * (size_t)Lk * N);
     pk->frac = b.take<Fr>(n); pk->rnd = b.take<Fr>(pk->n_draws); pk->random_poly = pk->rnd;  // set per proof
-    pk->h = b.take<Fr>(N); pk->h_coeff = b.take<Fr>(N); pk->h_poly = b.take<Fr>(n);
+    const size_t hcap = std::max<size_t>(N, (size_t)(S + Lk + 1) * n);   // also scratch for the S + Lk fraction columns
+    pk->h = b.take<Fr>(hcap); pk->h_coeff = b.take<Fr>(hcap); pk->h_poly = b.take<Fr>(n);
     pk->fold = b.take<Fr>(8 * n); pk->wpoly = b.take<Fr>(8 * n);
     pk->scratch = b.take<Fr>(8 * 4096 + std::max<size_t>(64, (n + 4095) / 4096) * (size_t)n_queries);
     pk->evals_dev = b.take<Fr>(n_queries + 8); pk->points_dev = b.take<Fr>(16); pk->coeff_dev = b.take<Fr>(n_queries + 8);
@@ -651,13 +660,15 @@ int zg_pk_load(zg_ctx* ctx, const zg_pk_desc* d, zg_pk** out) {
   Fr onev = fr_one();
   ZG_CUDA(cudaMemcpyAsync(pk->one_dev, &onev, sizeof(Fr), cudaMemcpyHostToDevice, st));
 
+  rc = ext_domain_init(ctx, pk->ext, pk->ext_mem, pk->scratch, pk->h);
+  if (rc) return rc;
   // fixed columns: values -> coeff -> extended; commitments (keygen_vk)
   for (uint32_t c = 0; c < F; c++)
     ZG_CUDA(cudaMemcpyAsync(pk->fixed_values + c * n, d->fixed[c], sizeof(Fr) * n, cudaMemcpyHostToDevice, st));
   if (F) {
     rc = zg_lagrange_to_coeff_dev(ctx, (const zg_fr*)pk->fixed_values, (zg_fr*)pk->fixed_polys, pk->k, F, n);
     if (rc) return rc;
-    rc = zg_coeff_to_extended_dev(ctx, (const zg_fr*)pk->fixed_polys, n, pk->k, pk->ext_k, (zg_fr*)pk->fixed_cosets, N, F);
+    rc = ext_from_coeff(ctx, pk->ext, pk->fixed_polys, n, pk->fixed_cosets, N, F);
     if (rc) return rc;
     std::vector<Affine> aff(F);
     rc = commit_batch(ctx, ZG_BASIS_LAGRANGE, pk->fixed_values, n, n, F, aff.data());
@@ -677,7 +688,7 @@ int zg_pk_load(zg_ctx* ctx, const zg_pk_desc* d, zg_pk** out) {
     fr_sigma_values(map_dev, pk->coeff_dev, pk->omega, m, n, pk->sigma_values, st, lc);
     rc = zg_lagrange_to_coeff_dev(ctx, (const zg_fr*)pk->sigma_values, (zg_fr*)pk->sigma_polys, pk->k, m, n);
     if (rc) return rc;
-    rc = zg_coeff_to_extended_dev(ctx, (const zg_fr*)pk->sigma_polys, n, pk->k, pk->ext_k, (zg_fr*)pk->sigma_cosets, N, m);
+    rc = ext_from_coeff(ctx, pk->ext, pk->sigma_polys, n, pk->sigma_cosets, N, m);
     if (rc) return rc;
     std::vector<Affine> aff(m);
     rc = commit_batch(ctx, ZG_BASIS_LAGRANGE, pk->sigma_values, n, n, m, aff.data());
@@ -700,11 +711,11 @@ int zg_pk_load(zg_ctx* ctx, const zg_pk_desc* d, zg_pk** out) {
     fr_scatter_rows(lag, pk->d_pidx, pk->evals_dev, (uint32_t)rows.size(), st, lc);
     rc = zg_lagrange_to_coeff_dev(ctx, (const zg_fr*)lag, (zg_fr*)coef, pk->k, 3, n);
     if (rc) return rc;
-    rc = zg_coeff_to_extended_dev(ctx, (const zg_fr*)coef, n, pk->k, pk->ext_k, (zg_fr*)pk->l0, N, 1);
+    rc = ext_from_coeff(ctx, pk->ext, coef, n, pk->l0, N, 1);
     if (rc) return rc;
-    rc = zg_coeff_to_extended_dev(ctx, (const zg_fr*)(coef + n), n, pk->k, pk->ext_k, (zg_fr*)pk->l_last, N, 1);
+    rc = ext_from_coeff(ctx, pk->ext, coef + n, n, pk->l_last, N, 1);
     if (rc) return rc;
-    rc = zg_coeff_to_extended_dev(ctx, (const zg_fr*)(coef + 2 * n), n, pk->k, pk->ext_k, (zg_fr*)pk->h, N, 1);
+    rc = ext_from_coeff(ctx, pk->ext, coef + 2 * n, n, pk->h, N, 1);
     if (rc) return rc;
     fr_one_minus_sum(pk->l_last, pk->h, pk->l_active, N, st, lc);
   }
@@ -713,17 +724,17 @@ int zg_pk_load(zg_ctx* ctx, const zg_pk_desc* d, zg_pk** out) {
     Fr* coef = pk->wpoly;
     ZG_CUDA(cudaMemsetAsync(coef, 0, sizeof(Fr) * n, st));
     ZG_CUDA(cudaMemcpyAsync(coef + 1, &onev, sizeof(Fr), cudaMemcpyHostToDevice, st));
-    rc = zg_coeff_to_extended_dev(ctx, (const zg_fr*)coef, n, pk->k, pk->ext_k, (zg_fr*)pk->coset_x, N, 1);
+    rc = ext_from_coeff(ctx, pk->ext, coef, n, pk->coset_x, N, 1);
     if (rc) return rc;
   }
-  // t_inv[i] = 1 / ((zeta * ext_omega^i)^n - 1), period 2^(ext_k - k)
+  // halo2's coset, for the C-ABI conversions only: t_inv[i] = (zeta * ext_omega^i)^n - 1 (NOT inverted), period 2^(ext_k - k)
   {
-    std::vector<Fr> t(pk->rot_scale);
+    std::vector<Fr> t((size_t)1 << (pk->ext_k - pk->k));
     Fr zn = fr_pow(host_fr_zeta(), n);
     Fr wn = fr_pow(host_omega(pk->ext_k), n);
     Fr cur = zn;
-    for (uint32_t i = 0; i < pk->rot_scale; i++) {
-      t[i] = fp_inv(fp_sub(cur, fr_one()));
+    for (size_t i = 0; i < t.size(); i++) {
+      t[i] = fp_sub(cur, fr_one());
       cur = fp_mul(cur, wn);
     }
     ZG_CUDA(cudaMemcpyAsync(pk->t_inv, t.data(), sizeof(Fr) * t.size(), cudaMemcpyHostToDevice, st));
@@ -952,7 +963,7 @@ static int create_proof_impl(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice,
   // column is scaled afterwards, which is the same product.
   {
     const uint32_t cnt = S + Lk;
-    if ((size_t)cnt * n > N || cnt > 16) return ctx->fail(ZG_E_INVALID, "create_proof: too many grand-product columns");
+    if (cnt > 16) return ctx->fail(ZG_E_INVALID, "create_proof: too many grand-product columns");
     Fr* num = pk->h;        // cnt columns of n
     Fr* den = pk->h_coeff;
     Fr deltaomega = fr_one();
@@ -1022,8 +1033,8 @@ static int create_proof_impl(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice,
   if (rc) return rc;
   ZG_CUDA(cudaEventRecord(ev[4], st));
   // ---- 8. vanishing::construct: divide, back to coefficients, commit the pieces ---------------------------------------------
-  fr_mul_periodic(pk->h, pk->t_inv, pk->rot_scale, N, st, lc);
-  rc = zg_extended_to_coeff_dev(ctx, (const zg_fr*)pk->h, pk->k, pk->ext_k, n * pk->qdeg, (zg_fr*)pk->h_coeff);
+  ext_divide_by_vanishing(pk->ext, pk->h, st, lc);
+  rc = ext_to_coeff(ctx, pk->ext, pk->h, pk->adv_cosets /* dead after the numerator */, n * pk->qdeg, pk->h_coeff);
   if (rc) return rc;
   draw += pk->qdeg;  // h piece blinds
   {
@@ -1193,8 +1204,20 @@ int zg_evaluate_h(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice_polys, cons
   memcpy(ch, challenges, sizeof(ch));   // theta, beta, gamma, y
   int rc = quotient_numerator(ctx, pk, ch[0], ch[1], ch[2], ch[3], /*transform=*/true);
   if (rc) return rc;
-  if (divide) fr_mul_periodic(pk->h, pk->t_inv, pk->rot_scale, N, st, lc);
-  ZG_CUDA(cudaMemcpyAsync(h_out, pk->h, sizeof(Fr) * N, cudaMemcpyDeviceToHost, st));
+  // The numerator lives on the internal domain (extdomain.cuh).  The ABI speaks halo2's coset zeta * <omega_ext>:
+  // quotient -> coefficients -> values on that coset, times (X^n - 1) again when the caller wants the numerator.
+  ext_divide_by_vanishing(pk->ext, pk->h, st, lc);
+  const size_t keep = std::min(pk->N, n * pk->qdeg);
+  rc = ext_to_coeff(ctx, pk->ext, pk->h, pk->adv_cosets, keep, pk->h_coeff);
+  if (rc) return rc;
+  const size_t NH = (size_t)1 << pk->ext_k;
+  rc = ws_reserve(ctx, ctx->ws_stage, sizeof(Fr) * NH);
+  if (rc) return rc;
+  Fr* hh = (Fr*)ctx->ws_stage.p;
+  rc = ntt_halo_coset_dev(ctx, pk->h_coeff, (uint32_t)keep, pk->ext_k, hh);
+  if (rc) return rc;
+  if (!divide) fr_mul_periodic(hh, pk->t_inv, 1u << (pk->ext_k - pk->k), NH, st, lc);
+  ZG_CUDA(cudaMemcpyAsync(h_out, hh, sizeof(Fr) * NH, cudaMemcpyDeviceToHost, st));
   ZG_CUDA(cudaStreamSynchronize(st));
   return ZG_OK;
 }

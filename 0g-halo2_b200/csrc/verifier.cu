@@ -7,7 +7,7 @@
 // launches a kernel, so a proof can be checked where no GPU exists.  The optimal-ate pairing below (tower
 // Fq2 = Fq[u]/(u^2+1), Fq6 = Fq2[v]/(v^3 - (9+u)), Fq12 = Fq6[w]/(w^2 - v); D-type twist; affine Miller loop over
 // 6x+2, two Frobenius lines, final exponentiation as conj/inverse followed by one plain square-and-multiply) is
-// written for this file; the test-only pairing in oracle/zg_oracle.c is the independent checker
+// written for this file; the test-only pairing of the CPU checker under oracle/ is the independent implementation
 // (tests/test_verifier.py compares the two on bilinearity and on accept / reject of whole proofs).
 #include <algorithm>
 #include <array>

@@ -68,6 +68,17 @@ def test_tiny_model_proof_bytes_match_oracle(ctx, tiny):
         first = next(i for i in range(len(proof)) if proof[i] != oproof[i])
         pytest.fail("proof bytes differ from the oracle first at offset %d: %s" % (first, _stage_of(first, circ0.cs)))
     assert H.verify_proof(srs, opk, [outputs], proof)
+    # the product's own verifier (Wnn::verify_proof, src/wnn.rs:265-280) on the product's own key: accept, reject a wrong
+    # output, reject a flipped byte -- and a proof drawn from the production RNG (OS-seeded ChaCha20) verifies as well
+    vparams = ParamsKZG(k, srs.g, srs.g_lagrange, srs.g2, srs.s_g2)
+    assert wnn.verify_proof(proof, pk, vparams, outputs)
+    assert not wnn.verify_proof(proof, pk, vparams, [outputs[0] + 1] + outputs[1:])
+    bad = bytearray(proof)
+    bad[1000] ^= 4
+    assert not wnn.verify_proof(bytes(bad), pk, vparams, outputs)
+    proof_os, out_os = wnn.proof(pk, params, img)
+    assert out_os == outputs and proof_os != proof and wnn.verify_proof(proof_os, pk, vparams, outputs)
+    assert H.verify_proof(srs, opk, [outputs], proof_os)
     bad = bytearray(proof)
     bad[1000] ^= 1
     assert not H.verify_proof(srs, opk, [outputs], bytes(bad))
