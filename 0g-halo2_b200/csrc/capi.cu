@@ -189,10 +189,14 @@ int zg_ctx_create(int device, void* stream, zg_ctx** out) {
   return ZG_OK;
 }
 
+extern "C" int zg_comm_destroy(zg_ctx* ctx);
+
 void zg_ctx_destroy(zg_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->comm) zg_comm_destroy(ctx);
+  if (ctx->d_gather) cudaFree(ctx->d_gather);
   for (int b = 0; b < 2; b++) {
     if (ctx->base[b]) cudaFree(ctx->base[b]);
     if (ctx->table[b].pts) cudaFree(ctx->table[b].pts);

@@ -56,6 +56,14 @@ struct zg_ctx {
   // twiddle tables keyed by (log_n, omega limbs)
   std::map<std::array<uint32_t, 9>, zg::Domain> domains;
 
+  // multi-GPU (dist.cu): NCCL communicator (opaque here), this rank, and whether zg_create_proof spreads a round's
+  // commitments over the ranks
+  void* comm = nullptr;
+  int nranks = 1, rank = 0;
+  bool dist_columns = false;
+  zg::G1Jac* d_gather = nullptr;
+  size_t gather_cap = 0;
+
   zg::Workspace ws_msm, ws_ntt, ws_stage;
   zg::G1Jac* d_msm_out = nullptr;  // small result staging (64 results)
   zg::MsmProbe probe;              // zg_probe_enable / zg_probe_read
@@ -76,6 +84,8 @@ int get_domain(zg_ctx* ctx, uint32_t logn, const Fr& omega, Domain** out);
 // zg_msm_dev with MSM m on the OTHER basis when bit m of other_mask is set (count <= 32)
 int msm_dev_mixed(zg_ctx* ctx, int basis, const Fr* scalars_dev, size_t stride, size_t n, size_t count, uint32_t other_mask,
                   G1Jac* out_dev);
+// the commitments of one round into ctx->d_msm_out[0..count) -- locally, or spread over the ranks of ctx->comm (dist.cu)
+int msm_round(zg_ctx* ctx, int basis, const Fr* cols, size_t stride, size_t n, size_t count, uint32_t other_mask);
 }  // namespace zg
 
 // CUDA's current device is per host thread: every entry point selects the context's device first

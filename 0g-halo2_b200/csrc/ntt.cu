@@ -211,7 +211,10 @@ cudaError_t ntt_run(const NttPlan& P, cudaStream_t stream, uint64_t* nl) {
   const uint32_t logn = P.logn;
   {
     static const bool force_stagewise = getenv("ZG_NTT_STAGEWISE") != nullptr;     // A/B switch for profiling
-    if (!force_stagewise && P.flat && ntt_fast_supported(logn)) return ntt_fast_run(P, stream, nl);
+    static const bool force_fast = getenv("ZG_NTT_FAST") != nullptr;
+    if (!force_stagewise && P.flat && ntt_fast_supported(logn) &&
+        (force_fast || ntt_fast_pays(logn, P.batch * (P.cosets ? P.cosets : 1))))
+      return ntt_fast_run(P, stream, nl);
   }
   uint32_t npass = (logn + NTT_MAX_S - 1) / NTT_MAX_S;
   if (npass == 0) npass = 1;

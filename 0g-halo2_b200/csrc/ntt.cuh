@@ -80,6 +80,7 @@ struct NttFastArgs {
   Fr out_scale[3];
 };
 bool ntt_fast_supported(uint32_t logn);
+bool ntt_fast_pays(uint32_t logn, uint32_t transforms);
 cudaError_t ntt_fast_run(const NttPlan& plan, cudaStream_t stream, uint64_t* launch_counter);
 
 // tab: stage-major table (n - 1 entries) for ntt.cu; flat: w^e for e < n/2 (kept: ntt_fast.cu reads it)

@@ -17,6 +17,10 @@
 //     coset), output scaling (1/N, optionally per element) and truncation are fused into the first / last pass;
 //     one launch covers a whole batch of polynomials and, for the prover's 3 x 2n extended domain, the three cosets.
 // The arithmetic is integer-pipe bound: the kernel is judged against the Montgomery-product rate.
+// The rounds are unrolled over a thread's 8 register-resident elements; with the multiplier inlined one pass was 212 KB of
+// SASS (cuobjdump) and ran slower than the stage-wise kernel (2^20: 0.277 vs 0.236 ms) on instruction fetch.  One shared
+// copy of the multiplier and ONE round body executed in a run-time loop keep the kernel near 30 KB.
+#define ZG_FP_MUL_NOINLINE 1
 #include <atomic>
 #include "ntt.cuh"
 
@@ -65,56 +69,37 @@ struct Planes {
   }
 };
 
-// One round: the thread holds the 8 elements whose row index j differs in bits PC+2, PC+1, PC (slot u = those bits) and
+// One round: the thread holds the 8 elements whose row index j differs in bits pc+2, pc+1, pc (slot u = those bits) and
 // runs the decimation-in-frequency stages of the ACTIVE ones among them, most significant first.  Stage at bit s pairs
-// rows j and j + 2^s and multiplies the difference by w_R^((j mod 2^s) << (S-1-s)).
-template <int S, int PC, int ACTIVE>
-__device__ __forceinline__ void nf_round(Fr (&x)[8], uint32_t jbase, const Planes& tw) {
+// rows j and j + 2^s and multiplies the difference by w_R^((j mod 2^s) << (S-1-s)).  pc / active are run-time values so
+// that the three rounds of a pass share one copy of this code.
+template <int S>
+__device__ __forceinline__ void nf_round(Fr (&x)[8], uint32_t jbase, uint32_t pc, uint32_t active, const Planes& tw) {
 #pragma unroll
   for (int q = 2; q >= 0; q--) {
-    if (!((ACTIVE >> q) & 1)) continue;
-    const int s = PC + q;
+    if (!((active >> q) & 1u)) continue;
+    const uint32_t s = pc + q;
+    const uint32_t smask = (1u << s) - 1u, sh = S - 1 - s;
 #pragma unroll
     for (int u0 = 0; u0 < 8; u0++) {
       if ((u0 >> q) & 1) continue;
       const int u1 = u0 | (1 << q);
-      const uint32_t jl = (jbase | ((uint32_t)u0 << PC)) & ((1u << s) - 1u);
+      const uint32_t jl = (jbase | ((uint32_t)u0 << pc)) & smask;
       Fr a = x[u0], b = x[u1];
       x[u0] = fp_add(a, b);
       Fr d = fp_sub(a, b);
-      if (PC == 0 && (u0 & ((1 << q) - 1)) == 0) {
-        x[u1] = d;                                    // twiddle w^0, known at compile time in the last round
-      } else {
-        x[u1] = fp_mul(d, tw.get(jl << (S - 1 - s)));
-      }
+      if (jl) d = fp_mul(d, tw.get(jl << sh));        // w^0 in the last round for half of the pairs, rarely elsewhere
+      x[u1] = d;
     }
   }
 }
 
-template <int S>
-struct NfRounds;   // PC of each round and which of its three bits still have a stage to run
-template <> struct NfRounds<9> { static constexpr int N = 3, pc[3] = {6, 3, 0}, act[3] = {7, 7, 7}; };
-template <> struct NfRounds<8> { static constexpr int N = 3, pc[3] = {5, 2, 0}, act[3] = {7, 7, 3}; };
-template <> struct NfRounds<7> { static constexpr int N = 3, pc[3] = {4, 1, 0}, act[3] = {7, 7, 1}; };
-template <> struct NfRounds<6> { static constexpr int N = 2, pc[3] = {3, 0, 0}, act[3] = {7, 7, 0}; };
-
-template <int PC>
-__device__ __forceinline__ uint32_t nf_jbase(uint32_t rest) {   // spread the S-3 thread bits around the register bits
-  return ((rest >> PC) << (PC + 3)) | (rest & ((1u << PC) - 1u));
-}
-
-template <int S, int PC, int ACTIVE>
-__device__ __forceinline__ void nf_round_smem(const Planes& sm, const Planes& tw, uint32_t rest, uint32_t col, Fr (&x)[8],
-                                              bool write_back) {
-  const uint32_t jbase = nf_jbase<PC>(rest);
-#pragma unroll
-  for (int u = 0; u < 8; u++) x[u] = sm.get(((jbase | ((uint32_t)u << PC)) << NF_LOGC) | col);
-  nf_round<S, PC, ACTIVE>(x, jbase, tw);
-  if (write_back) {
-#pragma unroll
-    for (int u = 0; u < 8; u++) sm.put(((jbase | ((uint32_t)u << PC)) << NF_LOGC) | col, x[u]);
-  }
-}
+// pc of each round (packed 4 bits each, first round lowest) and the active-stage masks (3 bits each)
+template <int S> struct NfRounds;
+template <> struct NfRounds<9> { static constexpr uint32_t N = 3, PC = 6 | (3 << 4) | (0 << 8), ACT = 7 | (7 << 4) | (7 << 8); };
+template <> struct NfRounds<8> { static constexpr uint32_t N = 3, PC = 5 | (2 << 4) | (0 << 8), ACT = 7 | (7 << 4) | (3 << 8); };
+template <> struct NfRounds<7> { static constexpr uint32_t N = 3, PC = 4 | (1 << 4) | (0 << 8), ACT = 7 | (7 << 4) | (1 << 8); };
+template <> struct NfRounds<6> { static constexpr uint32_t N = 2, PC = 3 | (0 << 4), ACT = 7 | (7 << 4); };
 
 }  // namespace
 
@@ -176,14 +161,18 @@ __global__ void __launch_bounds__((1 << S) * NF_C / 8, (S == 9 ? 2 : S == 8 ? 4 
   const uint32_t col = tid & (NF_C - 1), rest = tid >> NF_LOGC;
   Fr x[8];
   using RD = NfRounds<S>;
-  nf_round_smem<S, RD::pc[0], RD::act[0]>(sm, tw, rest, col, x, true);
-  __syncthreads();
-  if (RD::N == 3) {
-    nf_round_smem<S, RD::pc[1], RD::act[1]>(sm, tw, rest, col, x, true);
-    __syncthreads();
-    nf_round_smem<S, RD::pc[2], RD::act[2]>(sm, tw, rest, col, x, false);
-  } else {
-    nf_round_smem<S, RD::pc[1], RD::act[1]>(sm, tw, rest, col, x, false);
+#pragma unroll 1
+  for (uint32_t r = 0; r < RD::N; r++) {
+    const uint32_t pc = (RD::PC >> (4 * r)) & 15u, active = (RD::ACT >> (4 * r)) & 15u;
+    const uint32_t jbase = ((rest >> pc) << (pc + 3)) | (rest & ((1u << pc) - 1u));   // thread bits around the register bits
+#pragma unroll
+    for (int u = 0; u < 8; u++) x[u] = sm.get(((jbase | ((uint32_t)u << pc)) << NF_LOGC) | col);
+    nf_round<S>(x, jbase, pc, active, tw);
+    if (r + 1 < RD::N) {
+#pragma unroll
+      for (int u = 0; u < 8; u++) sm.put(((jbase | ((uint32_t)u << pc)) << NF_LOGC) | col, x[u]);
+      __syncthreads();
+    }
   }
 
   // registers -> global: slot u holds row j = (rest << 3) | u, i.e. output digit k = bitrev_S(j)
@@ -230,6 +219,11 @@ __global__ void __launch_bounds__((1 << S) * NF_C / 8, (S == 9 ? 2 : S == 8 ? 4 
 // flat[e] = w^e for e < N/2 is built by ntt_build_twiddles (ntt.cu)
 
 bool ntt_fast_supported(uint32_t logn) { return logn >= 12 && logn <= 28; }
+// tiles of 2^S x 4 elements: below about two CTAs per SM the stage-wise kernel (smaller tiles, more passes) fills the GPU better
+bool ntt_fast_pays(uint32_t logn, uint32_t transforms) {
+  const uint32_t npass = (logn + 8) / 9, s0 = (logn + npass - 1) / npass;
+  return ((uint64_t)transforms << (logn - s0 - NF_LOGC)) >= 296;
+}
 
 template <int S>
 static void nf_launch(const NttFastArgs& A, dim3 grid, cudaStream_t st) {

@@ -313,8 +313,11 @@ static cudaError_t upload(T* dst, const std::vector<T>& v, cudaStream_t st) {
 }
 
 // commit `count` columns (stride n) on `basis`, normalise on the host
-static int commit_batch(zg_ctx* ctx, int basis, const Fr* cols, size_t stride, size_t n, size_t count, Affine* out) {
-  int rc = zg_msm_dev(ctx, basis, (const zg_fr*)cols, stride, n, count, (zg_g1*)ctx->d_msm_out);
+static int commit_batch(zg_ctx* ctx, int basis, const Fr* cols, size_t stride, size_t n, size_t count, Affine* out,
+                        bool round_of_a_proof = false) {
+  // keygen commits locally on every rank; the rounds of a proof may be spread over the ranks (dist.cu)
+  int rc = round_of_a_proof ? msm_round(ctx, basis, cols, stride, n, count, 0)
+                            : zg_msm_dev(ctx, basis, (const zg_fr*)cols, stride, n, count, (zg_g1*)ctx->d_msm_out);
   if (rc) return rc;
   std::vector<G1Jac> jac(count);
   ZG_CUDA(cudaMemcpyAsync(jac.data(), ctx->d_msm_out, sizeof(G1Jac) * count, cudaMemcpyDeviceToHost, ctx->stream));
@@ -534,6 +537,24 @@ int zg_pk_commitments(zg_ctx* ctx, const zg_pk* pk, zg_g1_affine* fixed_out, zg_
   return ZG_OK;
 }
 
+int zg_pk_read_column(zg_ctx* ctx, const zg_pk* pk, int what, uint32_t index, zg_fr* out) {
+  ZG_ENTER(ctx);
+  if (!pk || !out) return ctx->fail(ZG_E_INVALID, "pk_read_column: null argument");
+  const Fr* base;
+  uint32_t count;
+  switch (what) {
+    case ZG_PK_FIXED_VALUES: base = pk->fixed_values; count = pk->F; break;
+    case ZG_PK_FIXED_POLYS: base = pk->fixed_polys; count = pk->F; break;
+    case ZG_PK_SIGMA_VALUES: base = pk->sigma_values; count = pk->m; break;
+    case ZG_PK_SIGMA_POLYS: base = pk->sigma_polys; count = pk->m; break;
+    default: return ctx->fail(ZG_E_INVALID, "pk_read_column: unknown column family");
+  }
+  if (index >= count) return ctx->fail(ZG_E_INVALID, "pk_read_column: index out of range");
+  ZG_CUDA(cudaMemcpyAsync(out, base + (size_t)index * pk->n, sizeof(Fr) * pk->n, cudaMemcpyDeviceToHost, ctx->stream));
+  ZG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return ZG_OK;
+}
+
 int zg_pk_load(zg_ctx* ctx, const zg_pk_desc* d, zg_pk** out) {
   ZG_ENTER(ctx);
   if (!d || !out) return ctx->fail(ZG_E_INVALID, "pk_load: null argument");
@@ -678,14 +699,24 @@ int zg_pk_load(zg_ctx* ctx, const zg_pk_desc* d, zg_pk** out) {
   }
   // permutation: sigma values from the mapping
   if (m) {
-    uint32_t* map_dev = (uint32_t*)pk->h;  // scratch: 2*m*n words fit in N Fr when 8*m*n <= 32*N
-    if ((size_t)8 * m * n > sizeof(Fr) * N) return ctx->fail(ZG_E_INVALID, "pk_load: permutation too wide for scratch");
-    ZG_CUDA(cudaMemcpyAsync(map_dev, d->perm_mapping, (size_t)8 * m * n, cudaMemcpyHostToDevice, st));
-    std::vector<Fr> dp(m);
-    Fr cur = fr_one();
-    for (uint32_t c = 0; c < m; c++) { dp[c] = cur; cur = fp_mul(cur, pk->delta); }
-    ZG_CUDA(cudaMemcpyAsync(pk->coeff_dev, dp.data(), sizeof(Fr) * m, cudaMemcpyHostToDevice, st));
-    fr_sigma_values(map_dev, pk->coeff_dev, pk->omega, m, n, pk->sigma_values, st, lc);
+    if (d->perm_mapping) {
+      uint32_t* map_dev = (uint32_t*)pk->h;  // scratch: 2*m*n words fit in N Fr when 8*m*n <= 32*N
+      if ((size_t)8 * m * n > sizeof(Fr) * N) return ctx->fail(ZG_E_INVALID, "pk_load: permutation too wide for scratch");
+      ZG_CUDA(cudaMemcpyAsync(map_dev, d->perm_mapping, (size_t)8 * m * n, cudaMemcpyHostToDevice, st));
+      std::vector<Fr> dp(m);
+      Fr cur = fr_one();
+      for (uint32_t c = 0; c < m; c++) { dp[c] = cur; cur = fp_mul(cur, pk->delta); }
+      ZG_CUDA(cudaMemcpyAsync(pk->coeff_dev, dp.data(), sizeof(Fr) * m, cudaMemcpyHostToDevice, st));
+      ZG_CUDA(cudaStreamSynchronize(st));      // `dp` is a host temporary
+      fr_sigma_values(map_dev, pk->coeff_dev, pk->omega, m, n, pk->sigma_values, st, lc);
+    } else if (d->sigma_values) {              // a serialized key carries the sigma columns themselves
+      for (uint32_t c = 0; c < m; c++) {
+        if (!d->sigma_values[c]) return ctx->fail(ZG_E_INVALID, "pk_load: null sigma column");
+        ZG_CUDA(cudaMemcpyAsync(pk->sigma_values + c * n, d->sigma_values[c], sizeof(Fr) * n, cudaMemcpyHostToDevice, st));
+      }
+    } else {
+      return ctx->fail(ZG_E_INVALID, "pk_load: neither perm_mapping nor sigma_values given");
+    }
     rc = zg_lagrange_to_coeff_dev(ctx, (const zg_fr*)pk->sigma_values, (zg_fr*)pk->sigma_polys, pk->k, m, n);
     if (rc) return rc;
     rc = ext_from_coeff(ctx, pk->ext, pk->sigma_polys, n, pk->sigma_cosets, N, m);
@@ -842,7 +873,7 @@ static int create_proof_impl(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice,
       if (rc) return rc;
     }
     std::vector<Affine> aff(A);
-    rc = zg_msm_dev(ctx, ZG_BASIS_LAGRANGE, (const zg_fr*)pk->adv_values, n, n, A, (zg_g1*)ctx->d_msm_out);
+    rc = msm_round(ctx, ZG_BASIS_LAGRANGE, pk->adv_values, n, n, A, 0);
     if (rc) return rc;
     // the big random polynomial is drawn on the host while the GPU commits
     const size_t rest = pk->n_draws - small_draws;
@@ -916,7 +947,7 @@ static int create_proof_impl(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice,
         rc = coset_lookup_permuted(ctx, pk);
         if (rc) return rc;
       }
-      rc = zg_msm_dev(ctx, ZG_BASIS_LAGRANGE, (const zg_fr*)pk->pa, n, n, 2 * Lk, (zg_g1*)ctx->d_msm_out);
+      rc = msm_round(ctx, ZG_BASIS_LAGRANGE, pk->pa, n, n, 2 * Lk, 0);
       if (rc) return rc;
       std::vector<G1Jac> jac(2 * Lk);
       std::vector<uint32_t> status(2 * Lk);
@@ -1015,7 +1046,7 @@ static int create_proof_impl(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice,
     // one pipeline for the whole round: the product columns on the Lagrange basis and, as MSM number `cnt`, the random
     // polynomial on the monomial basis (copied behind the product columns so the batch is one strided array)
     ZG_CUDA(cudaMemcpyAsync(pk->pz + (size_t)cnt * n, pk->random_poly, sizeof(Fr) * n, cudaMemcpyDeviceToDevice, st));
-    rc = msm_dev_mixed(ctx, ZG_BASIS_LAGRANGE, pk->pz, n, n, cnt + 1, 1u << cnt, ctx->d_msm_out);
+    rc = msm_round(ctx, ZG_BASIS_LAGRANGE, pk->pz, n, n, cnt + 1, 1u << cnt);
     if (rc) return rc;
     ZG_CUDA(cudaMemcpyAsync(jac.data(), ctx->d_msm_out, sizeof(G1Jac) * (cnt + 1), cudaMemcpyDeviceToHost, st));
     ZG_CUDA(cudaEventRecord(ev[3], st));
@@ -1039,7 +1070,7 @@ static int create_proof_impl(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice,
   draw += pk->qdeg;  // h piece blinds
   {
     std::vector<Affine> aff(pk->qdeg);
-    rc = commit_batch(ctx, ZG_BASIS_MONOMIAL, pk->h_coeff, n, n, pk->qdeg, aff.data());
+    rc = commit_batch(ctx, ZG_BASIS_MONOMIAL, pk->h_coeff, n, n, pk->qdeg, aff.data(), true);
     if (rc) return rc;
     for (uint32_t i = 0; i < pk->qdeg; i++)
       if (!tr.write_point(aff[i])) return ctx->fail(ZG_E_SYNTH, "create_proof: h commitment is the identity");
@@ -1153,7 +1184,7 @@ static int create_proof_impl(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice,
   }
   {
     std::vector<Affine> aff(nsetsQ);
-    rc = commit_batch(ctx, ZG_BASIS_MONOMIAL, pk->wpoly, n, n, nsetsQ, aff.data());
+    rc = commit_batch(ctx, ZG_BASIS_MONOMIAL, pk->wpoly, n, n, nsetsQ, aff.data(), true);
     if (rc) return rc;
     for (uint32_t g = 0; g < nsetsQ; g++)
       if (!tr.write_point(aff[g])) return ctx->fail(ZG_E_SYNTH, "create_proof: opening witness is the identity");

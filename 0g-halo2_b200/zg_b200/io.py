@@ -278,3 +278,117 @@ def encode_calldata(instances, proof: bytes) -> bytes:
         for v in col:
             out += (int(v) % R_MOD).to_bytes(32, "big")
     return bytes(out) + bytes(proof)
+
+
+# ---- proving / verifying key files (src/io.rs:159-176) ------------------------------------------------------------
+# `pk.write(writer, RawBytes)` / `pk.get_vk().write(writer, RawBytes)` of halo2_proofs v2023_04_20 (un-vendored;
+# layout [UPSTREAM-RECALLED] from plonk.rs / permutation.rs / poly.rs / helpers.rs of that tag, to be re-checked against
+# a file written by the Rust CLI):
+#   VerifyingKey : k (u32 BE) | num_fixed (u32 BE) | fixed commitments | permutation commitments (no count: one per
+#                  permutation column of the constraint system) | one bit per row per selector, packed LSB first,
+#                  ceil(n/8) bytes per selector (the selector activations BEFORE compression)
+#   ProvingKey   : VerifyingKey | l0 | l_last | l_active_row (Polynomial) | fixed_values | fixed_polys | fixed_cosets
+#                  (slices) | permutation.{permutations, polys, cosets} (slices)
+#   Polynomial   : len (u32 BE) | len field elements;   slice: count (u32 BE) | polynomials
+#   RawBytes     : Fr = four u64 LE Montgomery limbs (32 B); G1Affine = x | y, Fq likewise (64 B) -- the limbs the
+#                  C ABI uses, so columns are written verbatim.
+# The extended forms in the file live on halo2's coset (zeta * <omega_ext>, 2^extended_k points), not on this
+# backend's internal domain: `zg_b200.prover.export_proving_key` rebuilds them through the C ABI.
+def _u32be(v: int) -> bytes:
+    return int(v).to_bytes(4, "big")
+
+
+def _read_exact(f, nbytes: int) -> bytes:
+    b = f.read(nbytes)
+    if len(b) != nbytes:
+        raise ValueError("key file truncated")
+    return b
+
+
+def _write_poly(f, col) -> None:
+    a = np.ascontiguousarray(col, dtype="<u8").reshape(-1, 4)
+    f.write(_u32be(a.shape[0]))
+    f.write(a.tobytes())
+
+
+def _read_poly(f, expect_len=None) -> np.ndarray:
+    n = int.from_bytes(_read_exact(f, 4), "big")
+    if expect_len is not None and n != expect_len:
+        raise ValueError("key file: polynomial of %d elements where %d were expected" % (n, expect_len))
+    return np.frombuffer(_read_exact(f, 32 * n), dtype="<u8").reshape(n, 4).astype(np.uint64)
+
+
+def _write_poly_slice(f, cols) -> None:
+    f.write(_u32be(len(cols)))
+    for c in cols:
+        _write_poly(f, c)
+
+
+def _read_poly_slice(f, expect_count=None, expect_len=None) -> list:
+    cnt = int.from_bytes(_read_exact(f, 4), "big")
+    if expect_count is not None and cnt != expect_count:
+        raise ValueError("key file: %d polynomials where %d were expected" % (cnt, expect_count))
+    return [_read_poly(f, expect_len) for _ in range(cnt)]
+
+
+def write_vk(f, k: int, fixed_commitments, perm_commitments, selectors) -> None:
+    """VerifyingKey::write(RawBytes).  Commitments as (count, 8) uint64 limb arrays, selectors as lists of bools."""
+    fc = np.ascontiguousarray(fixed_commitments, dtype="<u8").reshape(-1, 8)
+    pc = np.ascontiguousarray(perm_commitments, dtype="<u8").reshape(-1, 8)
+    f.write(_u32be(k))
+    f.write(_u32be(fc.shape[0]))
+    f.write(fc.tobytes())
+    f.write(pc.tobytes())
+    for sel in selectors:
+        bits = np.asarray(sel, dtype=bool)
+        assert bits.shape[0] == 1 << k
+        f.write(np.packbits(bits, bitorder="little").tobytes())
+
+
+def read_vk(f, num_perm_columns: int, num_selectors: int) -> dict:
+    """VerifyingKey::read(RawBytes): the caller supplies what the Rust side takes from the circuit (`params` ->
+    configure): the number of permutation columns and of selectors.  Returns k, commitments, selector activations."""
+    k = int.from_bytes(_read_exact(f, 4), "big")
+    if not 1 <= k <= 28:
+        raise ValueError("key file: k = %d out of range (not a RawBytes key file?)" % k)
+    nf = int.from_bytes(_read_exact(f, 4), "big")
+    if nf > 1 << 16:
+        raise ValueError("key file: implausible number of fixed columns")
+    fc = np.frombuffer(_read_exact(f, 64 * nf), dtype="<u8").reshape(nf, 8).astype(np.uint64)
+    pc = np.frombuffer(_read_exact(f, 64 * num_perm_columns), dtype="<u8").reshape(num_perm_columns, 8).astype(np.uint64)
+    n = 1 << k
+    sels = []
+    for _ in range(num_selectors):
+        raw = np.frombuffer(_read_exact(f, (n + 7) // 8), dtype=np.uint8)
+        sels.append(np.unpackbits(raw, bitorder="little")[:n].astype(bool).tolist())
+    return {"k": k, "fixed_commitments": fc, "perm_commitments": pc, "selectors": sels}
+
+
+def write_pk(f, vk: dict, l0, l_last, l_active_row, fixed_values, fixed_polys, fixed_cosets, perm_values, perm_polys,
+             perm_cosets) -> None:
+    """ProvingKey::write(RawBytes); `vk` as returned by read_vk / assembled by export_proving_key."""
+    write_vk(f, vk["k"], vk["fixed_commitments"], vk["perm_commitments"], vk["selectors"])
+    for p in (l0, l_last, l_active_row):
+        _write_poly(f, p)
+    for sl in (fixed_values, fixed_polys, fixed_cosets, perm_values, perm_polys, perm_cosets):
+        _write_poly_slice(f, sl)
+
+
+def read_pk(f, num_perm_columns: int, num_selectors: int) -> dict:
+    """ProvingKey::read(RawBytes) (src/io.rs:166-170).  Lengths are cross-checked against k."""
+    d = read_vk(f, num_perm_columns, num_selectors)
+    n = 1 << d["k"]
+    d["l0"], d["l_last"], d["l_active_row"] = _read_poly(f), _read_poly(f), _read_poly(f)
+    ext_n = d["l0"].shape[0]
+    if ext_n < n or ext_n & (ext_n - 1) or d["l_last"].shape[0] != ext_n or d["l_active_row"].shape[0] != ext_n:
+        raise ValueError("key file: inconsistent extended-domain size")
+    nf = d["fixed_commitments"].shape[0]
+    d["fixed_values"] = _read_poly_slice(f, nf, n)
+    d["fixed_polys"] = _read_poly_slice(f, nf, n)
+    d["fixed_cosets"] = _read_poly_slice(f, nf, ext_n)
+    d["perm_values"] = _read_poly_slice(f, num_perm_columns, n)
+    d["perm_polys"] = _read_poly_slice(f, num_perm_columns, n)
+    d["perm_cosets"] = _read_poly_slice(f, num_perm_columns, ext_n)
+    if f.read(1):
+        raise ValueError("key file: trailing bytes")
+    return d

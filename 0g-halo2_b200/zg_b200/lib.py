@@ -30,9 +30,10 @@ EXPORTS = [
     "zg_ntt", "zg_ntt_dev", "zg_lagrange_to_coeff", "zg_lagrange_to_coeff_dev",
     "zg_coeff_to_extended", "zg_coeff_to_extended_dev", "zg_extended_to_coeff", "zg_extended_to_coeff_dev",
     "zg_bench_int_pipe", "zg_debug_field_op", "zg_debug_keccak256", "zg_probe_enable", "zg_probe_read",
-    "zg_xorshift_seed", "zg_xorshift_fill", "zg_chacha20_seed_os", "zg_chacha20_seed", "zg_chacha20_fill", "zg_pk_load", "zg_pk_free", "zg_pk_commitments", "zg_create_proof",
+    "zg_xorshift_seed", "zg_xorshift_fill", "zg_chacha20_seed_os", "zg_chacha20_seed", "zg_chacha20_fill", "zg_pk_load", "zg_pk_read_column", "zg_pk_free", "zg_pk_commitments", "zg_create_proof",
     "zg_pk_last_stage_ms", "zg_pk_set_transcript_repr",
     "zg_wnn_create", "zg_wnn_free", "zg_wnn_last_error", "zg_wnn_synthesize",
+    "zg_comm_unique_id", "zg_comm_init", "zg_comm_destroy", "zg_ctx_set_distribution", "zg_msm_sharded_dev", "zg_msm_sharded",
     "zg_vk_create", "zg_vk_free", "zg_vk_last_error", "zg_verify_proof", "zg_pairing_check",
     "zg_lookup_permute", "zg_grand_product", "zg_batch_invert", "zg_eval_poly_batch", "zg_kate_division", "zg_evaluate_h",
 ]
@@ -99,6 +100,7 @@ def load_library() -> ctypes.CDLL:
     L.zg_chacha20_fill.argtypes = [vp, vp, sz]
     L.zg_chacha20_fill.restype = None
     L.zg_pk_load.argtypes = [vp, vp, ctypes.POINTER(vp)]
+    L.zg_pk_read_column.argtypes = [vp, vp, ci, u32, vp]
     L.zg_pk_free.argtypes = [vp, vp]
     L.zg_pk_free.restype = None
     L.zg_pk_commitments.argtypes = [vp, vp, vp, vp]
@@ -111,6 +113,12 @@ def load_library() -> ctypes.CDLL:
     L.zg_wnn_last_error.argtypes = [vp]
     L.zg_wnn_last_error.restype = ctypes.c_char_p
     L.zg_wnn_synthesize.argtypes = [vp, vp, u32, u32, vp, vp]
+    L.zg_comm_unique_id.argtypes = [vp]
+    L.zg_comm_init.argtypes = [vp, ci, ci, vp]
+    L.zg_comm_destroy.argtypes = [vp]
+    L.zg_ctx_set_distribution.argtypes = [vp, ci]
+    L.zg_msm_sharded_dev.argtypes = [vp, ci, vp, sz, sz, sz, vp]
+    L.zg_msm_sharded.argtypes = [vp, ci, vp, sz, vp]
     L.zg_vk_create.argtypes = [u32, vp, sz, vp, sz, vp, vp, vp, ctypes.POINTER(vp)]
     L.zg_vk_free.argtypes = [vp]
     L.zg_vk_free.restype = None
@@ -201,6 +209,29 @@ class Context:
 
     def msm_dev(self, basis: int, scalars_ptr: int, stride: int, n: int, count: int, out_ptr: int):
         self._ck(self._L.zg_msm_dev(self._h, basis, scalars_ptr, stride, n, count, out_ptr))
+
+    # ---- multi-GPU (NCCL inside the library; dist.cu) ----
+    def comm_init(self, nranks: int, rank: int, unique_id: bytes):
+        """join an NCCL communicator; `unique_id` = the 128 bytes rank 0 got from `comm_unique_id()`"""
+        assert len(unique_id) == 128
+        buf = (ctypes.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._ck(self._L.zg_comm_init(self._h, nranks, rank, buf))
+
+    def comm_destroy(self):
+        self._ck(self._L.zg_comm_destroy(self._h))
+
+    def set_distribution(self, mode: int):
+        """0 = none, 1 = spread every round's commitments of zg_create_proof over the ranks (SPMD)"""
+        self._ck(self._L.zg_ctx_set_distribution(self._h, mode))
+
+    def msm_sharded(self, basis: int, scalars_slice) -> np.ndarray:
+        s = _np(scalars_slice, 4)
+        out = np.zeros(12, dtype=np.uint64)
+        self._ck(self._L.zg_msm_sharded(self._h, basis, _ptr(s), s.shape[0], _ptr(out)))
+        return out
+
+    def msm_sharded_dev(self, basis: int, scalars_ptr: int, stride: int, n_local: int, count: int, out_ptr: int):
+        self._ck(self._L.zg_msm_sharded_dev(self._h, basis, scalars_ptr, stride, n_local, count, out_ptr))
 
     # ---- NTT family ----
     def ntt(self, a, log_n: int, omega) -> np.ndarray:
@@ -320,11 +351,21 @@ class Context:
         return out
 
 
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId through the library (rank 0 calls it, the host plumbing broadcasts the 128 bytes)"""
+    buf = (ctypes.c_uint8 * 128)()
+    rc = load_library().zg_comm_unique_id(buf)
+    if rc != ZG_OK:
+        raise ZgError(rc, "zg_comm_unique_id: NCCL is not available")
+    return bytes(buf)
+
+
 class PkDesc(ctypes.Structure):
     """zg_pk_desc (include/zg_b200.h)."""
     _fields_ = [("k", ctypes.c_uint32), ("cs_words", ctypes.c_void_p), ("cs_nwords", ctypes.c_size_t),
                 ("constants", ctypes.c_void_p), ("n_constants", ctypes.c_size_t), ("fixed", ctypes.c_void_p),
-                ("perm_mapping", ctypes.c_void_p), ("transcript_repr", ctypes.c_uint64 * 4)]
+                ("perm_mapping", ctypes.c_void_p), ("transcript_repr", ctypes.c_uint64 * 4),
+                ("sigma_values", ctypes.c_void_p)]
 
 
 class XorShift(ctypes.Structure):

@@ -202,6 +202,108 @@ def keygen(ctx: zl.Context, params: ParamsKZG, cs, asm, transcript_repr: int | N
                       vk_parts=(words, constants, fc[:cs.num_fixed].copy(), pc[:len(asm.perm_cols)].copy()))
 
 
+def export_proving_key(pk: ProvingKey, selectors, f) -> None:
+    """`write_keys` for the proving key (src/io.rs:159-163): ProvingKey::write(RawBytes) to the binary file object `f`.
+    `selectors` are the activations before compression (Assembly.selectors).  The key's columns come back from the
+    device (zg_pk_read_column); the extended forms are rebuilt on halo2's zeta coset through the C ABI."""
+    from . import io as zio
+    ctx, k, cs = pk.ctx, pk.k, pk.cs
+    n = 1 << k
+    ext_k = k
+    while (1 << ext_k) < n * (cs.degree() - 1):
+        ext_k += 1
+
+    def col(what, i):
+        out = np.zeros((n, 4), dtype=np.uint64)
+        ctx._ck(ctx._L.zg_pk_read_column(ctx._h, pk._h, what, i, out.ctypes.data))
+        return out
+    nf, m = cs.num_fixed, len(cs.permutation)
+    fixed_values = [col(0, i) for i in range(nf)]
+    fixed_polys = [col(1, i) for i in range(nf)]
+    perm_values = [col(2, i) for i in range(m)]
+    perm_polys = [col(3, i) for i in range(m)]
+    ext = lambda c: ctx.coeff_to_extended(c, k, ext_k)
+    bf = cs.blinding_factors()
+    one = to_limbs([1])[0]
+
+    def unit_rows(rows):
+        v = np.zeros((n, 4), dtype=np.uint64)
+        v[list(rows)] = one
+        return ext(ctx.lagrange_to_coeff(v, k))
+    l0, l_last, l_blind = unit_rows([0]), unit_rows([n - bf - 1]), unit_rows(range(n - bf, n))
+    ones = np.tile(one, (1 << ext_k, 1))
+    l_active = ctx.debug_field_op(0, 4, ctx.debug_field_op(0, 4, ones, l_last), l_blind)      # 1 - l_last - l_blind (op 4 = sub)
+    words, constants, fc, pc = pk._vk_parts
+    vk = {"k": k, "fixed_commitments": fc, "perm_commitments": pc, "selectors": selectors}
+    zio.write_pk(f, vk, l0, l_last, l_active, fixed_values, fixed_polys, [ext(c) for c in fixed_polys], perm_values,
+                 perm_polys, [ext(c) for c in perm_polys])
+
+
+def export_verifying_key(pk: ProvingKey, selectors, f) -> None:
+    """`pk.get_vk().write(writer, RawBytes)` (src/io.rs:162)."""
+    from . import io as zio
+    _, _, fc, pc = pk._vk_parts
+    zio.write_vk(f, pk.k, fc, pc, selectors)
+
+
+def load_proving_key(ctx: zl.Context, params: ParamsKZG, cs, f, transcript_repr: int | None = None) -> ProvingKey:
+    """`read_pk` (src/io.rs:166-170): ProvingKey::read(RawBytes, circuit params) -> a key resident on the GPU.
+    `cs` is the circuit's constraint system as `configure` leaves it (BEFORE selector compression, exactly what the
+    Rust reader rebuilds from the circuit params); the file supplies the selector activations, the fixed columns and
+    the permutation columns.  Coefficient and extended forms are recomputed on the device (its extended domain is
+    internal), and the commitments it derives are checked against the file's."""
+    from . import io as zio
+    d = zio.read_pk(f, len(cs.permutation), len(cs.selectors))
+    if d["k"] != params.k:
+        raise ValueError("key file is for k = %d, parameters for k = %d" % (d["k"], params.k))
+    nf0 = cs.num_fixed
+    cs.compress_selectors(d["selectors"])                 # substitutes the selectors; the columns come from the file
+    if cs.num_fixed != d["fixed_commitments"].shape[0]:
+        raise ValueError("key file does not belong to this circuit (fixed column count)")
+    params.load(ctx)
+    words, constants = serialize_cs(cs)
+    fixed = [np.ascontiguousarray(c) for c in d["fixed_values"]]
+    sig = [np.ascontiguousarray(c) for c in d["perm_values"]]
+    desc = zl.PkDesc()
+    desc.k = params.k
+    desc.cs_words, desc.cs_nwords = words.ctypes.data, words.shape[0]
+    desc.constants, desc.n_constants = constants.ctypes.data, constants.shape[0]
+    fptr = (ctypes.c_void_p * max(len(fixed), 1))(*[a.ctypes.data for a in fixed])
+    sptr = (ctypes.c_void_p * max(len(sig), 1))(*[a.ctypes.data for a in sig])
+    desc.fixed = ctypes.cast(fptr, ctypes.c_void_p)
+    desc.perm_mapping = None
+    desc.sigma_values = ctypes.cast(sptr, ctypes.c_void_p)
+    h = ctypes.c_void_p()
+    ctx._ck(ctx._L.zg_pk_load(ctx._h, ctypes.byref(desc), ctypes.byref(h)))
+    fc = np.zeros((max(cs.num_fixed, 1), 8), dtype=np.uint64)
+    pc = np.zeros((max(len(sig), 1), 8), dtype=np.uint64)
+    ctx._ck(ctx._L.zg_pk_commitments(ctx._h, h, fc.ctypes.data, pc.ctypes.data))
+    if not ((fc[:cs.num_fixed] == d["fixed_commitments"]).all() and (pc[:len(sig)] == d["perm_commitments"]).all()):
+        ctx._L.zg_pk_free(ctx._h, h)
+        raise ValueError("key file: commitments do not match its columns under these parameters")
+    fixed_c, perm_c = _affine_points(fc[:cs.num_fixed]), _affine_points(pc[:len(sig)])
+    if transcript_repr is None:
+        transcript_repr = vk_transcript_repr(params.k, cs, fixed_c, perm_c)
+    repr_limbs = np.ascontiguousarray(to_limbs([transcript_repr])[0], dtype=np.uint64)
+    ctx._ck(ctx._L.zg_pk_set_transcript_repr(ctx._h, h, repr_limbs.ctypes.data))
+    return ProvingKey(ctx, h, params.k, cs, fixed_c, perm_c, transcript_repr,
+                      vk_parts=(words, constants, fc[:cs.num_fixed].copy(), pc[:len(sig)].copy()))
+
+
+def load_verifying_key(cs, f, transcript_repr: int | None = None) -> VerifyingKey:
+    """`read_vk` (src/io.rs:173-176): VerifyingKey::read(RawBytes, circuit params).  Host only."""
+    from . import io as zio
+    d = zio.read_vk(f, len(cs.permutation), len(cs.selectors))
+    if f.read(1):
+        raise ValueError("key file: trailing bytes")
+    cs.compress_selectors(d["selectors"])
+    words, constants = serialize_cs(cs)
+    fixed_c, perm_c = _affine_points(d["fixed_commitments"]), _affine_points(d["perm_commitments"])
+    if transcript_repr is None:
+        transcript_repr = vk_transcript_repr(d["k"], cs, fixed_c, perm_c)
+    return VerifyingKey(d["k"], words, constants, d["fixed_commitments"], d["perm_commitments"], transcript_repr)
+
+
 def advice_to_mont(ctx: zl.Context, advice_int) -> list:
     """host advice columns (canonical ints) -> Montgomery limb arrays, the form the C ABI takes."""
     return [ctx.debug_field_op(0, 7, ints_to_canonical(c)) for c in advice_int]

@@ -137,8 +137,11 @@ typedef struct {
   const uint32_t* cs_words; size_t cs_nwords;
   const zg_fr* constants; size_t n_constants;    /* constant pool of the expression programs */
   const zg_fr* const* fixed;                     /* num_fixed columns of 2^k Lagrange values */
-  const uint32_t* perm_mapping;                  /* [m][2^k][2]: (column, row) -> (column', row') of sigma */
+  const uint32_t* perm_mapping;                  /* [m][2^k][2]: (column, row) -> (column', row') of sigma; or NULL ... */
   zg_fr transcript_repr;                         /* VerifyingKey::transcript_repr, hashed first */
+  const zg_fr* const* sigma_values;              /* ... with the m permutation polynomials' Lagrange values given instead
+                                                  * (permutation::ProvingKey::permutations of a serialized key,
+                                                  * /root/reference/src/io.rs:166-170 read_pk); NULL when perm_mapping is set */
 } zg_pk_desc;
 
 /* keygen: commits fixed and sigma columns, builds coefficient + extended-coset forms, l_0/l_last/
@@ -150,6 +153,12 @@ void zg_pk_free(zg_ctx* ctx, zg_pk* pk);
 int zg_pk_set_transcript_repr(zg_ctx* ctx, zg_pk* pk, const zg_fr* transcript_repr);
 /* VerifyingKey: fixed_commitments (num_fixed) and permutation commitments (m), affine */
 int zg_pk_commitments(zg_ctx* ctx, const zg_pk* pk, zg_g1_affine* fixed_out, zg_g1_affine* sigma_out);
+/* Columns of a resident key, copied to the host (2^k elements): what `ProvingKey::write` serialises
+ * (/root/reference/src/io.rs:159-163 write_keys).  The extended-domain forms of the file format are halo2's
+ * (zeta coset of size 2^extended_k) and are rebuilt by the caller with zg_coeff_to_extended. */
+enum { ZG_PK_FIXED_VALUES = 0, ZG_PK_FIXED_POLYS = 1, ZG_PK_SIGMA_VALUES = 2, ZG_PK_SIGMA_POLYS = 3 };
+int zg_pk_read_column(zg_ctx* ctx, const zg_pk* pk, int what, uint32_t index, zg_fr* out);
+
 /* advice: num_advice columns of 2^k values, host pointers (or device pointers on the context's device: the
  * copy is direction-agnostic); rows >= 2^k - blinding_factors - 1 are replaced by blinding scalars; instances:
  * num_instance host columns with their lengths.  Writes the proof bytes.
@@ -191,6 +200,25 @@ int zg_evaluate_h(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice_polys, cons
                   const zg_fr* const* lookup_input_polys, const zg_fr* const* lookup_table_polys,
                   const zg_fr* const* lookup_product_polys, const zg_fr* const* perm_product_polys,
                   const zg_fr challenges[4], int divide, zg_fr* h_out);
+
+/* ---- multi-GPU (one process per GPU; NCCL over NVLink / NVSwitch) ---------------------------------------------
+ * SURVEY.md 8(e).  A context joins a communicator with zg_comm_init (rank 0 creates the id with zg_comm_unique_id and
+ * the host plumbing -- torch.distributed, MPI, a file -- hands its 128 bytes to the other ranks).  NCCL is loaded with
+ * dlopen at the first use; single-GPU users never touch it.
+ *  - zg_msm_sharded / _dev: ONE large MSM split by point range (BASELINE configs[3], [4]): the context's SRS holds this
+ *    rank's slice of the bases (zg_srs_load with the slice), `scalars` the matching slice; the G partial sums (96 B each)
+ *    are all-gathered and added on the device; every rank receives the total.
+ *  - zg_ctx_set_distribution(ZG_DIST_COLUMNS): zg_create_proof spreads the commitments of every Fiat-Shamir round over
+ *    the ranks (column j -> rank j mod G) and all-gathers the points.  Every rank must call zg_create_proof with the
+ *    same key, witness, instances and RNG stream (SPMD); every rank returns the same proof bytes. */
+enum { ZG_DIST_NONE = 0, ZG_DIST_COLUMNS = 1 };
+int zg_comm_unique_id(uint8_t out[128]);
+int zg_comm_init(zg_ctx* ctx, int nranks, int rank, const uint8_t unique_id[128]);
+int zg_comm_destroy(zg_ctx* ctx);
+int zg_ctx_set_distribution(zg_ctx* ctx, int mode);
+int zg_msm_sharded_dev(zg_ctx* ctx, int basis, const zg_fr* scalars_dev, size_t stride, size_t n_local, size_t count,
+                       zg_g1* out_dev);
+int zg_msm_sharded(zg_ctx* ctx, int basis, const zg_fr* scalars, size_t n_local, zg_g1* out);
 
 /* ---- verifier (host code, no GPU) ------------------------------------------------------------------------------
  * plonk::verify_proof::<KZGCommitmentScheme<Bn256>, VerifierGWC, _, EvmTranscript, SingleStrategy> as called by

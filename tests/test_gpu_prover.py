@@ -158,3 +158,47 @@ def test_large_shape_model_matches_oracle(ctx):
     srs = H.Srs(17, 0x1F3C5A7B9D2E4F60718293A4B5C6D7E8)
     outputs, ms = _parity(ctx, wnn, img, 17, srs)
     print("large stage ms", ms)
+
+
+def test_key_files_round_trip_through_the_gpu(ctx, tiny, tmp_path):
+    """write_keys / read_pk / read_vk (src/io.rs:159-176): a key exported in halo2's RawBytes layout and loaded again (fixed
+    and sigma columns from the file, everything else recomputed on the device) proves the same bytes; its extended
+    sections are halo2's zeta-coset forms and equal the oracle's; the vk file drives the host verifier."""
+    import zg_b200
+    from zg_b200 import io as zio
+    from zg_b200.prover import (ParamsKZG, create_proof, export_proving_key, export_verifying_key, keygen, load_proving_key,
+                                load_verifying_key)
+    wnn, img, k, srs = tiny
+    outputs = wnn.predict(img)
+    params = ParamsKZG(k, srs.g, srs.g_lagrange, srs.g2, srs.s_g2)
+    circ1, asm1 = wnn.synthesize(np.zeros((28, 28), dtype=np.uint8), k)
+    selectors = [list(s) for s in asm1.selectors]
+    pk = keygen(ctx, params, circ1.cs, asm1)
+    _, asm = wnn.synthesize(img, k)
+    proof = create_proof(params, pk, asm.advice, [outputs], zg_b200.lib.XorShift.from_seed(SEED))
+    pk_path, vk_path = tmp_path / "pk.bin", tmp_path / "vk.bin"
+    with open(pk_path, "wb") as f:
+        export_proving_key(pk, selectors, f)
+    with open(vk_path, "wb") as f:
+        export_verifying_key(pk, selectors, f)
+    # the file's sections against the oracle's key (same SRS): halo2's extended forms, not the backend's internal domain
+    circ0, asm0 = wnn.synthesize(np.zeros((28, 28), dtype=np.uint8), k)
+    opk = H.keygen(srs, circ0.cs, asm0)
+    d = zio.read_pk(open(pk_path, "rb"), len(asm0.perm_cols), len(selectors))
+    assert d["l0"].shape[0] == opk.domain.ext_n
+    for name, ref in (("fixed_values", opk.fixed_values), ("fixed_polys", opk.fixed_polys), ("fixed_cosets", opk.fixed_cosets),
+                      ("perm_values", opk.perm_values), ("perm_polys", opk.perm_polys), ("perm_cosets", opk.perm_cosets)):
+        assert all((a == b).all() for a, b in zip(d[name], ref)), name
+    assert (d["l0"] == opk.l0).all() and (d["l_last"] == opk.l_last).all() and (d["l_active_row"] == opk.l_active).all()
+    # load it back
+    circ2, _ = wnn.synthesize(np.zeros((28, 28), dtype=np.uint8), k)
+    pk2 = load_proving_key(ctx, params, circ2.cs, open(pk_path, "rb"))
+    assert pk2.fixed_commitments == pk.fixed_commitments and pk2.perm_commitments == pk.perm_commitments
+    assert pk2.transcript_repr == pk.transcript_repr
+    proof2 = create_proof(params, pk2, asm.advice, [outputs], zg_b200.lib.XorShift.from_seed(SEED))
+    assert proof2 == proof
+    circ3, _ = wnn.synthesize(np.zeros((28, 28), dtype=np.uint8), k)
+    vk = load_verifying_key(circ3.cs, open(vk_path, "rb"))
+    assert vk.verify(params, [outputs], proof2)
+    pk2.close()
+    pk.close()

@@ -118,3 +118,32 @@ def test_vk_create_rejects_malformed_blob(tiny_case):
     w[0] ^= 1
     with pytest.raises(zl.ZgError):
         VerifyingKey(vk.k, w, vk.constants, vk.fixed_limbs, vk.perm_limbs, 1)
+
+
+def test_vk_file_round_trip_verifies(tiny_case, tmp_path):
+    """write_keys / read_vk (src/io.rs:159-176): the verifying key written in halo2's RawBytes layout, read back against a
+    freshly configured circuit (selectors are re-compressed from the activations in the file) still verifies the proof."""
+    import io as pyio
+    from zg_b200 import io as zio
+    from zg_b200.prover import load_verifying_key
+    wnn, srs, opk, vk, params, out, proof = tiny_case
+    k = vk.k
+    circ, asm = wnn.synthesize(np.zeros(wnn.img_shape(), dtype=np.uint8), k)       # uncompressed constraint system
+    path = tmp_path / "vk.bin"
+    with open(path, "wb") as f:
+        zio.write_vk(f, k, vk.fixed_limbs, vk.perm_limbs, asm.selectors)
+    raw = open(path, "rb").read()
+    nsel, m, nf = len(circ.cs.selectors), len(circ.cs.permutation), vk.fixed_limbs.shape[0]
+    assert raw[:4] == k.to_bytes(4, "big") and raw[4:8] == nf.to_bytes(4, "big")
+    assert len(raw) == 8 + 64 * (nf + m) + nsel * ((1 << k) // 8)
+    circ2, _ = wnn.synthesize(np.zeros(wnn.img_shape(), dtype=np.uint8), k)
+    vk2 = load_verifying_key(circ2.cs, open(path, "rb"), transcript_repr=vk.transcript_repr)
+    assert (vk2.cs_words == vk.cs_words).all() and (vk2.constants == vk.constants).all()
+    assert vk2.verify(params, [out], proof)
+    # truncated / trailing bytes are rejected
+    circ3, _ = wnn.synthesize(np.zeros(wnn.img_shape(), dtype=np.uint8), k)
+    with pytest.raises(ValueError):
+        load_verifying_key(circ3.cs, pyio.BytesIO(raw[:-5]))
+    circ4, _ = wnn.synthesize(np.zeros(wnn.img_shape(), dtype=np.uint8), k)
+    with pytest.raises(ValueError):
+        load_verifying_key(circ4.cs, pyio.BytesIO(raw + b"\0"))
