@@ -3,10 +3,14 @@ torchrun; `torch.distributed` is plumbing only.
 
   * prove_many      independent proofs (BASELINE configs[4]): image i -> rank i mod world; every rank holds the
                     full SRS + proving key; NO data-path collective -- rank 0 gathers the ~3.8 KB proofs.
-  * sharded_msm     one large MSM split by point range (configs[3]): rank g owns bases [g n/G, (g+1) n/G) and
-                    receives the matching scalar slice; the G partial sums (96 B Jacobian points) are all-gathered
-                    and added locally.  EC addition is not an NCCL reduce op, so this is an all_gather, never an
-                    all_reduce.
+  * join_communicator + Context.msm_sharded / set_distribution: the NCCL paths INSIDE the library (csrc/dist.cu):
+                    one large MSM split by point range (configs[3]: rank g owns bases [g n/G, (g+1) n/G) and the
+                    matching scalar slice; ncclAllGather of the G 96-byte partial sums, G - 1 additions on the device),
+                    and one proof's commitment rounds spread over the ranks by column.  torch.distributed only
+                    carries the 128-byte NCCL id.
+  * sharded_msm     the same point-range split driven from the host with `torch.distributed.all_gather` (works on
+                    gloo: the CPU tests of the N > 1 host logic use it).  EC addition is not an NCCL reduce op, so
+                    this is an all_gather, never an all_reduce.
 NTT / quotient / lookup stages do not shard at these sizes (an all-to-all of 32-byte elements costs more than
 the single-GPU pass): replicas only.
 """
@@ -17,6 +21,18 @@ from typing import Callable, List, Sequence
 import numpy as np
 
 from .bn254_host import Q_MOD, from_limbs
+
+
+def join_communicator(ctx, dist=None) -> None:
+    """Gives `ctx` the library-level NCCL communicator of this job: rank 0 creates the id, torch.distributed
+    broadcasts its 128 bytes, every rank calls zg_comm_init.  No-op for a single process."""
+    from . import lib as zl
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return
+    rank, world = dist.get_rank(), dist.get_world_size()
+    box = [zl.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    ctx.comm_init(world, rank, box[0])
 
 
 def shard_indices(n_items: int, rank: int, world: int) -> List[int]:

@@ -13,6 +13,7 @@ Workloads:
                    `e2e`: image -> native witness synthesis -> proof bytes (what benches/bench.rs:30-36 times).
   msm              one 2^LOGN-point BN254 G1 MSM per step (uniform scalars)      -> points/s
   keygen           keygen_vk + keygen_pk of `--model` on the device (benches/bench.rs bench_key_generation)  -> keygens/s
+  verify           Wnn::verify_proof of one proof of `--model` (benches/bench.rs bench_verification; host code) -> verifications/s
   msm_sharded      ONE 2^LOGN-point MSM split by point range over the ranks, partial sums all-gathered (NCCL)
                    and added (strong scaling, BASELINE configs[3])                -> points/s
   ntt              one 2^LOGN-point BN254 Fr NTT per step                        -> GB/s (algorithmic)
@@ -68,6 +69,10 @@ def parse():
     ap.add_argument("--proofs-per-lane", type=int, default=int(os.environ.get("ZG_BENCH_PPL", "2")),
                     help="proof workload: proofs every lane proves back to back in one step (a step = inflight x this many "
                          "proofs); 2 keeps the default run's timed region above two seconds")
+    ap.add_argument("--shard", default=os.environ.get("ZG_BENCH_SHARD", "proofs"), choices=["proofs", "columns"],
+                    help="proof workload with N > 1 GPUs: `proofs` = independent proofs per GPU (weak scaling, no data-path "
+                         "collective); `columns` = ONE stream of proofs, every round's commitment MSMs spread over the ranks by "
+                         "column and all-gathered over NCCL (strong scaling of one proof, BASELINE configs[3]); one lane")
     ap.add_argument("--images", type=int, default=int(os.environ.get("ZG_BENCH_IMAGES", "1")),
                     help="proof workload: 1 = benches/example_image_7.png for every proof (the reference's bench input); "
                          "K > 1 = K distinct synthetic MNIST-shaped images per rank, proofs cycle through them "
@@ -286,10 +291,11 @@ def main():
         wnn, img, k = load_model(args.model)
         n = 1 << k
         srs = H.Srs(k, SRS_SECRET)
+        shard_cols = args.shard == "columns" and world > 1
         # the inputs every proof cycles through: (advice columns, public outputs) per image
         from zg_b200.io import synthetic_image
         nimg = max(1, args.images)
-        imgs = [img] if nimg == 1 else [synthetic_image(rank * nimg + i, wnn.img_shape()) for i in range(nimg)]
+        imgs = [img] if nimg == 1 else [synthetic_image((0 if shard_cols else rank * nimg) + i, wnn.img_shape()) for i in range(nimg)]
         witnesses = []
         usable_rows = None
         for im in imgs:
@@ -321,7 +327,7 @@ def main():
                     self.adv_host.append([t.numpy().view(np.uint64) for t in ht])
                     self.adv_dev_t.append(dt)
                     self.adv_dev.append([DevCol(t) for t in dt])
-                self.seed = rank * 100000 + idx * 1000
+                self.seed = (0 if shard_cols else rank * 100000) + idx * 1000     # SPMD: every rank draws the same stream
                 self.turn = idx                      # which image this lane proves next
 
             def rng(self):
@@ -344,10 +350,16 @@ def main():
                     return w, create_proof_limbs(self.pk, cols, [to_limbs(scores)], self.rng())
                 return w, create_proof_limbs(self.pk, self.adv_host[w], witnesses[w][2], self.rng())
 
-        K = max(1, args.inflight)
+        K = 1 if shard_cols else max(1, args.inflight)
         lane_streams = [stream] + [torch.cuda.Stream() for _ in range(K - 1)]
         lanes = [Lane(0, ctx)] + [Lane(i, zg_b200.Context(local, lane_streams[i].cuda_stream)) for i in range(1, K)]
         pk = lanes[0].pk
+        if shard_cols:
+            from zg_b200 import farm
+            farm.join_communicator(ctx, dist)
+            ctx.set_distribution(1)
+            extra["scaling_override"] = "strong"
+            extra["shard"] = "one proof stream; every round's commitments spread over %d GPUs by column, all-gathered (NCCL)" % world
         pool = ThreadPoolExecutor(K) if K > 1 else None
 
         PPL = max(1, args.proofs_per_lane)
@@ -363,19 +375,24 @@ def main():
         step_e2e = lambda: run_all("prove_e2e")
         # every measured proof is a real proof: check one per lane against the restated verifier (untimed)
         opk = None
-        if rank == 0:
-            circ_o, asm_o = wnn.synthesize(np.zeros(wnn.img_shape(), dtype=np.uint8), k)
-            opk = H.keygen(srs, circ_o.cs, asm_o)
-            assert pk.fixed_commitments == opk.fixed_commitments and pk.perm_commitments == opk.perm_commitments
+        if rank == 0 or shard_cols:                    # (column sharding: the proofs are collectives, every rank takes part)
+            if rank == 0:
+                circ_o, asm_o = wnn.synthesize(np.zeros(wnn.img_shape(), dtype=np.uint8), k)
+                opk = H.keygen(srs, circ_o.cs, asm_o)
+                assert pk.fixed_commitments == opk.fixed_commitments and pk.perm_commitments == opk.perm_commitments
+                vparams = ParamsKZG(k, srs.g, srs.g_lagrange, srs.g2, srs.s_g2)
             seen = set()
             for _ in range((len(witnesses) + K * PPL - 1) // (K * PPL) + 1):
                 for w, pr in step_e2e():
-                    if w not in seen:
+                    if rank == 0 and w not in seen:
                         assert H.verify_proof(srs, opk, [witnesses[w][1]], pr), "GPU proof rejected by the restated verifier"
+                        assert pk.get_vk().verify(vparams, [witnesses[w][1]], pr), "GPU proof rejected by the product verifier"
                         seen.add(w)
-            assert len(seen) == len(witnesses), "not every image was proven during the check"
+            assert rank != 0 or len(seen) == len(witnesses), "not every image was proven during the check"
         metric, unit, units = "proofs_per_s", "proofs/s", K * PPL
         h2d, d2h = units * (len(lanes[0].adv_host[0]) * n * 32 + len(outputs) * 32), units * 3840
+        if shard_cols:
+            units = units / world                      # ONE proof stream for the whole job: value = proofs / time
         dom_kernel = "msm_accumulate_kernel"
         extra["inflight"] = K
         extra["proofs_per_step"] = K * PPL
@@ -413,35 +430,27 @@ def main():
         sc_host = sc_host_t.numpy().view(np.uint64)
         sc_dev = sc_host_t.cuda()
         out_dev = torch.zeros(12, dtype=torch.int64, device="cuda")
-        gathered = [torch.zeros(12, dtype=torch.int64, device="cuda") for _ in range(world)]
         result = [None]
+        farm.join_communicator(ctx, dist if world > 1 else None)     # NCCL inside the library (csrc/dist.cu)
 
-        def gather_and_add():
-            if world > 1:
-                dist.all_gather(gathered, out_dev)
-                parts = torch.stack(gathered).cpu().numpy().view(np.uint64)
-            else:
-                parts = out_dev.cpu().numpy().view(np.uint64)[None]
-            result[0] = farm.combine_partials(parts)
+        def step_dev():      # local MSM over this rank's point range, ncclAllGather of 96 B, G - 1 adds on the device
+            ctx.msm_sharded_dev(0, sc_dev.data_ptr(), hi - lo, hi - lo, 1, out_dev.data_ptr())
 
-        def step_dev():
-            ctx.msm_dev(0, sc_dev.data_ptr(), hi - lo, hi - lo, 1, out_dev.data_ptr())
-            gather_and_add()
-
-        def step_e2e():
-            out_dev.copy_(torch.from_numpy(ctx.msm(0, sc_host).view(np.int64)))
-            gather_and_add()
+        def step_e2e():      # host scalars in, the total (96 B) back on the host of every rank
+            result[0] = ctx.msm_sharded(0, sc_host)
         metric, unit, units = "msm_points_per_s", "points/s", n / world      # value = n / time (units * world below)
         h2d, d2h = (hi - lo) * 32, 96 * world
         dom_kernel = "msm_accumulate_kernel"
         extra["scaling_override"] = "strong"
         if logn <= 20:
-            step_dev()                                 # a collective: every rank takes part, rank 0 checks
+            step_e2e()                                 # a collective: every rank takes part, rank 0 checks
+            step_dev()
         if rank == 0 and logn <= 20:
             import cpu_ref
             exp = cpu_ref.g1_to_affine(cpu_ref.best_multiexp(sc_full, bases))[0]
-            got = bn254.g1_affine_to_limbs([result[0]])[0] if result[0] is not None else np.zeros(8, dtype=np.uint64)
-            assert (np.asarray(got).reshape(-1) == np.asarray(exp).reshape(-1)).all(), "sharded MSM differs from the oracle"
+            for got_jac in (result[0], out_dev.cpu().numpy().view(np.uint64)):
+                got = cpu_ref.g1_to_affine(np.ascontiguousarray(got_jac, dtype=np.uint64).reshape(1, 12))[0]
+                assert (np.asarray(got).reshape(-1) == np.asarray(exp).reshape(-1)).all(), "sharded MSM differs from the oracle"
         if not args.no_cpu_baseline and rank == 0:
             import cpu_ref
             cpu_fn = lambda: cpu_ref.best_multiexp(sc_full, bases)
@@ -460,6 +469,29 @@ def main():
         if not args.no_cpu_baseline and rank == 0:
             import cpu_ref
             cpu_fn = lambda: cpu_ref.best_fft(a_host, w, logn)
+    elif args.workload == "verify":
+        # benches/bench.rs:38-45 `bench_verification`: Wnn::verify_proof (src/wnn.rs:265-280) of one proof.  Host work in the
+        # reference and here (csrc/verifier.cu: transcript, expression evaluation, one ~70-term MSM, two pairings); the GPU
+        # only produces the proof that is verified.
+        import halo2_ref as H
+        from zg_b200.prover import ParamsKZG, keygen
+        wnn, img, k = load_model(args.model)
+        n = 1 << k
+        srs = H.Srs(k, SRS_SECRET)
+        params = ParamsKZG(k, srs.g, srs.g_lagrange, srs.g2, srs.s_g2)
+        circ0, asm0 = wnn.synthesize(np.zeros(wnn.img_shape(), dtype=np.uint8), k)
+        vpk = keygen(ctx, params, circ0.cs, asm0)
+        proof, outs = wnn.proof(vpk, params, img)
+        vk = vpk.get_vk()
+        assert vk.verify(params, [outs], proof)
+
+        def step_dev():
+            assert vk.verify(params, [outs], proof)
+        step_e2e = step_dev
+        metric, unit, units = "verifications_per_s", "verifications/s", 1
+        h2d, d2h = 0, 0
+        dom_kernel = None
+        extra["note"] = "verification is host code by design (as in the reference); no kernel launches in the timed region"
     elif args.workload == "keygen":
         # keygen_vk + keygen_pk on the device (benches/bench.rs:24-28 `bench_key_generation`): commitments of the 16 fixed and
         # 8 sigma columns, their coefficient and extended-coset forms, l_0 / l_last / l_active.  Host circuit synthesis and
@@ -585,7 +617,7 @@ def main():
         roof = kernel_roofline(probe, imad_peak, ms, peak_src="measured in this run (zg_bench_int_pipe kind 0)",
                                traffic=NCU_TRAFFIC.get("%s_%d" % (args.workload, logn)))
         extra["survey_formula_roofline"] = step_roof
-    elif args.workload == "keygen":
+    elif args.workload in ("keygen", "verify"):
         roof = None                                # a secondary number: no roofline claim (24 MSMs + 27 extended NTTs + uploads)
     else:
         roof = kernel_roofline(probe, imad_peak, lat_ms * args.steps, peak_src="measured in this run (zg_bench_int_pipe kind 0)",

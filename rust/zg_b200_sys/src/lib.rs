@@ -20,8 +20,9 @@ pub struct zg_pk_desc {
     pub constants: *const Fr,
     pub n_constants: usize,
     pub fixed: *const *const Fr,
-    pub perm_mapping: *const u32,
+    pub perm_mapping: *const u32,        // or null, with sigma_values set (a key read from a file)
     pub transcript_repr: Fr,
+    pub sigma_values: *const *const Fr,
 }
 
 pub type zg_rng_fill_fn = unsafe extern "C" fn(state: *mut c_void, out: *mut u64, n: usize);
