@@ -55,14 +55,15 @@ int get_domain(zg_ctx* ctx, uint32_t logn, const Fr& omega, Domain** out) {
   Domain d;
   size_t n = (size_t)1 << logn;
   ZG_CUDA(cudaMalloc(&d.tw, sizeof(Fr) * n));
-  cudaError_t e = cudaMalloc(&d.flat, sizeof(Fr) * (n / 2 + 1));
+  Fr* flat = nullptr;
+  cudaError_t e = cudaMalloc(&flat, sizeof(Fr) * (n / 2 + 1));
   if (e == cudaSuccess) {
-    e = ntt_build_twiddles(d.tw, d.flat, omega, logn, ctx->stream);
+    e = ntt_build_twiddles(d.tw, flat, omega, logn, ctx->stream);
     ctx->launches += 2;
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   }
-  if (e != cudaSuccess) {                 // nothing stays allocated when the tables could not be built
-    if (d.flat) cudaFree(d.flat);
+  if (flat) cudaFree(flat);
+  if (e != cudaSuccess) {                 // nothing stays allocated when the table could not be built
     cudaFree(d.tw);
     return ctx->cuda_fail(e, "ntt_build_twiddles");
   }
@@ -101,7 +102,6 @@ static int ntt_generic_dev(zg_ctx* ctx, const Fr* in, size_t in_stride, Fr* out,
     P.tmp = (Fr*)ctx->ws_ntt.p;
   }
   P.tw = d->tw;
-  P.flat = d->flat;
   P.logn = logn;
   P.batch = (uint32_t)batch;
   P.n_in = n_in;
@@ -201,7 +201,7 @@ void zg_ctx_destroy(zg_ctx* ctx) {
     if (ctx->base[b]) cudaFree(ctx->base[b]);
     if (ctx->table[b].pts) cudaFree(ctx->table[b].pts);
   }
-  for (auto& kv : ctx->domains) { cudaFree(kv.second.tw); cudaFree(kv.second.flat); }
+  for (auto& kv : ctx->domains) cudaFree(kv.second.tw);
   if (ctx->ws_msm.p) cudaFree(ctx->ws_msm.p);
   if (ctx->ws_ntt.p) cudaFree(ctx->ws_ntt.p);
   if (ctx->ws_stage.p) cudaFree(ctx->ws_stage.p);

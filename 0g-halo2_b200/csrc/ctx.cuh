@@ -14,9 +14,8 @@
 
 namespace zg {
 
-struct Domain {       // twiddle tables for one (log_n, omega)
-  Fr* tw = nullptr;   // stage-major, n-1 entries (ntt.cu)
-  Fr* flat = nullptr; // omega^e, e < n/2 (ntt_fast.cu)
+struct Domain {       // twiddle table for one (log_n, omega)
+  Fr* tw = nullptr;   // stage-major, n-1 entries
 };
 
 struct Workspace {

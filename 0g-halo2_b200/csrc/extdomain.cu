@@ -136,7 +136,7 @@ int ext_from_coeff(zg_ctx* ctx, const ExtDomain& d, const Fr* coeff, size_t in_s
   P.in = coeff; P.in_stride = in_stride; P.in_coset_stride = 0;
   P.out = out; P.out_stride = out_stride; P.out_coset_stride = d.B;
   P.tmp = (Fr*)ctx->ws_ntt.p; P.tmp_stride = d.B;
-  P.tw = dom->tw; P.flat = dom->flat;
+  P.tw = dom->tw;
   P.logn = d.bk; P.batch = (uint32_t)batch; P.cosets = d.cosets;
   P.n_in = (uint32_t)d.n; P.n_out = (uint32_t)d.B; P.flags = 0;
   for (int i = 0; i < 3; i++) P.in_scale[i] = P.out_scale[i] = fp_one<FrParams>();
@@ -157,7 +157,7 @@ int ext_to_coeff(zg_ctx* ctx, const ExtDomain& d, const Fr* ext, Fr* work, size_
   P.in = ext; P.in_stride = d.N; P.in_coset_stride = d.B;
   P.out = d.cosets == 1 ? out : work; P.out_stride = d.N; P.out_coset_stride = d.B;
   P.tmp = (Fr*)ctx->ws_ntt.p; P.tmp_stride = d.B;
-  P.tw = dom->tw; P.flat = dom->flat;
+  P.tw = dom->tw;
   P.logn = d.bk; P.batch = 1; P.cosets = d.cosets;
   P.n_in = (uint32_t)d.B; P.n_out = d.cosets == 1 ? (uint32_t)keep : (uint32_t)d.B; P.flags = 0;
   for (int i = 0; i < 3; i++) P.in_scale[i] = P.out_scale[i] = fp_one<FrParams>();

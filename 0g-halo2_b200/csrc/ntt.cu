@@ -209,13 +209,6 @@ cudaError_t ntt_build_twiddles(Fr* tab, Fr* scratch_flat, const Fr& w, uint32_t 
 // Passes are planned top-down; every strided pass keeps lo >= NTT_LOGC.
 cudaError_t ntt_run(const NttPlan& P, cudaStream_t stream, uint64_t* nl) {
   const uint32_t logn = P.logn;
-  {
-    static const bool force_stagewise = getenv("ZG_NTT_STAGEWISE") != nullptr;     // A/B switch for profiling
-    static const bool force_fast = getenv("ZG_NTT_FAST") != nullptr;
-    if (!force_stagewise && P.flat && ntt_fast_supported(logn) &&
-        (force_fast || ntt_fast_pays(logn, P.batch * (P.cosets ? P.cosets : 1))))
-      return ntt_fast_run(P, stream, nl);
-  }
   uint32_t npass = (logn + NTT_MAX_S - 1) / NTT_MAX_S;
   if (npass == 0) npass = 1;
   // a lone small transform would run on a handful of CTAs: trade one more pass for a grid that covers the SMs

@@ -52,9 +52,8 @@ struct NttPlan {
   uint32_t n_in, n_out, flags;
   Fr in_scale[3];
   Fr out_scale[3];
-  // ntt_fast.cu (log n >= 12): flat twiddles w^e (e < n/2); `cosets` transforms per polynomial that differ in the
-  // per-element input table (coset c multiplies input i by in_table[c * in_table_stride + i]) or output table
-  const Fr* flat = nullptr;
+  // `cosets` transforms per polynomial that differ in the per-element input table (coset c multiplies input i by
+  // in_table[c * in_table_stride + i]) or output table: the prover's 3 x 2n extended domain (extdomain.cuh)
   uint32_t cosets = 1;
   size_t in_coset_stride = 0, out_coset_stride = 0;
   const Fr* in_table = nullptr;
@@ -63,28 +62,7 @@ struct NttPlan {
   size_t out_table_stride = 0;
 };
 
-// one pass of ntt_fast.cu
-struct NttFastArgs {
-  const Fr* in;
-  Fr* out;
-  size_t in_stride, out_stride, in_coset_stride, out_coset_stride;
-  const Fr* flat;
-  const Fr* in_table;
-  const Fr* out_table;
-  size_t in_table_stride, out_table_stride;
-  uint32_t logn, lo, hi_bits;      // this pass's digit occupies index bits [lo, lo + S); hi_bits digits above are done
-  uint32_t ndig, dig[4];           // widths of the finished digits, leading digit first (last pass: output permutation)
-  uint32_t n_in, n_out, cosets, flags;
-  uint32_t first, last;
-  Fr in_scale[3];
-  Fr out_scale[3];
-};
-bool ntt_fast_supported(uint32_t logn);
-bool ntt_fast_pays(uint32_t logn, uint32_t transforms);
-cudaError_t ntt_fast_run(const NttPlan& plan, cudaStream_t stream, uint64_t* launch_counter);
-
-// tab: stage-major table (n - 1 entries) for ntt.cu; flat: w^e for e < n/2 (kept: ntt_fast.cu reads it)
-cudaError_t ntt_build_twiddles(Fr* tab, Fr* flat, const Fr& w, uint32_t logn,
+cudaError_t ntt_build_twiddles(Fr* tab, Fr* scratch_flat, const Fr& w, uint32_t logn,
                                cudaStream_t stream);
 cudaError_t ntt_run(const NttPlan& plan, cudaStream_t stream, uint64_t* launch_counter);
 
