@@ -97,6 +97,47 @@ __global__ void __launch_bounds__(128) k_batch_invert(Fr* a, size_t n) {
   }
 }
 
+// Two-level form for long vectors.  One Fermat inversion (~380 products) per 16-element chunk makes the kernel above cost
+// ~27 products per element (0.44 ms for the 6 x 2^17 grand-product denominators of a k = 17 proof); here every thread
+// multiplies a strided chunk of BI2_CHUNK elements (coalesced: element i of thread t is a[i * T + t]), the T chunk products
+// are inverted by the kernel above, and a second pass turns them into the element inverses: 4 products per element.
+constexpr int BI2_CHUNK = 32;
+__global__ void __launch_bounds__(128) k_bi2_products(const Fr* __restrict__ a, size_t n, size_t T, Fr* __restrict__ totals) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  Fr acc = fp_one<FrParams>();
+  for (int i = 0; i < BI2_CHUNK; i++) {
+    size_t idx = (size_t)i * T + t;
+    if (idx >= n) break;
+    Fr x = ldf(a + idx);
+    if (!fp_is_zero(x)) acc = fp_mul(acc, x);
+  }
+  stf(totals + t, acc);
+}
+__global__ void __launch_bounds__(128) k_bi2_apply(Fr* __restrict__ a, size_t n, size_t T, const Fr* __restrict__ totals_inv) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  Fr pre[BI2_CHUNK];
+  Fr acc = fp_one<FrParams>();
+  int len = 0;
+  for (int i = 0; i < BI2_CHUNK; i++) {
+    size_t idx = (size_t)i * T + t;
+    if (idx >= n) break;
+    pre[i] = acc;
+    Fr x = ldf(a + idx);
+    if (!fp_is_zero(x)) acc = fp_mul(acc, x);
+    len = i + 1;
+  }
+  Fr inv = ldf(totals_inv + t);
+  for (int i = len - 1; i >= 0; i--) {
+    size_t idx = (size_t)i * T + t;
+    Fr x = ldf(a + idx);
+    if (fp_is_zero(x)) continue;
+    stf(a + idx, fp_mul(inv, pre[i]));
+    inv = fp_mul(inv, x);
+  }
+}
+
 // ---- scans ---------------------------------------------------------------------------------------
 struct ScanGeom {
   uint32_t chunks, len;
@@ -221,7 +262,7 @@ __global__ void k_kd_apply(const Fr* __restrict__ a, size_t n, Fr zz, uint32_t l
 }
 
 // ---- evaluation at points ---------------------------------------------------------------------------
-constexpr int EV_PER_THREAD = 16;
+constexpr int EV_PER_THREAD = 64;   // Horner run per thread; its x^(64 t) offset is (x^64)^t: ~1.35 products per coefficient
 constexpr int EV_THREADS = 256;
 // grid (blocks, count); partial[j * gridDim.x + blockIdx.x]
 __global__ void __launch_bounds__(EV_THREADS) k_eval_partial(const Fr* const* __restrict__ polys, const uint32_t* __restrict__ pidx,
@@ -236,7 +277,10 @@ __global__ void __launch_bounds__(EV_THREADS) k_eval_partial(const Fr* const* __
   if (b < n) {
     size_t e = b + EV_PER_THREAD < n ? b + EV_PER_THREAD : n;
     for (size_t i = e; i-- > b;) acc = fp_add(fp_mul(acc, x), ldf(p + i));
-    acc = fp_mul(acc, fp_pow_var(x, (uint64_t)b));
+    Fr xs = x;
+#pragma unroll 1
+    for (int sq = 1; sq < EV_PER_THREAD; sq <<= 1) xs = fp_sqr(xs);       // x^EV_PER_THREAD
+    acc = fp_mul(acc, fp_pow_var(xs, (uint64_t)t));
   }
   sm[threadIdx.x] = acc;
   __syncthreads();
@@ -428,8 +472,18 @@ void fr_scatter_rows(Fr* a, const uint32_t* idx_dev, const Fr* v_dev, uint32_t m
   k_scatter_rows<<<blocks_for(m, 64), 64, 0, st>>>(a, idx_dev, v_dev, m);
   lc++;
 }
-void fr_batch_invert(Fr* a, size_t n, cudaStream_t st, LaunchCounter lc) {
+void fr_batch_invert(Fr* a, size_t n, cudaStream_t st, LaunchCounter lc, Fr* scratch) {
   if (!n) return;
+  if (scratch && n >= (size_t)1 << 14) {        // two-level: chunk products -> their inverses -> element inverses
+    const size_t T = (n + BI2_CHUNK - 1) / BI2_CHUNK;
+    k_bi2_products<<<blocks_for(T, 128), 128, 0, st>>>(a, n, T, scratch);
+    lc++;
+    k_batch_invert<<<blocks_for((T + BI_CHUNK - 1) / BI_CHUNK, 128), 128, 0, st>>>(scratch, T);
+    lc++;
+    k_bi2_apply<<<blocks_for(T, 128), 128, 0, st>>>(a, n, T, scratch);
+    lc++;
+    return;
+  }
   size_t threads = (n + BI_CHUNK - 1) / BI_CHUNK;
   k_batch_invert<<<blocks_for(threads, 128), 128, 0, st>>>(a, n);
   lc++;

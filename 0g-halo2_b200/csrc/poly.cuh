@@ -23,7 +23,8 @@ void fr_one_minus_sum(const Fr* a, const Fr* b, Fr* out, size_t n, cudaStream_t 
 void fr_scatter_rows(Fr* a, const uint32_t* idx_dev, const Fr* v_dev, uint32_t m, cudaStream_t st, LaunchCounter lc);
 
 // batch inversion in place (zeros stay zero), Montgomery trick per thread chunk
-void fr_batch_invert(Fr* a, size_t n, cudaStream_t st, LaunchCounter lc);
+// scratch (optional): ceil(n / 32) elements; enables the two-level form for n >= 2^14
+void fr_batch_invert(Fr* a, size_t n, cudaStream_t st, LaunchCounter lc, Fr* scratch = nullptr);
 // z[0] = *start_dev, z[i] = z[i-1] * f[i-1] for i < n_out  (grand products); scratch >= 3 * 2048 Fr
 void fr_running_product(const Fr* f, const Fr* start_dev, Fr* z, size_t n_out, Fr* scratch, cudaStream_t st,
                         LaunchCounter lc);

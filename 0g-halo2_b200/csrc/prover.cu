@@ -1012,7 +1012,7 @@ static int create_proof_impl(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice,
     for (uint32_t l = 0; l < Lk; l++)
       lookup_fraction(pk->ci + l * n, pk->ct + l * n, pk->pa + l * n, pk->ps + l * n, beta, gamma, num + (S + l) * n, den + (S + l) * n, n,
                       st, lc);
-    fr_batch_invert(den, (size_t)cnt * n, st, lc);
+    fr_batch_invert(den, (size_t)cnt * n, st, lc, pk->wpoly);       // wpoly (8n) is free until the scan below
     fr_mul_vec(num, den, den, (size_t)cnt * n, st, lc);
     std::vector<uint32_t> nout(cnt);
     for (uint32_t s = 0; s < S; s++) nout[s] = (uint32_t)n;
