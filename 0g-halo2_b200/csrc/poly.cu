@@ -75,24 +75,40 @@ __global__ void k_scatter_rows(Fr* a, const uint32_t* __restrict__ idx, const Fr
 }
 
 // ---- batch inversion --------------------------------------------------------------------------
+template <class P>
+__device__ __forceinline__ Fp<P> ldp(const Fp<P>* p) {
+  Fp<P> r;
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = q[0], b = q[1];
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+template <class P>
+__device__ __forceinline__ void stp(Fp<P>* p, const Fp<P>& r) {
+  uint4* q = reinterpret_cast<uint4*>(p);
+  q[0] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+  q[1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
 constexpr int BI_CHUNK = 16;
-__global__ void __launch_bounds__(128) k_batch_invert(Fr* a, size_t n) {
+template <class P>
+__global__ void __launch_bounds__(128) k_batch_invert(Fp<P>* a, size_t n) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t b = t * BI_CHUNK;
   if (b >= n) return;
   int len = (int)((n - b < (size_t)BI_CHUNK) ? (n - b) : BI_CHUNK);
-  Fr pre[BI_CHUNK];
-  Fr acc = fp_one<FrParams>();
+  Fp<P> pre[BI_CHUNK];
+  Fp<P> acc = fp_one<P>();
   for (int i = 0; i < len; i++) {
     pre[i] = acc;
-    Fr x = ldf(a + b + i);
+    Fp<P> x = ldp(a + b + i);
     if (!fp_is_zero(x)) acc = fp_mul(acc, x);
   }
-  Fr inv = fp_inv(acc);
+  Fp<P> inv = fp_inv(acc);
   for (int i = len - 1; i >= 0; i--) {
-    Fr x = ldf(a + b + i);
+    Fp<P> x = ldp(a + b + i);
     if (fp_is_zero(x)) continue;
-    stf(a + b + i, fp_mul(inv, pre[i]));
+    stp(a + b + i, fp_mul(inv, pre[i]));
     inv = fp_mul(inv, x);
   }
 }
@@ -102,38 +118,40 @@ __global__ void __launch_bounds__(128) k_batch_invert(Fr* a, size_t n) {
 // multiplies a strided chunk of BI2_CHUNK elements (coalesced: element i of thread t is a[i * T + t]), the T chunk products
 // are inverted by the kernel above, and a second pass turns them into the element inverses: 4 products per element.
 constexpr int BI2_CHUNK = 32;
-__global__ void __launch_bounds__(128) k_bi2_products(const Fr* __restrict__ a, size_t n, size_t T, Fr* __restrict__ totals) {
+template <class P>
+__global__ void __launch_bounds__(128) k_bi2_products(const Fp<P>* __restrict__ a, size_t n, size_t T, Fp<P>* __restrict__ totals) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
-  Fr acc = fp_one<FrParams>();
+  Fp<P> acc = fp_one<P>();
   for (int i = 0; i < BI2_CHUNK; i++) {
     size_t idx = (size_t)i * T + t;
     if (idx >= n) break;
-    Fr x = ldf(a + idx);
+    Fp<P> x = ldp(a + idx);
     if (!fp_is_zero(x)) acc = fp_mul(acc, x);
   }
-  stf(totals + t, acc);
+  stp(totals + t, acc);
 }
-__global__ void __launch_bounds__(128) k_bi2_apply(Fr* __restrict__ a, size_t n, size_t T, const Fr* __restrict__ totals_inv) {
+template <class P>
+__global__ void __launch_bounds__(128) k_bi2_apply(Fp<P>* __restrict__ a, size_t n, size_t T, const Fp<P>* __restrict__ totals_inv) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
-  Fr pre[BI2_CHUNK];
-  Fr acc = fp_one<FrParams>();
+  Fp<P> pre[BI2_CHUNK];
+  Fp<P> acc = fp_one<P>();
   int len = 0;
   for (int i = 0; i < BI2_CHUNK; i++) {
     size_t idx = (size_t)i * T + t;
     if (idx >= n) break;
     pre[i] = acc;
-    Fr x = ldf(a + idx);
+    Fp<P> x = ldp(a + idx);
     if (!fp_is_zero(x)) acc = fp_mul(acc, x);
     len = i + 1;
   }
-  Fr inv = ldf(totals_inv + t);
+  Fp<P> inv = ldp(totals_inv + t);
   for (int i = len - 1; i >= 0; i--) {
     size_t idx = (size_t)i * T + t;
-    Fr x = ldf(a + idx);
+    Fp<P> x = ldp(a + idx);
     if (fp_is_zero(x)) continue;
-    stf(a + idx, fp_mul(inv, pre[i]));
+    stp(a + idx, fp_mul(inv, pre[i]));
     inv = fp_mul(inv, x);
   }
 }
@@ -472,22 +490,25 @@ void fr_scatter_rows(Fr* a, const uint32_t* idx_dev, const Fr* v_dev, uint32_t m
   k_scatter_rows<<<blocks_for(m, 64), 64, 0, st>>>(a, idx_dev, v_dev, m);
   lc++;
 }
-void fr_batch_invert(Fr* a, size_t n, cudaStream_t st, LaunchCounter lc, Fr* scratch) {
+template <class P>
+static void batch_invert_any(Fp<P>* a, size_t n, cudaStream_t st, LaunchCounter lc, Fp<P>* scratch) {
   if (!n) return;
   if (scratch && n >= (size_t)1 << 14) {        // two-level: chunk products -> their inverses -> element inverses
     const size_t T = (n + BI2_CHUNK - 1) / BI2_CHUNK;
-    k_bi2_products<<<blocks_for(T, 128), 128, 0, st>>>(a, n, T, scratch);
+    k_bi2_products<P><<<blocks_for(T, 128), 128, 0, st>>>(a, n, T, scratch);
     lc++;
-    k_batch_invert<<<blocks_for((T + BI_CHUNK - 1) / BI_CHUNK, 128), 128, 0, st>>>(scratch, T);
+    k_batch_invert<P><<<blocks_for((T + BI_CHUNK - 1) / BI_CHUNK, 128), 128, 0, st>>>(scratch, T);
     lc++;
-    k_bi2_apply<<<blocks_for(T, 128), 128, 0, st>>>(a, n, T, scratch);
+    k_bi2_apply<P><<<blocks_for(T, 128), 128, 0, st>>>(a, n, T, scratch);
     lc++;
     return;
   }
   size_t threads = (n + BI_CHUNK - 1) / BI_CHUNK;
-  k_batch_invert<<<blocks_for(threads, 128), 128, 0, st>>>(a, n);
+  k_batch_invert<P><<<blocks_for(threads, 128), 128, 0, st>>>(a, n);
   lc++;
 }
+void fr_batch_invert(Fr* a, size_t n, cudaStream_t st, LaunchCounter lc, Fr* scratch) { batch_invert_any<FrParams>(a, n, st, lc, scratch); }
+void fq_batch_invert(Fq* a, size_t n, cudaStream_t st, LaunchCounter lc, Fq* scratch) { batch_invert_any<FqParams>(a, n, st, lc, scratch); }
 void fr_running_product(const Fr* f, const Fr* start_dev, Fr* z, size_t n_out, Fr* scratch, cudaStream_t st, LaunchCounter lc) {
   if (!n_out) return;
   // chunks are laid over z (n_out entries); chunk c's product covers f[c*len .. (c+1)*len)

@@ -179,12 +179,6 @@ def kernel_roofline(probe, imad_peak, region_ms, peak_src, traffic=None):
                     "per launch (profiles/ncu_traffic.json) when captured for this workload"}
 
 
-def proof_msm_imad(n, k):
-    """30 MSMs per proof at the window the backend uses for 2^k points."""
-    c = max(8, min(16, k - 2))
-    return 30 * msm_imad(n, c), c
-
-
 # ---- the proof workload: model, witness, SRS -----------------------------------------------------------
 def load_model(name):
     from zg_b200.io import load_wnn, load_grayscale_image, synthetic_wnn
@@ -609,7 +603,7 @@ def main():
     elif args.workload in ("msm", "msm_sharded"):
         nl = n // world if args.workload == "msm_sharded" else n           # points per GPU
         ll = nl.bit_length() - 1
-        c = int(os.environ.get("ZG_MSM_C", "0")) or max(8, min(16, ll - 2))
+        c = int(os.environ.get("ZG_MSM_C", "0")) or (16 if ll >= 17 else max(8, ll - 2))
         ach = msm_imad(nl, c) / 1e9 / (ms_per_step * 1e-3)
         step_roof = {"bound": "int", "achieved": ach, "peak": imad_peak, "unit": "GIMAD/s", "frac": ach / imad_peak,
                      "window_c": c, "note": "SURVEY 8(d) per-window formula IMAD(N, c) / step time; it OVER-COUNTS for this fixed-base "
