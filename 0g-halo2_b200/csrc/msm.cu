@@ -27,7 +27,6 @@
 #include <atomic>
 #include <cstdlib>
 #include "msm.cuh"
-#include "msm_ba.cuh"
 #include "scan.cuh"
 
 namespace zg {
@@ -261,15 +260,6 @@ uint32_t msm_pick_c(uint32_t k) {
   return (uint32_t)c;
 }
 
-int msm_pick_ba_rounds(uint64_t entries_max) {
-  if (const char* e = getenv("ZG_MSM_BA")) {
-    int v = atoi(e);
-    if (v >= 0 && v <= 4) return v;
-  }
-  (void)entries_max;
-  return 0;
-}
-
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 MsmWorkspaceLayout msm_workspace_layout(uint32_t n, uint32_t c, uint32_t W, uint32_t M) {
@@ -324,11 +314,6 @@ MsmWorkspaceLayout msm_workspace_layout(uint32_t n, uint32_t c, uint32_t W, uint
   l.off_t1 = o; o = align_up(o + (size_t)M * n1 * sizeof(G1Xyzz));
   l.off_l2 = o; o = align_up(o + (size_t)M * 3 * ((n1 + 31) / 32) * sizeof(G1Xyzz));
   l.off_scan = o; o = align_up(o + scan_scratch_words((uint32_t)cnt, 1) * 4);
-  l.ba_rounds = msm_pick_ba_rounds(lmax);
-  if (l.ba_rounds) {
-    l.off_ba = o;
-    o = align_up(o + ba_workspace_bytes(l.L_max, (uint32_t)cnt, l.ba_rounds));
-  }
   l.bytes = o;
   return l;
 }
@@ -383,22 +368,7 @@ cudaError_t msm_run(const MsmTable& tb, const Fr* scalars, size_t stride, uint32
   msm_hist_offsets_kernel<<<(cnt + 255) / 256, 256, 0, st>>>(H, l.J, NB, cnt, offsets);
   launches++;
   msm_digits_kernel<true><<<dgrid, DG_THREADS, dsm, st>>>(scalars, stride, n_used, tb.n, tb.c, tb.W, NB, l.chunk, H, entries);
-  // optional batched-affine halving rounds: the accumulation then reads the reduced list of materialised points
-  const uint2* acc_entries = entries;
-  const uint32_t* acc_count = offsets + cnt;
-  const G1Affine* acc_tab = tb.pts;
-  const G1Affine* acc_alt = alt_pts ? alt_pts : tb.pts;
-  uint32_t acc_alt_mask = alt_pts ? alt_mask : 0u;
-  if (l.ba_rounds) {
-    BaSrc s0{entries, tb.pts, acc_alt, acc_alt_mask, tb.c - 1};
-    BaSrc red;
-    cudaError_t be = ba_reduce(s0, offsets, cnt, l.L_max, l.ba_rounds, ws + l.off_ba, st, &launches, &red, &acc_count);
-    if (be != cudaSuccess) return be;
-    acc_entries = red.ent;
-    acc_tab = acc_alt = red.tab;
-    acc_alt_mask = 0;
-  }
-  // level 0: serial chunks over the sorted list (length *acc_count, read on device)
+  // level 0: serial chunks over the sorted list (length offsets[cnt], read on device)
   uint32_t T0 = l.T0;
   launches++;
   const bool probing = probe && probe->on && probe->used < probe->cap;
@@ -410,11 +380,11 @@ cudaError_t msm_run(const MsmTable& tb, const Fr* scalars, size_t stride, uint32
     }
     cudaEventRecord(probe->ev[2 * probe->used], st);
   }
-  msm_accumulate_kernel<<<(T0 + 127) / 128, 128, 0, st>>>(acc_entries, acc_count, acc_tab, acc_alt, acc_alt_mask, tb.c - 1, l.K0,
-                                                          buckets, pk[0], pp[0], T0);
+  msm_accumulate_kernel<<<(T0 + 127) / 128, 128, 0, st>>>(entries, offsets + cnt, tb.pts, alt_pts ? alt_pts : tb.pts,
+                                                          alt_pts ? alt_mask : 0u, tb.c - 1, l.K0, buckets, pk[0], pp[0], T0);
   if (probing) {
     cudaEventRecord(probe->ev[2 * probe->used + 1], st);
-    cudaMemcpyAsync(probe->counts + probe->used, acc_count, 4, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(probe->counts + probe->used, offsets + cnt, 4, cudaMemcpyDeviceToHost, st);
     probe->used++;
   }
   uint32_t slots = 2 * T0;

@@ -26,11 +26,7 @@ struct MsmWorkspaceLayout {
   size_t off_pkeys_a, off_ppts_a, off_pkeys_b, off_ppts_b, off_s1, off_t1, off_l2, off_scan;
   uint32_t L_max, K0, T0, slots_a, slots_b, NB, M;
   uint32_t J, chunk;   // digit sort: J chunks of `chunk` scalars per MSM
-  int ba_rounds = 0;   // batched-affine halving rounds ahead of the XYZZ accumulation (msm_ba.cu)
-  size_t off_ba = 0;
 };
-// rounds used for a batch of this size (0 below the size where the extra launches pay; ZG_MSM_BA overrides)
-int msm_pick_ba_rounds(uint64_t entries_max);
 MsmWorkspaceLayout msm_workspace_layout(uint32_t n, uint32_t c, uint32_t W, uint32_t M);
 
 // Optional live timing of the level-0 accumulation kernel (the dominant kernel of the path): every launch is bracketed

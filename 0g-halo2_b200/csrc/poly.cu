@@ -508,7 +508,6 @@ static void batch_invert_any(Fp<P>* a, size_t n, cudaStream_t st, LaunchCounter 
   lc++;
 }
 void fr_batch_invert(Fr* a, size_t n, cudaStream_t st, LaunchCounter lc, Fr* scratch) { batch_invert_any<FrParams>(a, n, st, lc, scratch); }
-void fq_batch_invert(Fq* a, size_t n, cudaStream_t st, LaunchCounter lc, Fq* scratch) { batch_invert_any<FqParams>(a, n, st, lc, scratch); }
 void fr_running_product(const Fr* f, const Fr* start_dev, Fr* z, size_t n_out, Fr* scratch, cudaStream_t st, LaunchCounter lc) {
   if (!n_out) return;
   // chunks are laid over z (n_out entries); chunk c's product covers f[c*len .. (c+1)*len)

@@ -29,7 +29,7 @@ EXPORTS = [
     "zg_srs_load", "zg_msm", "zg_msm_batch", "zg_msm_dev",
     "zg_ntt", "zg_ntt_dev", "zg_lagrange_to_coeff", "zg_lagrange_to_coeff_dev",
     "zg_coeff_to_extended", "zg_coeff_to_extended_dev", "zg_extended_to_coeff", "zg_extended_to_coeff_dev",
-    "zg_bench_int_pipe", "zg_debug_field_op", "zg_debug_keccak256", "zg_probe_enable", "zg_probe_read", "zg_debug_ba_selftest",
+    "zg_bench_int_pipe", "zg_debug_field_op", "zg_debug_keccak256", "zg_probe_enable", "zg_probe_read",
     "zg_xorshift_seed", "zg_xorshift_fill", "zg_chacha20_seed_os", "zg_chacha20_seed", "zg_chacha20_fill", "zg_pk_load", "zg_pk_read_column", "zg_pk_free", "zg_pk_commitments", "zg_create_proof",
     "zg_pk_last_stage_ms", "zg_pk_set_transcript_repr",
     "zg_wnn_create", "zg_wnn_free", "zg_wnn_last_error", "zg_wnn_synthesize",
@@ -88,7 +88,6 @@ def load_library() -> ctypes.CDLL:
     L.zg_debug_field_op.argtypes = [vp, ci, ci, vp, vp, vp, sz]
     L.zg_debug_keccak256.argtypes = [vp, sz, vp]
     L.zg_debug_keccak256.restype = None
-    L.zg_debug_ba_selftest.argtypes = [u32, u32, ci, u32]
     L.zg_probe_enable.argtypes = [vp, ci]
     L.zg_probe_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u64), ctypes.POINTER(u64)]
     L.zg_xorshift_seed.argtypes = [vp, vp]

@@ -201,11 +201,6 @@ int zg_evaluate_h(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice_polys, cons
                   const zg_fr* const* lookup_product_polys, const zg_fr* const* perm_product_polys,
                   const zg_fr challenges[4], int divide, zg_fr* h_out);
 
-/* host-only self-test of the batched-affine bucket pre-reduction (csrc/msm_ba.cu): the per-thread code of its kernels run
- * thread by thread on the CPU over a synthetic sorted list with heavy / empty buckets, doublings, P + (-P) and identity
- * points, compared with plain XYZZ bucket sums.  0 = agree.  (No GPU: lets the CPU test suite cover the pairing logic.) */
-int zg_debug_ba_selftest(uint32_t n_buckets, uint32_t max_per_bucket, int rounds, uint32_t seed);
-
 /* ---- multi-GPU (one process per GPU; NCCL over NVLink / NVSwitch) ---------------------------------------------
  * SURVEY.md 8(e).  A context joins a communicator with zg_comm_init (rank 0 creates the id with zg_comm_unique_id and
  * the host plumbing -- torch.distributed, MPI, a file -- hands its 128 bytes to the other ranks).  NCCL is loaded with

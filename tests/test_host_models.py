@@ -177,13 +177,3 @@ def test_fp64_montgomery_multiplication_prototype():
         got = [sum(int(O[i, j]) << (64 * j) for j in range(4)) for i in range(n)]
         assert got == [x * y * rinv % mod for x, y in zip(a, b)]
 
-
-def test_batched_affine_prereduction_host_selftest():
-    """csrc/msm_ba.cu: the per-thread code of the batched-affine halving rounds, executed thread by thread on the CPU over
-    synthetic sorted (bucket, point) lists -- heavy and empty buckets, equal points (doubling), P + (-P), identity
-    operands -- against plain XYZZ bucket sums (zg_debug_ba_selftest returns 0 when every bucket agrees)."""
-    import zg_b200.lib as zl
-    L = zl.load_library()
-    for nb, mx, rounds, seed in [(40, 5, 1, 1), (40, 5, 2, 2), (64, 9, 3, 3), (33, 40, 2, 4), (16, 1, 2, 5), (50, 3, 4, 6),
-                                 (97, 17, 2, 7), (7, 0, 2, 8)]:
-        assert L.zg_debug_ba_selftest(nb, mx, rounds, seed) == 0, (nb, mx, rounds, seed)
