@@ -7,9 +7,7 @@
 // msm.cu, poly.cu, expr.cu and lookup.cu; the host only sequences rounds, hashes (keccak256) and
 // normalises <= 8 commitments per round.  Witness synthesis is the caller's (BASELINE north_star).
 #include <algorithm>
-#include <cerrno>
 #include <memory>
-#include <sys/random.h>
 #include "ctx.cuh"
 #include "expr.cuh"
 #include "extdomain.cuh"
@@ -446,65 +444,6 @@ void zg_xorshift_fill(void* state, uint64_t* out, size_t n) {
     out[i] = lo | ((uint64_t)w << 32);
   }
   r->x = x; r->y = y; r->z = z; r->w = w;
-}
-
-// ---- ChaCha20 keystream RNG (RFC 8439 block function; 64-bit counter in words 12-13, nonce in 14-15) -----------------
-static inline uint32_t rotl32(uint32_t v, int c) { return (v << c) | (v >> (32 - c)); }
-#define ZG_QR(a, b, c, d) \
-  a += b; d ^= a; d = rotl32(d, 16); c += d; b ^= c; b = rotl32(b, 12); a += b; d ^= a; d = rotl32(d, 8); c += d; b ^= c; b = rotl32(b, 7);
-static void chacha20_block(const zg_chacha20* r, uint64_t counter, uint8_t out[64]) {
-  uint32_t in[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u};
-  for (int i = 0; i < 8; i++) in[4 + i] = r->key[i];
-  in[12] = (uint32_t)counter; in[13] = (uint32_t)(counter >> 32); in[14] = r->nonce[0]; in[15] = r->nonce[1];
-  uint32_t x[16];
-  memcpy(x, in, sizeof(x));
-  for (int round = 0; round < 10; round++) {
-    ZG_QR(x[0], x[4], x[8], x[12]) ZG_QR(x[1], x[5], x[9], x[13]) ZG_QR(x[2], x[6], x[10], x[14]) ZG_QR(x[3], x[7], x[11], x[15])
-    ZG_QR(x[0], x[5], x[10], x[15]) ZG_QR(x[1], x[6], x[11], x[12]) ZG_QR(x[2], x[7], x[8], x[13]) ZG_QR(x[3], x[4], x[9], x[14])
-  }
-  for (int i = 0; i < 16; i++) {
-    const uint32_t v = x[i] + in[i];
-    memcpy(out + 4 * i, &v, 4);            // little-endian hosts only (x86-64 / aarch64)
-  }
-}
-#undef ZG_QR
-void zg_chacha20_seed(zg_chacha20* r, const uint8_t key[32]) {
-  memset(r, 0, sizeof(*r));
-  memcpy(r->key, key, 32);
-}
-int zg_chacha20_seed_os(zg_chacha20* r) {
-  uint8_t key[32];
-  size_t got = 0;
-  while (got < sizeof(key)) {
-    ssize_t k = getrandom(key + got, sizeof(key) - got, 0);
-    if (k < 0) {
-      if (errno == EINTR) continue;
-      return ZG_E_STATE;
-    }
-    got += (size_t)k;
-  }
-  zg_chacha20_seed(r, key);
-  memset(key, 0, sizeof(key));
-  return ZG_OK;
-}
-void zg_chacha20_fill(void* state, uint64_t* out, size_t n) {
-  zg_chacha20* r = (zg_chacha20*)state;
-  uint8_t* dst = (uint8_t*)out;
-  size_t left = n * 8;
-  while (left) {
-    if (!r->have) {
-      if (left >= 64) {                    // whole blocks go straight to the destination
-        chacha20_block(r, r->counter++, dst);
-        dst += 64; left -= 64;
-        continue;
-      }
-      chacha20_block(r, r->counter++, r->buf);
-      r->have = 64;
-    }
-    const size_t take = left < r->have ? left : r->have;
-    memcpy(dst, r->buf + (64 - r->have), take);
-    r->have -= (uint32_t)take; dst += take; left -= take;
-  }
 }
 
 void zg_pk_free(zg_ctx* ctx, zg_pk* pk) {

@@ -3,8 +3,9 @@
 `Wnn::proof` (/root/reference/src/wnn.rs:232-262) proves one image at a time; a proof of this size leaves a B200 idle
 during its latency-bound stretches (MSM tails, sorts, host round trips for the Fiat-Shamir challenges).  Contexts of the
 backend are independent, so `ProofService` keeps `lanes` of them per GPU -- each with its own streams, SRS window
-tables, proving key and pinned witness buffers -- and drives every lane from its own host thread (the ctypes calls
-release the GIL).  Image in, proof bytes out: witness synthesis is the native `zg_wnn_synthesize`.
+tables, proving key and two sets of pinned witness buffers -- and drives every lane from its own host thread (the ctypes
+calls release the GIL).  Image in, proof bytes out: witness synthesis is the native `zg_wnn_synthesize`, run one image
+ahead of the proof on a helper thread per lane.
 
 This is what `bench.py --inflight K --synth native` measures (profiles/README.md: 115 -> 183 proofs/s from 1 to 4 lanes
 on the 1024-entry MNIST model) and what `farm.prove_many` runs on every rank of a multi-GPU job.  No CPU fallback.
@@ -13,6 +14,7 @@ from __future__ import annotations
 
 import queue
 import threading
+from concurrent.futures import ThreadPoolExecutor
 from typing import Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -28,15 +30,25 @@ class _Lane:
         self.params = ParamsKZG(service.params.k, service.params.g, service.params.g_lagrange)
         self.pk = service.wnn.generate_proving_key(ctx, self.params)
         n = 1 << self.pk.k
-        try:
-            import torch
-            self._pinned = [torch.empty((n, 4), dtype=torch.int64).pin_memory() for _ in range(6)]
-            self.cols = [t.numpy().view(np.uint64) for t in self._pinned]
-        except Exception:                      # torch is only used for pinned host memory here
-            self.cols = [np.empty((n, 4), dtype=np.uint64) for _ in range(6)]
+        # two sets of pinned advice buffers: the witness of the next image is synthesized (host, C++) into one while
+        # zg_create_proof reads the other
+        self.bufs = []
+        self._pinned = []
+        for _ in range(2):
+            try:
+                import torch
+                pinned = [torch.empty((n, 4), dtype=torch.int64).pin_memory() for _ in range(6)]
+                self._pinned.append(pinned)
+                self.bufs.append([t.numpy().view(np.uint64) for t in pinned])
+            except Exception:                  # torch is only used for pinned host memory here
+                self.bufs.append([np.empty((n, 4), dtype=np.uint64) for _ in range(6)])
+        self.cols = self.bufs[0]
+        self.flip = 0
         self.usable = n - (self.pk.cs.blinding_factors() + 1)
+        self.synth_pool = ThreadPoolExecutor(1)
 
     def close(self):
+        self.synth_pool.shutdown(wait=True)
         self.pk.close()
 
 
@@ -48,7 +60,8 @@ class ProofService:
     streams are for reproducible tests only."""
 
     def __init__(self, wnn, params: ParamsKZG, device: int = 0, lanes: int = 4,
-                 rng_factory: Optional[Callable[[int], object]] = None, streams: Optional[Sequence[int]] = None):
+                 rng_factory: Optional[Callable[[int], object]] = None, streams: Optional[Sequence[int]] = None,
+                 contexts: Optional[Sequence[zl.Context]] = None):
         assert lanes >= 1
         self.wnn, self.params, self.device = wnn, params, device
         self.synth = wnn.native_synthesizer()
@@ -56,8 +69,11 @@ class ProofService:
         self._owned_ctx = []
         self.lanes: List[_Lane] = []
         for i in range(lanes):
-            ctx = zl.Context(device, None if streams is None else streams[i])
-            self._owned_ctx.append(ctx)
+            if contexts is not None and i < len(contexts):
+                ctx = contexts[i]                                  # the caller's context (kept open by close())
+            else:
+                ctx = zl.Context(device, None if streams is None else streams[i])
+                self._owned_ctx.append(ctx)
             self.lanes.append(_Lane(self, i, ctx))
 
     @staticmethod
@@ -78,7 +94,9 @@ class ProofService:
         return self._prove_on(self.lanes[0], 0, image)
 
     def prove_many(self, images: Sequence) -> List[Tuple[bytes, List[int]]]:
-        """All images, `lanes` at a time; results in input order.  The first error of any lane is re-raised."""
+        """All images, `lanes` at a time; results in input order.  Every lane runs a two-stage pipeline: while
+        zg_create_proof works on image i, the lane's helper thread synthesizes the witness of its next image into the
+        other pinned buffer set (the ctypes calls release the GIL).  The first error of any lane is re-raised."""
         jobs: "queue.Queue[int]" = queue.Queue()
         for i in range(len(images)):
             jobs.put(i)
@@ -86,16 +104,27 @@ class ProofService:
         errors: List[BaseException] = []
 
         def work(lane: _Lane):
-            while not errors:
+            def claim():
                 try:
                     i = jobs.get_nowait()
                 except queue.Empty:
-                    return
+                    return None
+                buf = lane.bufs[lane.flip]
+                lane.flip ^= 1
+                return i, lane.synth_pool.submit(self.synth.synthesize, images[i], lane.pk.k, lane.usable, buf)
+            cur = claim()
+            while cur is not None and not errors:
+                i, fut = cur
+                nxt = claim()                    # the next witness is built while this proof runs
                 try:
-                    out[i] = self._prove_on(lane, i, images[i])
+                    cols, scores = fut.result()
+                    out[i] = (create_proof_limbs(lane.pk, cols, [to_limbs(scores)], self.rng_factory(i)), scores)
                 except BaseException as e:      # surfaced to the caller below
                     errors.append(e)
+                    if nxt is not None:
+                        nxt[1].cancel()
                     return
+                cur = nxt
         threads = [threading.Thread(target=work, args=(l,), daemon=True) for l in self.lanes[:max(1, min(len(self.lanes), len(images)))]]
         for t in threads:
             t.start()

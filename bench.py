@@ -306,20 +306,32 @@ def main():
                 self.ctypes = type("c", (), {"data": t.data_ptr()})
                 self.shape = (t.shape[0],)
 
+        # The lanes are the product's own throughput front-end (zg_b200/service.py::ProofService): one context + proving key
+        # + host thread per lane, witness synthesis pipelined one image ahead of the proof on a helper thread per lane.
+        # The e2e leg calls service.prove_many (image in, proof bytes out); the device leg proves from advice columns that
+        # already sit in HBM on the same lanes.
+        import itertools
+        from zg_b200.service import ProofService
+        K = 1 if shard_cols else max(1, args.inflight)
+        PPL = max(1, args.proofs_per_lane)
+        lane_streams = [stream] + [torch.cuda.Stream() for _ in range(K - 1)]
+        contexts = [ctx] + [zg_b200.Context(local, lane_streams[i].cuda_stream) for i in range(1, K)]
+        job_counter = itertools.count(1)
+        seeded = lambda _job: zg_b200.lib.XorShift.from_seed(int(next(job_counter)).to_bytes(16, "little"))
+        # e2e draws from the production RNG (OS-seeded ChaCha20, the reference's OsRng) unless the ranks must agree (SPMD)
+        service = ProofService(wnn, ParamsKZG(k, srs.g, srs.g_lagrange, srs.g2, srs.s_g2), device=local, lanes=K,
+                               rng_factory=seeded if shard_cols else None, contexts=contexts)
+
         class Lane:
-            """one in-flight proof: own context (stream, SRS tables, workspaces) and proving key"""
-            def __init__(self, idx, lane_ctx):
-                self.ctx = lane_ctx
-                params = ParamsKZG(k, srs.g, srs.g_lagrange)
-                circ0, asm0 = wnn.synthesize(np.zeros(wnn.img_shape(), dtype=np.uint8), k)
-                self.pk = keygen(lane_ctx, params, circ0.cs, asm0)
-                self.adv_host_t, self.adv_host, self.adv_dev_t, self.adv_dev = [], [], [], []
+            """the device-resident leg of one service lane"""
+            def __init__(self, idx, sl):
+                self.ctx, self.pk = sl.ctx, sl.pk
+                self.adv_host, self.adv_dev_t, self.adv_dev = [], [], []
                 for adv, _, _ in witnesses:
-                    ht = [torch.from_numpy(a.view(np.int64)).pin_memory() for a in advice_to_mont(lane_ctx, adv)]
+                    ht = [torch.from_numpy(a.view(np.int64)).pin_memory() for a in advice_to_mont(sl.ctx, adv)]
                     dt = [t.cuda() for t in ht]
-                    self.adv_host_t.append(ht)
                     self.adv_host.append([t.numpy().view(np.uint64) for t in ht])
-                    self.adv_dev_t.append(dt)
+                    self.adv_dev_t.append((ht, dt))
                     self.adv_dev.append([DevCol(t) for t in dt])
                 self.seed = (0 if shard_cols else rank * 100000) + idx * 1000     # SPMD: every rank draws the same stream
                 self.turn = idx                      # which image this lane proves next
@@ -337,16 +349,11 @@ def main():
                 w = self._next()
                 return w, create_proof_limbs(self.pk, self.adv_dev[w], witnesses[w][2], self.rng())
 
-            def prove_e2e(self):
+            def prove_host_cols(self):               # --synth cached: witnesses synthesized ahead of time, host buffers
                 w = self._next()
-                if native is not None:             # image -> witness (host, C++) -> proof: nothing is precomputed
-                    cols, scores = native.synthesize(imgs[w], k, usable_rows, out=self.adv_host[w])
-                    return w, create_proof_limbs(self.pk, cols, [to_limbs(scores)], self.rng())
                 return w, create_proof_limbs(self.pk, self.adv_host[w], witnesses[w][2], self.rng())
 
-        K = 1 if shard_cols else max(1, args.inflight)
-        lane_streams = [stream] + [torch.cuda.Stream() for _ in range(K - 1)]
-        lanes = [Lane(0, ctx)] + [Lane(i, zg_b200.Context(local, lane_streams[i].cuda_stream)) for i in range(1, K)]
+        lanes = [Lane(i, service.lanes[i]) for i in range(K)]
         pk = lanes[0].pk
         if shard_cols:
             from zg_b200 import farm
@@ -356,8 +363,6 @@ def main():
             extra["shard"] = "one proof stream; every round's commitments spread over %d GPUs by column, all-gathered (NCCL)" % world
         pool = ThreadPoolExecutor(K) if K > 1 else None
 
-        PPL = max(1, args.proofs_per_lane)
-
         def lane_run(lane, method):
             return [getattr(lane, method)() for _ in range(PPL)]
 
@@ -366,7 +371,14 @@ def main():
                 return lane_run(lanes[0], method)
             return [r for f in [pool.submit(lane_run, l, method) for l in lanes] for r in f.result()]
         step_dev = lambda: run_all("prove_dev")
-        step_e2e = lambda: run_all("prove_e2e")
+        e2e_turn = [0]
+
+        def step_e2e():
+            if native is None:
+                return run_all("prove_host_cols")
+            ws = [(e2e_turn[0] + i) % len(imgs) for i in range(K * PPL)]
+            e2e_turn[0] += K * PPL
+            return [(w, pr) for w, (pr, _) in zip(ws, service.prove_many([imgs[w] for w in ws]))]
         # every measured proof is a real proof: check one per lane against the restated verifier (untimed)
         opk = None
         if rank == 0 or shard_cols:                    # (column sharding: the proofs are collectives, every rank takes part)
@@ -391,7 +403,9 @@ def main():
         extra["inflight"] = K
         extra["proofs_per_step"] = K * PPL
         extra["images"] = "example_image_7.png" if nimg == 1 else "%d synthetic MNIST-shaped images per rank" % nimg
-        extra["e2e_starts_from"] = "image (native witness synthesis timed)" if native is not None else "synthesized advice columns"
+        extra["e2e_starts_from"] = ("image (native witness synthesis timed, pipelined one image ahead per lane by ProofService)"
+                                    if native is not None else "synthesized advice columns")
+        extra["e2e_rng"] = "seeded XorShift (SPMD ranks must agree)" if shard_cols or native is None else "ChaCha20 keyed from the OS per proof"
         if not args.no_cpu_baseline and rank == 0:
             cpu_fn = lambda: H.create_proof(srs, opk, asm_advice, [outputs], H.XorShiftRng(bytes(range(16))), real_msm=True)
             cpu_units = 1

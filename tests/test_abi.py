@@ -83,3 +83,23 @@ def test_transcript_keccak256_known_answers():
     for n in (1, 31, 32, 33, 64, 96, 135, 136, 137, 271, 272, 273, 1000):
         data = bytes((7 * i + n) & 0xFF for i in range(n))
         assert k(data) == H.keccak256(data), n
+
+
+def test_chacha20_rng_known_answer_and_stream():
+    """zg_chacha20_* (the production RNG, OsRng's role at src/wnn.rs:256): the block function against RFC 8439 section 2.3.2
+    (key 00..1f, block counter 1, nonce 00:00:00:09:00:00:00:4a:00:00:00:00 mapped onto the 64-bit counter / 64-bit nonce
+    layout), stream continuity across calls of any size, and two OS-seeded generators never repeating each other."""
+    import numpy as np
+    import zg_b200.lib as zl
+    r = zl.ChaCha20Rng.from_key(bytes(range(32)))
+    r.counter = 1 | (0x09000000 << 32)
+    r.nonce[0], r.nonce[1] = 0x4A000000, 0
+    assert r.draw(8).tobytes().hex() == ("10f1e7e4d13b5915500fdd1fa32071c4c7d1f4c733c068030422aa9ac3d46c4e"
+                                         "d2826446079faa0914c2d705d98b02a2b5129cd1de164eb9cbd083e8a2503c4e")
+    a = zl.ChaCha20Rng.from_key(b"\x07" * 32)
+    b = zl.ChaCha20Rng.from_key(b"\x07" * 32)
+    whole = a.draw(1000)
+    parts = np.concatenate([b.draw(k) for k in (1, 7, 8, 9, 120, 855)])
+    assert (whole == parts).all() and len(set(whole.tolist())) == 1000
+    x, y = zl.ChaCha20Rng.from_os().draw(16), zl.ChaCha20Rng.from_os().draw(16)
+    assert (x != y).any()
