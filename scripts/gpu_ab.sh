@@ -1,5 +1,5 @@
 #!/bin/bash
-# A/B lines for tuning knobs on the k = 17 proof (4 lanes): usage bash scripts/gpu_r02_ab.sh tag "ENV1=.. ENV2=.." ...
+# A/B lines for tuning knobs on the k = 17 proof (4 lanes): usage bash scripts/ab.sh tag "ENV1=.. ENV2=.." ...
 set -u
 cd "${GRAFT_REPO_ROOT:-.}"
 TAG=${1:-ab}; shift

@@ -1,6 +1,6 @@
 #!/bin/bash
 # per-kernel launch lists of ONE proof stream (ncu --metrics gpu__time_duration.sum; cold-cache, serialised times)
-# usage: bash scripts/gpu_r02_launches.sh tag [model ...]   (env is passed through, e.g. ZG_NTT_STAGEWISE=1)
+# usage: bash scripts/launches.sh tag [model ...]   (env is passed through, e.g. ZG_NTT_STAGEWISE=1)
 set -u
 cd "${GRAFT_REPO_ROOT:-.}"
 TAG=${1:-launches}; shift || true
