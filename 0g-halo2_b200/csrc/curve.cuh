@@ -143,68 +143,6 @@ ZG_HD void xyzz_add(G1Xyzz& acc, const G1Xyzz& b) {
   acc.zzz = fp_mul(fp_mul(acc.zzz, b.zzz), ppp);
 }
 
-#if defined(__CUDACC__)
-// Latency-oriented forms of the two group operations for single-warp chains (msm_tail.cu): the same formulas as xyzz_add /
-// xyzz_double with their independent products issued three at a time (fp_mul3_outlined) -- 5 calls instead of 14 products
-// for an addition, 4 instead of 9 for a doubling.
-__device__ __forceinline__ void xyzz_add_ilp(G1Xyzz& acc, const G1Xyzz& b) {
-  if (xyzz_is_identity(b)) return;
-  if (xyzz_is_identity(acc)) {
-    acc = b;
-    return;
-  }
-  Fq A[3], B[3], R[3];
-  A[0] = acc.x; B[0] = b.zz;  A[1] = b.x; B[1] = acc.zz;  A[2] = acc.y; B[2] = b.zzz;
-  fp_mul3_outlined<FqParams>(A, B, R);
-  const Fq u1 = R[0], u2 = R[1], s1 = R[2];
-  A[0] = b.y; B[0] = acc.zzz;  A[1] = acc.zz; B[1] = b.zz;  A[2] = acc.zzz; B[2] = b.zzz;
-  fp_mul3_outlined<FqParams>(A, B, R);
-  const Fq s2 = R[0], zz12 = R[1], zzz12 = R[2];
-  const Fq p = fp_sub(u2, u1), r = fp_sub(s2, s1);
-  if (fp_is_zero(p)) {
-    if (fp_is_zero(r)) acc = xyzz_double(acc);
-    else acc = xyzz_identity();
-    return;
-  }
-  A[0] = p; B[0] = p;  A[1] = r; B[1] = r;  A[2] = p; B[2] = p;
-  fp_mul3_outlined<FqParams>(A, B, R);
-  const Fq pp = R[0], rr = R[1];
-  A[0] = p; B[0] = pp;  A[1] = u1; B[1] = pp;  A[2] = zz12; B[2] = pp;
-  fp_mul3_outlined<FqParams>(A, B, R);
-  const Fq ppp = R[0], q = R[1];
-  acc.zz = R[2];
-  const Fq x3 = fp_sub(fp_sub(rr, ppp), fp_dbl(q));
-  A[0] = r; B[0] = fp_sub(q, x3);  A[1] = s1; B[1] = ppp;  A[2] = zzz12; B[2] = ppp;
-  fp_mul3_outlined<FqParams>(A, B, R);
-  acc.x = x3;
-  acc.y = fp_sub(R[0], R[1]);
-  acc.zzz = R[2];
-}
-__device__ __forceinline__ G1Xyzz xyzz_double_ilp(const G1Xyzz& p) {
-  if (xyzz_is_identity(p)) return p;
-  G1Xyzz o;
-  Fq A[3], B[3], R[3];
-  const Fq u = fp_dbl(p.y);
-  A[0] = u; B[0] = u;  A[1] = p.x; B[1] = p.x;  A[2] = u; B[2] = u;
-  fp_mul3_outlined<FqParams>(A, B, R);
-  const Fq v = R[0], xx = R[1];
-  const Fq m = fp_add(fp_dbl(xx), xx);
-  A[0] = u; B[0] = v;  A[1] = p.x; B[1] = v;  A[2] = v; B[2] = p.zz;
-  fp_mul3_outlined<FqParams>(A, B, R);
-  const Fq w = R[0], s = R[1];
-  o.zz = R[2];
-  A[0] = m; B[0] = m;  A[1] = w; B[1] = p.y;  A[2] = w; B[2] = p.zzz;
-  fp_mul3_outlined<FqParams>(A, B, R);
-  o.x = fp_sub(R[0], fp_dbl(s));
-  const Fq wy = R[1];
-  o.zzz = R[2];
-  A[0] = m; B[0] = fp_sub(s, o.x);  A[1] = m; B[1] = m;  A[2] = m; B[2] = m;
-  fp_mul3_outlined<FqParams>(A, B, R);
-  o.y = fp_sub(R[0], wy);
-  return o;
-}
-#endif
-
 // XYZZ -> Jacobian without an inversion: Z = ZZ*ZZZ, X' = X*ZZ*ZZZ^2, Y' = Y*ZZ^3*ZZZ^2
 // (then X'/Z^2 = X/ZZ and Y'/Z^3 = Y/ZZZ).
 ZG_HD G1Jac xyzz_to_jacobian(const G1Xyzz& p) {

@@ -492,24 +492,6 @@ __device__ __noinline__ Fp<P> fp_mul_outlined(Fp<P> a, Fp<P> b) {
 }
 #endif
 
-// Three independent products in one call: the three multiplier bodies sit in one basic block, so ptxas interleaves their
-// carry chains (about three times the instruction-level parallelism of fp_mul_outlined).  For kernels bound by the latency
-// of a chain of EC additions in a single warp (msm_tail.cu): one XYZZ addition is 5 of these calls instead of 14
-// dependent single products.  Operands and results go through the caller's stack frame.
-#if defined(__CUDACC__)
-template <class P>
-__device__ __noinline__ void fp_mul3_outlined(const Fp<P>* a, const Fp<P>* b, Fp<P>* out) {
-#if defined(__CUDA_ARCH__)
-  const Fp<P> r0 = fp_mul_eo<P>(a[0], b[0]);
-  const Fp<P> r1 = fp_mul_eo<P>(a[1], b[1]);
-  const Fp<P> r2 = fp_mul_eo<P>(a[2], b[2]);
-  out[0] = r0;
-  out[1] = r1;
-  out[2] = r2;
-#endif
-}
-#endif
-
 template <class P>
 ZG_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
 #if defined(__CUDA_ARCH__) && defined(ZG_FP_MUL_NOINLINE)

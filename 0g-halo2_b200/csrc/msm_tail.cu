@@ -9,15 +9,6 @@
 
 namespace zg {
 
-// single-warp chains of dependent EC operations: latency-oriented forms (curve.cuh), unless ZG_TAIL_PLAIN is defined
-#ifndef ZG_TAIL_PLAIN
-#define TADD xyzz_add_ilp
-#define TDBL xyzz_double_ilp
-#else
-#define TADD xyzz_add
-#define TDBL xyzz_double
-#endif
-
 __device__ __forceinline__ G1Xyzz shfl_down_xyzz(const G1Xyzz& p, int d) {
   G1Xyzz r;
 #pragma unroll
@@ -65,7 +56,7 @@ __global__ void __launch_bounds__(128) msm_serial_reduce_kernel(
       acc = xyzz_identity();
     }
     G1Xyzz p = pts_in[e];
-    TADD(acc, p);
+    xyzz_add(acc, p);
   }
   if (nruns == 0) {
     pkeys[2 * t] = cur;
@@ -96,7 +87,7 @@ __global__ void __launch_bounds__(128) msm_warp_reduce_kernel(
   for (int d = 1; d < 32; d <<= 1) {
     G1Xyzz other = shfl_down_xyzz(acc, d);
     uint32_t okey = __shfl_down_sync(0xffffffffu, key, d);
-    if (lane + d < 32 && okey == key && key != MSM_INVALID_KEY) TADD(acc, other);
+    if (lane + d < 32 && okey == key && key != MSM_INVALID_KEY) xyzz_add(acc, other);
   }
   uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
   uint32_t last_key = __shfl_sync(0xffffffffu, key, 31);
@@ -133,14 +124,14 @@ __device__ __forceinline__ void warp_weighted(G1Xyzz x, uint32_t lane, G1Xyzz& s
 #pragma unroll 1
   for (int d = 1; d < 32; d <<= 1) {
     G1Xyzz o = shfl_down_xyzz(x, d);
-    if (lane + d < 32) TADD(x, o);
+    if (lane + d < 32) xyzz_add(x, o);
   }
   s = x;  // lane 0: total
   G1Xyzz y = (lane >= 1) ? x : xyzz_identity();
 #pragma unroll 1
   for (int d = 16; d >= 1; d >>= 1) {
     G1Xyzz o = shfl_down_xyzz(y, d);
-    if (lane < (uint32_t)d) TADD(y, o);
+    if (lane < (uint32_t)d) xyzz_add(y, o);
   }
   t = y;
 }
@@ -148,7 +139,7 @@ __device__ __forceinline__ G1Xyzz warp_sum(G1Xyzz y, uint32_t lane) {
 #pragma unroll 1
   for (int d = 16; d >= 1; d >>= 1) {
     G1Xyzz o = shfl_down_xyzz(y, d);
-    if (lane < (uint32_t)d) TADD(y, o);
+    if (lane < (uint32_t)d) xyzz_add(y, o);
   }
   return y;
 }
@@ -160,7 +151,7 @@ __device__ __forceinline__ G1Xyzz warp_sum(G1Xyzz y, uint32_t lane) {
 // k = 17: 232 us per batch of 8 MSMs, profiles/r01_launches_proof_large_a.csv.)
 __device__ __forceinline__ G1Xyzz xyzz_mul_pow2(G1Xyzz p, int log2w) {
 #pragma unroll 1
-  for (int i = 0; i < log2w; i++) p = TDBL(p);
+  for (int i = 0; i < log2w; i++) p = xyzz_double(p);
   return p;
 }
 __global__ void __launch_bounds__(128) msm_bucket_l1_kernel(const G1Xyzz* __restrict__ buckets, uint32_t NB,
@@ -177,13 +168,13 @@ __global__ void __launch_bounds__(128) msm_bucket_l1_kernel(const G1Xyzz* __rest
     for (int l = 7; l >= 1; l--) {
       if ((size_t)q * 8 + l < NB) {
         G1Xyzz x = B[l];
-        TADD(run, x);
+        xyzz_add(run, x);
       }
-      TADD(acc, run);                                      // acc = sum_{l >= 1} l * X_l
+      xyzz_add(acc, run);                                      // acc = sum_{l >= 1} l * X_l
     }
     if ((size_t)q * 8 < NB) {
       G1Xyzz x = B[0];
-      TADD(run, x);                                        // run = sum X_l
+      xyzz_add(run, x);                                        // run = sum X_l
     }
   }
   // merge pairs: (sub 0, 1) and (2, 3) with width 8, then (0, 2) with width 16
@@ -193,10 +184,10 @@ __global__ void __launch_bounds__(128) msm_bucket_l1_kernel(const G1Xyzz* __rest
     G1Xyzz so = shfl_down_xyzz(run, d);
     G1Xyzz to = shfl_down_xyzz(acc, d);
     if ((sub & (2 * d - 1)) == 0) {
-      TADD(run, so);
-      TADD(acc, to);
+      xyzz_add(run, so);
+      xyzz_add(acc, to);
       so = xyzz_mul_pow2(so, 3 + step);
-      TADD(acc, so);
+      xyzz_add(acc, so);
     }
   }
   if (live && sub == 0) {
@@ -225,7 +216,7 @@ __global__ void __launch_bounds__(128) msm_bucket_l1_warp_kernel(const G1Xyzz* _
 }
 
 __device__ __forceinline__ G1Xyzz xyzz_mul32(G1Xyzz p) {
-  for (int i = 0; i < 5; i++) p = TDBL(p);
+  for (int i = 0; i < 5; i++) p = xyzz_double(p);
   return p;
 }
 
@@ -277,10 +268,10 @@ __global__ void __launch_bounds__(96) msm_finish_kernel(const G1Xyzz* __restrict
   __syncthreads();
   if (tid == 0) {
     G1Xyzz r = xyzz_mul32(fin[1]);
-    TADD(r, fin[2]);
+    xyzz_add(r, fin[2]);
     r = xyzz_mul32(r);
-    TADD(r, fin[3]);
-    TADD(r, fin[0]);
+    xyzz_add(r, fin[3]);
+    xyzz_add(r, fin[0]);
     out[m] = xyzz_to_jacobian(r);
   }
 }
