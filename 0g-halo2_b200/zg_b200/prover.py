@@ -54,10 +54,21 @@ class ParamsKZG:
             self._loaded_on = ctx
 
 
+_warned_stand_in = False
+
+
 def vk_transcript_repr(k, cs, fixed_commitments, perm_commitments) -> int:
     """Stand-in for VerifyingKey::transcript_repr (the real value hashes the Rust Debug rendering of the
     vk and cannot be restated without the crate): Blake2b-512, personal
-    "Halo2-Verify-Key", over a canonical serialisation; reduced like from_uniform_bytes."""
+    "Halo2-Verify-Key", over a canonical serialisation; reduced like from_uniform_bytes.
+    Proofs made under it verify with this repository's verifiers only: pass the real value (`transcript_repr=` of keygen /
+    load_proving_key, taken from a Rust-built key) for proofs the Rust or EVM verifier must accept.  Warns once."""
+    global _warned_stand_in
+    if not _warned_stand_in:
+        import warnings
+        warnings.warn("zg_b200: using the stand-in vk.transcript_repr; proofs will not verify under the Rust / EVM verifier "
+                      "until the real value is supplied (keygen(..., transcript_repr=...))", stacklevel=3)
+        _warned_stand_in = True
     h = hashlib.blake2b(digest_size=64, person=b"Halo2-Verify-Key")
     h.update(("k=%d;adv=%d;fix=%d;inst=%d;deg=%d;perm=%d;lookups=%d;gates=%d" % (
         k, cs.num_advice, cs.num_fixed, cs.num_instance, cs.degree(), len(cs.permutation), len(cs.lookups),
