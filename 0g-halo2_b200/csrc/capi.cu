@@ -197,10 +197,7 @@ void zg_ctx_destroy(zg_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->comm) zg_comm_destroy(ctx);
   if (ctx->d_gather) cudaFree(ctx->d_gather);
-  for (int b = 0; b < 2; b++) {
-    if (ctx->base[b]) cudaFree(ctx->base[b]);
-    if (ctx->table[b].pts) cudaFree(ctx->table[b].pts);
-  }
+  ctx->srs_release();
   for (auto& kv : ctx->domains) cudaFree(kv.second.tw);
   if (ctx->ws_msm.p) cudaFree(ctx->ws_msm.p);
   if (ctx->ws_ntt.p) cudaFree(ctx->ws_ntt.p);
@@ -295,24 +292,43 @@ int zg_srs_load(zg_ctx* ctx, uint32_t k, const zg_g1_affine* g, const zg_g1_affi
   const uint32_t W = msm_windows(c);
   if ((uint64_t)n * W >= (1ull << 31)) return ctx->fail(ZG_E_INVALID, "srs_load: table index overflow");
   const zg_g1_affine* src[2] = {g, g_lagrange};
+  ZG_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->srs_release();                        // the previous parameters (other contexts that share them keep them alive)
+  ctx->srs = new SrsShared();
   for (int b = 0; b < 2; b++) {
-    if (ctx->base[b]) { ZG_CUDA(cudaFree(ctx->base[b])); ctx->base[b] = nullptr; }
-    if (ctx->table[b].pts) { ZG_CUDA(cudaFree(ctx->table[b].pts)); ctx->table[b].pts = nullptr; }
     if (!src[b]) continue;
-    ZG_CUDA(cudaMalloc(&ctx->base[b], sizeof(G1Affine) * n));
+    ZG_CUDA(cudaMalloc(&ctx->srs->base[b], sizeof(G1Affine) * n));
+    ctx->base[b] = ctx->srs->base[b];
     ZG_CUDA(cudaMemcpyAsync(ctx->base[b], src[b], sizeof(G1Affine) * n, cudaMemcpyHostToDevice, ctx->stream));
     MsmTable& t = ctx->table[b];
     t.n = (uint32_t)n;
     t.c = c;
     t.W = W;
-    cudaError_t e = cudaMalloc(&t.pts, sizeof(G1Affine) * n * W);
+    cudaError_t e = cudaMalloc(&ctx->srs->table[b], sizeof(G1Affine) * n * W);
     if (e != cudaSuccess) return ctx->fail(ZG_E_NOMEM, "srs_load: window table allocation failed");
+    t.pts = ctx->srs->table[b];
     e = msm_precompute_table(ctx->base[b], t.n, c, W, t.pts, ctx->stream);
     ctx->launches += 1;
     if (e != cudaSuccess) return ctx->cuda_fail(e, "msm_precompute_table");
   }
   ZG_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->srs_k = k;
+  ctx->srs_loaded = true;
+  return ZG_OK;
+}
+
+// `ctx` uses the parameters `from` has loaded (same device): no copy, no second set of window tables
+int zg_srs_share(zg_ctx* ctx, zg_ctx* from) {
+  ZG_ENTER(ctx);
+  if (!from || !from->srs_loaded || !from->srs) return ctx->fail(ZG_E_STATE, "srs_share: the source context has no SRS");
+  if (from->device != ctx->device) return ctx->fail(ZG_E_INVALID, "srs_share: contexts on different devices");
+  if (from == ctx) return ZG_OK;
+  ZG_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->srs_release();
+  from->srs->refs.fetch_add(1);
+  ctx->srs = from->srs;
+  for (int b = 0; b < 2; b++) { ctx->base[b] = from->base[b]; ctx->table[b] = from->table[b]; }
+  ctx->srs_k = from->srs_k;
   ctx->srs_loaded = true;
   return ZG_OK;
 }

@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 #include <array>
+#include <atomic>
 #include "../../include/zg_b200.h"
 #include "msm.cuh"
 #include "ntt.cuh"
@@ -16,6 +17,20 @@ namespace zg {
 
 struct Domain {       // twiddle table for one (log_n, omega)
   Fr* tw = nullptr;   // stage-major, n-1 entries
+};
+
+// SRS bases and their window tables on one device: shared by the contexts that proved they want the same parameters
+// (zg_srs_share), freed with the last of them
+struct SrsShared {
+  std::atomic<int> refs{1};
+  G1Affine* base[2] = {nullptr, nullptr};
+  G1Affine* table[2] = {nullptr, nullptr};
+  ~SrsShared() {
+    for (int b = 0; b < 2; b++) {
+      if (base[b]) cudaFree(base[b]);
+      if (table[b]) cudaFree(table[b]);
+    }
+  }
 };
 
 struct Workspace {
@@ -49,8 +64,15 @@ struct zg_ctx {
   // SRS
   uint32_t srs_k = 0;
   bool srs_loaded = false;
+  zg::SrsShared* srs = nullptr;               // owner of the device memory behind base[] / table[]
   zg::G1Affine* base[2] = {nullptr, nullptr};
   zg::MsmTable table[2];
+  void srs_release() {
+    if (srs && srs->refs.fetch_sub(1) == 1) delete srs;
+    srs = nullptr;
+    for (int b = 0; b < 2; b++) { base[b] = nullptr; table[b] = zg::MsmTable(); }
+    srs_loaded = false;
+  }
 
   // twiddle tables keyed by (log_n, omega limbs)
   std::map<std::array<uint32_t, 9>, zg::Domain> domains;

@@ -7,6 +7,7 @@
 // msm.cu, poly.cu, expr.cu and lookup.cu; the host only sequences rounds, hashes (keccak256) and
 // normalises <= 8 commitments per round.  Witness synthesis is the caller's (BASELINE north_star).
 #include <algorithm>
+#include <atomic>
 #include <memory>
 #include "ctx.cuh"
 #include "expr.cuh"
@@ -172,6 +173,14 @@ struct Bump {
 
 }  // namespace
 
+// The read-only half of a proving key (fixed / sigma columns in three forms, l_0 / l_last / l_active / X, domain tables,
+// programs): shared by the clones of a key (zg_pk_clone), freed with the last of them.
+struct PkResident {
+  std::atomic<int> refs{1};
+  uint8_t* arena = nullptr;
+  ~PkResident() { if (arena) cudaFree(arena); }
+};
+
 struct zg_pk {
   uint32_t k = 0, ext_k = 0, rot_scale = 0;   // ext_k: halo2's extended_k (only the C-ABI conversions of zg_evaluate_h use it)
   size_t n = 0, N = 0;                        // N = ext.N rows of the internal extended domain
@@ -185,7 +194,9 @@ struct zg_pk {
   std::vector<uint32_t> in_first, in_count, tab_first, tab_count;
   Fr transcript_repr, omega, omega_inv, delta;
   std::vector<G1Affine> fixed_comm, sigma_comm;
-  uint8_t* arena = nullptr;
+  PkResident* res = nullptr;    // resident half (shared)
+  uint8_t* arena = nullptr;     // per-proof workspace half (this key's own)
+  size_t n_ops = 0, n_prog_off = 0, n_constants = 0, n_queries = 0;
   // resident
   Fr *fixed_values, *fixed_polys, *fixed_cosets, *sigma_values, *sigma_polys, *sigma_cosets;
   Fr *l0, *l_last, *l_active, *coset_x, *t_inv, *constants, *omega_pows;
@@ -216,9 +227,10 @@ struct zg_pk {
   float stage_ms[8] = {0};
   std::vector<char> table_cacheable;   // per lookup: the table reads fixed columns and constants only
   zg_pk() = default;
-  zg_pk(const zg_pk&) = delete;
+  zg_pk(const zg_pk&) = default;       // only zg_pk_clone copies, and it re-points every owned resource at once
   zg_pk& operator=(const zg_pk&) = delete;
-  ~zg_pk() {                           // every early return of zg_pk_load releases the arena through this
+  ~zg_pk() {                           // every early return of zg_pk_load / zg_pk_clone releases through this
+    if (res && res->refs.fetch_sub(1) == 1) delete res;
     if (arena) cudaFree(arena);
     if (rnd_words_host) cudaFreeHost(rnd_words_host);
   }
@@ -420,6 +432,93 @@ static int quotient_numerator(zg_ctx* ctx, zg_pk* pk, const Fr& theta, const Fr&
   return ZG_OK;
 }
 
+
+// ---- device memory of a key: resident half (shared by clones) and workspace half (one per key) ---------------------------
+static size_t carve_resident(zg_pk* pk, uint8_t* base) {
+  const size_t n = pk->n, N = pk->N;
+  const uint32_t F = pk->F, m = pk->m, Lk = pk->n_lookups;
+  Bump b;
+  b.base = base;
+  pk->fixed_values = b.take<Fr>(F * n); pk->fixed_polys = b.take<Fr>(F * n); pk->fixed_cosets = b.take<Fr>(F * N);
+  pk->sigma_values = b.take<Fr>(m * n); pk->sigma_polys = b.take<Fr>(m * n); pk->sigma_cosets = b.take<Fr>(m * N);
+  pk->l0 = b.take<Fr>(N); pk->l_last = b.take<Fr>(N); pk->l_active = b.take<Fr>(N); pk->coset_x = b.take<Fr>(N);
+  pk->t_inv = b.take<Fr>((size_t)1 << (pk->ext_k - pk->k)); pk->ext_mem = b.take<Fr>(ext_domain_table_elems(pk->ext));
+  pk->constants = b.take<Fr>(pk->n_constants + 1); pk->omega_pows = b.take<Fr>(n);
+  pk->ops = b.take<uint32_t>(pk->n_ops + 1); pk->prog_off = b.take<uint32_t>(pk->n_prog_off);
+  pk->d_in_first = b.take<uint32_t>(Lk + 1); pk->d_in_count = b.take<uint32_t>(Lk + 1);
+  pk->d_tab_first = b.take<uint32_t>(Lk + 1); pk->d_tab_count = b.take<uint32_t>(Lk + 1);
+  for (int kind = 0; kind < 3; kind++) {
+    pk->d_qcol[kind] = b.take<uint32_t>(pk->q[kind].size() + 1);
+    pk->d_qrot[kind] = b.take<int32_t>(pk->q[kind].size() + 1);
+  }
+  pk->d_sigma_cosets = b.take<const Fr*>(m + 1);
+  return b.off;
+}
+static size_t carve_workspace(zg_pk* pk, uint8_t* base) {
+  const size_t n = pk->n, N = pk->N;
+  const uint32_t A = pk->A, F = pk->F, I = pk->I, m = pk->m, Lk = pk->n_lookups, S = pk->nsets;
+  const size_t n_queries = pk->n_queries;
+  Bump b;
+  b.base = base;
+  const uint32_t ncols[3] = {A, F, I};
+  for (int kind = 0; kind < 3; kind++) {
+    pk->d_cols_base[kind] = b.take<const Fr*>(ncols[kind] + 1);
+    pk->d_cols_ext[kind] = b.take<const Fr*>(ncols[kind] + 1);
+  }
+  pk->d_perm_cosets = b.take<const Fr*>(m + 1);
+  pk->d_z_cosets = b.take<const Fr*>(S + 1);
+  pk->adv_values = b.take<Fr>(A * n); pk->adv_polys = b.take<Fr>(A * n); pk->adv_cosets = b.take<Fr>(A * N);
+  pk->inst_values = b.take<Fr>(I * n); pk->inst_polys = b.take<Fr>(I * n); pk->inst_cosets = b.take<Fr>(I * N);
+  pk->ci = b.take<Fr>(Lk * n); pk->ct = b.take<Fr>(Lk * n);
+  pk->pa = b.take<Fr>(2 * Lk * n); pk->ps = pk->pa ? pk->pa + (size_t)Lk * n : nullptr;   // pa | ps contiguous: one MSM batch
+  pk->pa_poly = b.take<Fr>(2 * Lk * n); pk->ps_poly = pk->pa_poly ? pk->pa_poly + (size_t)Lk * n : nullptr;
+  pk->pz = b.take<Fr>((S + Lk + 1) * n); pk->lz = pk->pz ? pk->pz + (size_t)S * n : nullptr;   // pz | lz | (random poly) contiguous
+  pk->pz_poly = b.take<Fr>((S + Lk) * n); pk->lz_poly = pk->pz_poly ? pk->pz_poly + (size_t)S * n : nullptr;
+  pk->pz_coset = b.take<Fr>(S * N); pk->lk_cosets = b.take<Fr>(3 * (size_t)Lk * N);
+  pk->frac = b.take<Fr>(n); pk->rnd = b.take<Fr>(pk->n_draws); pk->random_poly = pk->rnd;  // set per proof
+  const size_t hcap = std::max<size_t>(N, (size_t)(S + Lk + 1) * n);   // also scratch for the S + Lk fraction columns
+  pk->h = b.take<Fr>(hcap); pk->h_coeff = b.take<Fr>(hcap); pk->h_poly = b.take<Fr>(n);
+  pk->fold = b.take<Fr>(8 * n); pk->wpoly = b.take<Fr>(8 * n);
+  pk->scratch = b.take<Fr>(8 * 4096 + std::max<size_t>(64, (n + 4095) / 4096) * n_queries);
+  pk->evals_dev = b.take<Fr>(n_queries + 8); pk->points_dev = b.take<Fr>(16); pk->coeff_dev = b.take<Fr>(n_queries + 8);
+  pk->one_dev = b.take<Fr>(8);
+  pk->d_polyptrs = b.take<const Fr*>(std::max<size_t>(n_queries + 8, 2 * (size_t)m + 8)); pk->d_pidx = b.take<uint32_t>(n_queries + 8);
+  pk->d_status = b.take<uint32_t>(64);
+  pk->lookup_ws_stride = (lookup_workspace_bytes(pk->usable) + 255) & ~(size_t)255;
+  pk->lookup_ws = b.take<uint8_t>(pk->lookup_ws_stride * zg_ctx::N_SIDE);
+  pk->table_cache_stride = (lookup_table_bytes(pk->usable) + 255) & ~(size_t)255;
+  pk->table_cache = b.take<uint8_t>(pk->table_cache_stride * (Lk + 1));     // per key: filled lazily by its first proof
+  pk->rnd_words_dev = b.take<uint64_t>(8 * pk->n_draws);
+  return b.off;
+}
+// the pointer tables that name workspace columns (and the constant 1) -- once per key, also for a clone
+static int upload_workspace_tables(zg_ctx* ctx, zg_pk* pk) {
+  const size_t n = pk->n, N = pk->N;
+  const uint32_t A = pk->A, F = pk->F, I = pk->I, m = pk->m, S = pk->nsets;
+  cudaStream_t st = ctx->stream;
+  std::vector<const Fr*> pb[3], pe[3];
+  for (uint32_t c = 0; c < A; c++) { pb[0].push_back(pk->adv_values + c * n); pe[0].push_back(pk->adv_cosets + c * N); }
+  for (uint32_t c = 0; c < F; c++) { pb[1].push_back(pk->fixed_values + c * n); pe[1].push_back(pk->fixed_cosets + c * N); }
+  for (uint32_t c = 0; c < I; c++) { pb[2].push_back(pk->inst_values + c * n); pe[2].push_back(pk->inst_cosets + c * N); }
+  for (int kind = 0; kind < 3; kind++) {
+    ZG_CUDA(upload(pk->d_cols_base[kind], pb[kind], st));
+    ZG_CUDA(upload(pk->d_cols_ext[kind], pe[kind], st));
+  }
+  std::vector<const Fr*> pcos, zcos;
+  for (uint32_t c = 0; c < m; c++) {
+    uint32_t kind = pk->perm[c].first, idx = pk->perm[c].second;
+    if (kind > 2 || idx >= (kind == 0 ? A : kind == 1 ? F : I)) return ctx->fail(ZG_E_INVALID, "pk_load: bad permutation column");
+    pcos.push_back(pe[kind][idx]);
+  }
+  for (uint32_t s = 0; s < S; s++) zcos.push_back(pk->pz_coset + s * N);
+  ZG_CUDA(upload(pk->d_perm_cosets, pcos, st));
+  ZG_CUDA(upload(pk->d_z_cosets, zcos, st));
+  Fr onev = fr_one();
+  ZG_CUDA(cudaMemcpyAsync(pk->one_dev, &onev, sizeof(Fr), cudaMemcpyHostToDevice, st));
+  ZG_CUDA(cudaStreamSynchronize(st));          // the vectors above are host temporaries
+  return ZG_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -473,6 +572,34 @@ int zg_pk_commitments(zg_ctx* ctx, const zg_pk* pk, zg_g1_affine* fixed_out, zg_
   if (!pk) return ctx->fail(ZG_E_INVALID, "pk_commitments: null pk");
   if (fixed_out) memcpy(fixed_out, pk->fixed_comm.data(), sizeof(G1Affine) * pk->F);
   if (sigma_out) memcpy(sigma_out, pk->sigma_comm.data(), sizeof(G1Affine) * pk->m);
+  return ZG_OK;
+}
+
+// A second key over the same resident columns: own workspace, own lookup-table cache, own pinned RNG staging.  The clone
+// may live on another context of the SAME device (one lane of a ProofService each); the resident half is freed with the
+// last key that uses it.
+int zg_pk_clone(zg_ctx* ctx, const zg_pk* src, zg_pk** out) {
+  ZG_ENTER(ctx);
+  if (!src || !out) return ctx->fail(ZG_E_INVALID, "pk_clone: null argument");
+  *out = nullptr;
+  if (!ctx->srs_loaded || ctx->srs_k != src->k || !ctx->table[0].pts || !ctx->table[1].pts)
+    return ctx->fail(ZG_E_STATE, "pk_clone: load (or share) an SRS with both bases for the same k first");
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, src->res->arena) != cudaSuccess || attr.device != ctx->device)
+    return ctx->fail(ZG_E_INVALID, "pk_clone: the source key lives on another device");
+  std::unique_ptr<zg_pk> pk(new zg_pk(*src));
+  pk->arena = nullptr;                     // nothing of the source's own resources may be released by the copy
+  pk->rnd_words_host = nullptr;
+  pk->res->refs.fetch_add(1);
+  pk->table_cached.assign(pk->n_lookups, 0);
+  memset(pk->stage_ms, 0, sizeof(pk->stage_ms));
+  const size_t bytes = carve_workspace(pk.get(), nullptr);
+  if (cudaMalloc(&pk->arena, bytes) != cudaSuccess) return ctx->fail(ZG_E_NOMEM, "pk_clone: workspace allocation failed");
+  carve_workspace(pk.get(), pk->arena);
+  ZG_CUDA(cudaMallocHost(&pk->rnd_words_host, 8 * pk->n_draws * sizeof(uint64_t)));
+  int rc = upload_workspace_tables(ctx, pk.get());
+  if (rc) return rc;
+  *out = pk.release();
   return ZG_OK;
 }
 
@@ -530,54 +657,18 @@ int zg_pk_load(zg_ctx* ctx, const zg_pk_desc* d, zg_pk** out) {
                 (size_t)Lk * (pk->bf + 1) + (n + 1) + pk->qdeg;
   const uint32_t n_queries = (uint32_t)(pk->q[0].size() + pk->q[1].size() + m + 3 * S + 5 * Lk + 2);
 
-  // one arena: first pass sizes, second pass carves
-  for (int pass = 0; pass < 2; pass++) {
-    Bump b;
-    b.base = pass ? pk->arena : nullptr;
-    pk->fixed_values = b.take<Fr>(F * n); pk->fixed_polys = b.take<Fr>(F * n); pk->fixed_cosets = b.take<Fr>(F * N);
-    pk->sigma_values = b.take<Fr>(m * n); pk->sigma_polys = b.take<Fr>(m * n); pk->sigma_cosets = b.take<Fr>(m * N);
-    pk->l0 = b.take<Fr>(N); pk->l_last = b.take<Fr>(N); pk->l_active = b.take<Fr>(N); pk->coset_x = b.take<Fr>(N);
-    pk->t_inv = b.take<Fr>((size_t)1 << (pk->ext_k - pk->k)); pk->ext_mem = b.take<Fr>(ext_domain_table_elems(pk->ext)); pk->constants = b.take<Fr>(d->n_constants + 1); pk->omega_pows = b.take<Fr>(n);
-    pk->ops = b.take<uint32_t>(ops.size() + 1); pk->prog_off = b.take<uint32_t>(prog_off.size());
-    pk->d_in_first = b.take<uint32_t>(Lk + 1); pk->d_in_count = b.take<uint32_t>(Lk + 1);
-    pk->d_tab_first = b.take<uint32_t>(Lk + 1); pk->d_tab_count = b.take<uint32_t>(Lk + 1);
-    for (int kind = 0; kind < 3; kind++) {
-      pk->d_qcol[kind] = b.take<uint32_t>(pk->q[kind].size() + 1);
-      pk->d_qrot[kind] = b.take<int32_t>(pk->q[kind].size() + 1);
-    }
-    const uint32_t ncols[3] = {A, F, I};
-    for (int kind = 0; kind < 3; kind++) {
-      pk->d_cols_base[kind] = b.take<const Fr*>(ncols[kind] + 1);
-      pk->d_cols_ext[kind] = b.take<const Fr*>(ncols[kind] + 1);
-    }
-    pk->d_perm_cosets = b.take<const Fr*>(m + 1); pk->d_sigma_cosets = b.take<const Fr*>(m + 1);
-    pk->d_z_cosets = b.take<const Fr*>(S + 1);
-    pk->adv_values = b.take<Fr>(A * n); pk->adv_polys = b.take<Fr>(A * n); pk->adv_cosets = b.take<Fr>(A * N);
-    pk->inst_values = b.take<Fr>(I * n); pk->inst_polys = b.take<Fr>(I * n); pk->inst_cosets = b.take<Fr>(I * N);
-    pk->ci = b.take<Fr>(Lk * n); pk->ct = b.take<Fr>(Lk * n);
-    pk->pa = b.take<Fr>(2 * Lk * n); pk->ps = pk->pa ? pk->pa + (size_t)Lk * n : nullptr;   // pa | ps contiguous: one MSM batch
-    pk->pa_poly = b.take<Fr>(2 * Lk * n); pk->ps_poly = pk->pa_poly ? pk->pa_poly + (size_t)Lk * n : nullptr;
-    pk->pz = b.take<Fr>((S + Lk + 1) * n); pk->lz = pk->pz ? pk->pz + (size_t)S * n : nullptr;   // pz | lz | (random poly) contiguous
-    pk->pz_poly = b.take<Fr>((S + Lk) * n); pk->lz_poly = pk->pz_poly ? pk->pz_poly + (size_t)S * n : nullptr;
-    pk->pz_coset = b.take<Fr>(S * N); pk->lk_cosets = b.take<Fr>(3 * (size_t)Lk * N);
-    pk->frac = b.take<Fr>(n); pk->rnd = b.take<Fr>(pk->n_draws); pk->random_poly = pk->rnd;  // set per proof
-    const size_t hcap = std::max<size_t>(N, (size_t)(S + Lk + 1) * n);   // also scratch for the S + Lk fraction columns
-    pk->h = b.take<Fr>(hcap); pk->h_coeff = b.take<Fr>(hcap); pk->h_poly = b.take<Fr>(n);
-    pk->fold = b.take<Fr>(8 * n); pk->wpoly = b.take<Fr>(8 * n);
-    pk->scratch = b.take<Fr>(8 * 4096 + std::max<size_t>(64, (n + 4095) / 4096) * (size_t)n_queries);
-    pk->evals_dev = b.take<Fr>(n_queries + 8); pk->points_dev = b.take<Fr>(16); pk->coeff_dev = b.take<Fr>(n_queries + 8);
-    pk->one_dev = b.take<Fr>(8);
-    pk->d_polyptrs = b.take<const Fr*>(std::max<size_t>(n_queries + 8, 2 * (size_t)m + 8)); pk->d_pidx = b.take<uint32_t>(n_queries + 8);
-    pk->d_status = b.take<uint32_t>(64);
-    pk->lookup_ws_stride = (lookup_workspace_bytes(pk->usable) + 255) & ~(size_t)255;
-    pk->lookup_ws = b.take<uint8_t>(pk->lookup_ws_stride * zg_ctx::N_SIDE);
-    pk->table_cache_stride = (lookup_table_bytes(pk->usable) + 255) & ~(size_t)255;
-    pk->table_cache = b.take<uint8_t>(pk->table_cache_stride * (Lk + 1));
-    pk->rnd_words_dev = b.take<uint64_t>(8 * pk->n_draws);
-    if (!pass) {
-      cudaError_t e = cudaMalloc(&pk->arena, b.off);
-      if (e != cudaSuccess) return ctx->fail(ZG_E_NOMEM, "pk_load: device arena allocation failed");
-    }
+  pk->n_ops = ops.size(); pk->n_prog_off = prog_off.size(); pk->n_constants = d->n_constants; pk->n_queries = n_queries;
+  // two arenas, each sized by a dry pass and carved by a second one: the resident half and the per-proof workspace
+  pk->res = new PkResident();
+  {
+    size_t bytes = carve_resident(pk.get(), nullptr);
+    cudaError_t e = cudaMalloc(&pk->res->arena, bytes);
+    if (e != cudaSuccess) return ctx->fail(ZG_E_NOMEM, "pk_load: device arena allocation failed (resident half)");
+    carve_resident(pk.get(), pk->res->arena);
+    bytes = carve_workspace(pk.get(), nullptr);
+    e = cudaMalloc(&pk->arena, bytes);
+    if (e != cudaSuccess) return ctx->fail(ZG_E_NOMEM, "pk_load: device arena allocation failed (workspace half)");
+    carve_workspace(pk.get(), pk->arena);
   }
   ZG_CUDA(cudaMallocHost(&pk->rnd_words_host, 8 * pk->n_draws * sizeof(uint64_t)));
   cudaStream_t st = ctx->stream;
@@ -597,28 +688,16 @@ int zg_pk_load(zg_ctx* ctx, const zg_pk_desc* d, zg_pk** out) {
     ZG_CUDA(upload(pk->d_qcol[kind], qc[kind], st));
     ZG_CUDA(upload(pk->d_qrot[kind], qr[kind], st));
   }
-  // column pointer tables
-  std::vector<const Fr*> pb[3], pe[3];
-  for (uint32_t c = 0; c < A; c++) { pb[0].push_back(pk->adv_values + c * n); pe[0].push_back(pk->adv_cosets + c * N); }
-  for (uint32_t c = 0; c < F; c++) { pb[1].push_back(pk->fixed_values + c * n); pe[1].push_back(pk->fixed_cosets + c * N); }
-  for (uint32_t c = 0; c < I; c++) { pb[2].push_back(pk->inst_values + c * n); pe[2].push_back(pk->inst_cosets + c * N); }
-  for (int kind = 0; kind < 3; kind++) {
-    ZG_CUDA(upload(pk->d_cols_base[kind], pb[kind], st));
-    ZG_CUDA(upload(pk->d_cols_ext[kind], pe[kind], st));
+  // pointer tables: sigma cosets live in the resident half, the others name workspace columns
+  {
+    std::vector<const Fr*> scos;
+    for (uint32_t c = 0; c < m; c++) scos.push_back(pk->sigma_cosets + c * N);
+    ZG_CUDA(upload(pk->d_sigma_cosets, scos, st));
+    ZG_CUDA(cudaStreamSynchronize(st));
   }
-  std::vector<const Fr*> pcos, scos, zcos;
-  for (uint32_t c = 0; c < m; c++) {
-    uint32_t kind = pk->perm[c].first, idx = pk->perm[c].second;
-    if (kind > 2 || idx >= (kind == 0 ? A : kind == 1 ? F : I)) return ctx->fail(ZG_E_INVALID, "pk_load: bad permutation column");
-    pcos.push_back(pe[kind][idx]);
-    scos.push_back(pk->sigma_cosets + c * N);
-  }
-  for (uint32_t s = 0; s < S; s++) zcos.push_back(pk->pz_coset + s * N);
-  ZG_CUDA(upload(pk->d_perm_cosets, pcos, st));
-  ZG_CUDA(upload(pk->d_sigma_cosets, scos, st));
-  ZG_CUDA(upload(pk->d_z_cosets, zcos, st));
+  rc = upload_workspace_tables(ctx, pk.get());
+  if (rc) return rc;
   Fr onev = fr_one();
-  ZG_CUDA(cudaMemcpyAsync(pk->one_dev, &onev, sizeof(Fr), cudaMemcpyHostToDevice, st));
 
   rc = ext_domain_init(ctx, pk->ext, pk->ext_mem, pk->scratch, pk->h);
   if (rc) return rc;

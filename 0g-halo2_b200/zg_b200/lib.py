@@ -26,11 +26,11 @@ BASIS_LAGRANGE = 1
 EXPORTS = [
     "zg_version", "zg_ctx_create", "zg_ctx_destroy", "zg_last_error", "zg_sync", "zg_launch_count",
     "zg_dev_alloc", "zg_dev_free", "zg_h2d", "zg_d2h",
-    "zg_srs_load", "zg_msm", "zg_msm_batch", "zg_msm_dev",
+    "zg_srs_load", "zg_srs_share", "zg_msm", "zg_msm_batch", "zg_msm_dev",
     "zg_ntt", "zg_ntt_dev", "zg_lagrange_to_coeff", "zg_lagrange_to_coeff_dev",
     "zg_coeff_to_extended", "zg_coeff_to_extended_dev", "zg_extended_to_coeff", "zg_extended_to_coeff_dev",
     "zg_bench_int_pipe", "zg_debug_field_op", "zg_debug_keccak256", "zg_probe_enable", "zg_probe_read",
-    "zg_xorshift_seed", "zg_xorshift_fill", "zg_chacha20_seed_os", "zg_chacha20_seed", "zg_chacha20_fill", "zg_pk_load", "zg_pk_read_column", "zg_pk_free", "zg_pk_commitments", "zg_create_proof",
+    "zg_xorshift_seed", "zg_xorshift_fill", "zg_chacha20_seed_os", "zg_chacha20_seed", "zg_chacha20_fill", "zg_pk_load", "zg_pk_clone", "zg_pk_read_column", "zg_pk_free", "zg_pk_commitments", "zg_create_proof",
     "zg_pk_last_stage_ms", "zg_pk_set_transcript_repr",
     "zg_wnn_create", "zg_wnn_free", "zg_wnn_last_error", "zg_wnn_synthesize",
     "zg_comm_unique_id", "zg_comm_init", "zg_comm_destroy", "zg_ctx_set_distribution", "zg_msm_sharded_dev", "zg_msm_sharded",
@@ -73,6 +73,8 @@ def load_library() -> ctypes.CDLL:
     L.zg_h2d.argtypes = [vp, vp, vp, sz]
     L.zg_d2h.argtypes = [vp, vp, vp, sz]
     L.zg_srs_load.argtypes = [vp, u32, vp, vp]
+    L.zg_srs_share.argtypes = [vp, vp]
+    L.zg_pk_clone.argtypes = [vp, vp, ctypes.POINTER(vp)]
     L.zg_msm.argtypes = [vp, ci, vp, sz, vp]
     L.zg_msm_batch.argtypes = [vp, ci, vp, sz, sz, vp]
     L.zg_msm_dev.argtypes = [vp, ci, vp, sz, sz, sz, vp]
@@ -191,6 +193,10 @@ class Context:
             if a is not None and a.shape[0] != n:
                 raise ValueError("SRS basis must have 2^k points")
         self._ck(self._L.zg_srs_load(self._h, k, None if g is None else _ptr(g), None if gl is None else _ptr(gl)))
+
+    def srs_share(self, other: "Context"):
+        """use the SRS (bases + window tables) `other` has loaded on the same device -- no second copy"""
+        self._ck(self._L.zg_srs_share(self._h, other._h))
 
     def msm(self, basis: int, scalars) -> np.ndarray:
         s = _np(scalars, 4)

@@ -53,6 +53,11 @@ class ParamsKZG:
             ctx.srs_load(self.k, self.g, self.g_lagrange)
             self._loaded_on = ctx
 
+    def share(self, ctx: zl.Context, owner: zl.Context):
+        """`ctx` uses the device copy (bases + window tables) `owner` already holds: zg_srs_share"""
+        ctx.srs_share(owner)
+        self._loaded_on = ctx
+
 
 _warned_stand_in = False
 
@@ -157,6 +162,14 @@ class ProvingKey:
             words, constants, fc, pc = self._vk_parts
             self._vk = VerifyingKey(self.k, words, constants, fc, pc, self.transcript_repr)
         return self._vk
+
+    def clone(self, ctx: "zl.Context") -> "ProvingKey":
+        """zg_pk_clone: a key for another context of the same device that shares this key's resident columns and owns only
+        its per-proof workspace (`ctx` must hold an SRS of the same k, e.g. through `ctx.srs_share`)."""
+        h = ctypes.c_void_p()
+        ctx._ck(ctx._L.zg_pk_clone(ctx._h, self._h, ctypes.byref(h)))
+        return ProvingKey(ctx, h, self.k, self.cs, self.fixed_commitments, self.perm_commitments, self.transcript_repr,
+                          vk_parts=self._vk_parts)
 
     def stage_ms(self):
         out = (ctypes.c_float * 8)()

@@ -2,8 +2,9 @@
 
 `Wnn::proof` (/root/reference/src/wnn.rs:232-262) proves one image at a time; a proof of this size leaves a B200 idle
 during its latency-bound stretches (MSM tails, sorts, host round trips for the Fiat-Shamir challenges).  Contexts of the
-backend are independent, so `ProofService` keeps `lanes` of them per GPU -- each with its own streams, SRS window
-tables, proving key and two sets of pinned witness buffers -- and drives every lane from its own host thread (the ctypes
+backend are independent, so `ProofService` keeps `lanes` of them per GPU -- each with its own streams, per-proof
+workspace and two sets of pinned witness buffers; the SRS window tables and the key's resident columns exist once
+(`zg_srs_share`, `zg_pk_clone`) -- and drives every lane from its own host thread (the ctypes
 calls release the GIL).  Image in, proof bytes out: witness synthesis is the native `zg_wnn_synthesize`, run one image
 ahead of the proof on a helper thread per lane.
 
@@ -28,7 +29,13 @@ class _Lane:
     def __init__(self, service: "ProofService", index: int, ctx: zl.Context):
         self.ctx = ctx
         self.params = ParamsKZG(service.params.k, service.params.g, service.params.g_lagrange)
-        self.pk = service.wnn.generate_proving_key(ctx, self.params)
+        if index == 0 or not service.share:
+            self.pk = service.wnn.generate_proving_key(ctx, self.params)
+        else:
+            # read-only state exists once per GPU: the SRS window tables and the key's resident columns of lane 0
+            first = service.lanes[0]
+            self.params.share(ctx, first.ctx)
+            self.pk = first.pk.clone(ctx)
         n = 1 << self.pk.k
         # two sets of pinned advice buffers: the witness of the next image is synthesized (host, C++) into one while
         # zg_create_proof reads the other
@@ -61,9 +68,9 @@ class ProofService:
 
     def __init__(self, wnn, params: ParamsKZG, device: int = 0, lanes: int = 4,
                  rng_factory: Optional[Callable[[int], object]] = None, streams: Optional[Sequence[int]] = None,
-                 contexts: Optional[Sequence[zl.Context]] = None):
+                 contexts: Optional[Sequence[zl.Context]] = None, share: bool = True):
         assert lanes >= 1
-        self.wnn, self.params, self.device = wnn, params, device
+        self.wnn, self.params, self.device, self.share = wnn, params, device, share
         self.synth = wnn.native_synthesizer()
         self.rng_factory = rng_factory or self._os_rng
         self._owned_ctx = []

@@ -75,6 +75,9 @@ int zg_d2h(zg_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
  * Uploads both bases (n = 2^k points each; either may be NULL) and builds the fixed-base window
  * tables used by every MSM on that basis.  One SRS per context. */
 int zg_srs_load(zg_ctx* ctx, uint32_t k, const zg_g1_affine* g, const zg_g1_affine* g_lagrange);
+/* `ctx` uses the parameters `from` has loaded (both on the same device): no upload, no second set of window tables; the
+ * memory is freed with the last context that uses it.  For several contexts that prove side by side on one GPU. */
+int zg_srs_share(zg_ctx* ctx, zg_ctx* from);
 
 /* ---- MSM: arithmetic::best_multiexp via ParamsKZG::commit (basis 0) / commit_lagrange (1) --- */
 /* out = sum_i scalars[i] * basis[i], n <= 2^k */
@@ -158,6 +161,10 @@ int zg_pk_commitments(zg_ctx* ctx, const zg_pk* pk, zg_g1_affine* fixed_out, zg_
  * (zeta coset of size 2^extended_k) and are rebuilt by the caller with zg_coeff_to_extended. */
 enum { ZG_PK_FIXED_VALUES = 0, ZG_PK_FIXED_POLYS = 1, ZG_PK_SIGMA_VALUES = 2, ZG_PK_SIGMA_POLYS = 3 };
 int zg_pk_read_column(zg_ctx* ctx, const zg_pk* pk, int what, uint32_t index, zg_fr* out);
+/* A second key over the SAME resident columns (fixed / sigma forms, domain tables, programs: 672 MiB at k = 17 that are
+ * read-only after zg_pk_load): own per-proof workspace, usable from another context of the same device whose SRS has the
+ * same k.  Both keys are freed with zg_pk_free; the shared half goes with the last one. */
+int zg_pk_clone(zg_ctx* ctx, const zg_pk* src, zg_pk** out);
 
 /* advice: num_advice columns of 2^k values, host pointers (or device pointers on the context's device: the
  * copy is direction-agnostic); rows >= 2^k - blinding_factors - 1 are replaced by blinding scalars; instances:
