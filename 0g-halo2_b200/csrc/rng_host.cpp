@@ -6,6 +6,7 @@
 #include <cerrno>
 #include <cstdint>
 #include <cstring>
+#include <thread>
 #include <sys/random.h>
 #include "../../include/zg_b200.h"
 
@@ -99,6 +100,24 @@ void zg_chacha20_fill(void* state, uint64_t* out, size_t n) {
       const size_t take = left < r->have ? left : r->have;
       memcpy(dst, r->buf + (64 - r->have), take);
       r->have -= (uint32_t)take; dst += take; left -= take;
+      continue;
+    }
+    if (left >= ((size_t)1 << 20)) {
+      // a k = 17 proof draws 8.4 MB for its random polynomial while the GPU commits the advice columns (2.3 ms): the
+      // keystream is seekable, so a large request is cut into four ranges of whole block runs generated side by side
+      const size_t runs = left / sizeof(tmp);
+      const int T = 4;
+      const size_t per = (runs + T - 1) / T;
+      std::thread th[T];
+      for (int t = 0; t < T; t++) {
+        const size_t r0 = (size_t)t * per, r1 = r0 + per < runs ? r0 + per : runs;
+        th[t] = std::thread([=]() {
+          for (size_t q = r0; q < r1; q++) chacha20_blocks(r->key, r->counter + q * LANES, r->nonce, dst + q * sizeof(tmp));
+        });
+      }
+      for (int t = 0; t < T; t++) th[t].join();
+      r->counter += runs * LANES;
+      dst += runs * sizeof(tmp); left -= runs * sizeof(tmp);
       continue;
     }
     if (left >= sizeof(tmp)) {                       // whole runs of LANES blocks go straight to the destination
