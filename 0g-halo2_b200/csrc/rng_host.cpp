@@ -5,6 +5,7 @@
 // generated lane-parallel -- the loops over `l` vectorise (AVX2 clone picked at load time, baseline SSE2 otherwise).
 #include <cerrno>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <sys/random.h>
@@ -104,11 +105,15 @@ void zg_chacha20_fill(void* state, uint64_t* out, size_t n) {
     }
     if (left >= ((size_t)1 << 20)) {
       // a k = 17 proof draws 8.4 MB for its random polynomial while the GPU commits the advice columns (2.3 ms): the
-      // keystream is seekable, so a large request is cut into four ranges of whole block runs generated side by side
+      // keystream is seekable, so a large request is cut into ranges of whole block runs generated side by side
       const size_t runs = left / sizeof(tmp);
-      const int T = 4;
+      static const int T = [] {                     // two threads by default: several lanes and ranks share the host
+        const char* e = getenv("ZG_RNG_THREADS");
+        int v = e ? atoi(e) : 2;
+        return v < 1 ? 1 : v > 8 ? 8 : v;
+      }();
       const size_t per = (runs + T - 1) / T;
-      std::thread th[T];
+      std::thread th[8];
       for (int t = 0; t < T; t++) {
         const size_t r0 = (size_t)t * per, r1 = r0 + per < runs ? r0 + per : runs;
         th[t] = std::thread([=]() {
