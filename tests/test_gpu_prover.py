@@ -202,3 +202,32 @@ def test_key_files_round_trip_through_the_gpu(ctx, tiny, tmp_path):
     assert vk.verify(params, [outputs], proof2)
     pk2.close()
     pk.close()
+
+
+def test_cloned_key_and_shared_srs(ctx, tiny):
+    """zg_srs_share / zg_pk_clone: a second context of the same GPU proves with the first one's window tables and the first
+    key's resident columns -- the same bytes as the original -- and keeps working after the original key and context are gone
+    (the shared halves are reference-counted)."""
+    import zg_b200
+    from zg_b200.prover import ParamsKZG, create_proof, keygen
+    wnn, img, k, srs = tiny
+    outputs = wnn.predict(img)
+    _, asm = wnn.synthesize(img, k)
+    first = zg_b200.Context(0)
+    params = ParamsKZG(k, srs.g, srs.g_lagrange, srs.g2, srs.s_g2)
+    circ, asm0 = wnn.synthesize(np.zeros((28, 28), dtype=np.uint8), k)
+    pk = keygen(first, params, circ.cs, asm0)
+    proof = create_proof(params, pk, asm.advice, [outputs], zg_b200.lib.XorShift.from_seed(SEED))
+    second = zg_b200.Context(0)
+    with pytest.raises(zg_b200.ZgError):
+        pk.clone(second)                                   # no SRS on that context yet
+    params2 = ParamsKZG(k, srs.g, srs.g_lagrange)
+    params2.share(second, first)
+    pk2 = pk.clone(second)
+    assert create_proof(params2, pk2, asm.advice, [outputs], zg_b200.lib.XorShift.from_seed(SEED)) == proof
+    pk.close()
+    first.close()
+    again = create_proof(params2, pk2, asm.advice, [outputs], zg_b200.lib.XorShift.from_seed(SEED))
+    assert again == proof and pk2.get_vk().verify(params, [outputs], again)
+    pk2.close()
+    second.close()
