@@ -231,3 +231,32 @@ def test_cloned_key_and_shared_srs(ctx, tiny):
     assert again == proof and pk2.get_vk().verify(params, [outputs], again)
     pk2.close()
     second.close()
+
+
+def test_small_gadget_circuit_proof_matches_oracle(ctx):
+    """The prover is not specific to the WNN circuit: the hash gadget's test circuit (src/gadgets/hash.rs:222-372) at k = 9 --
+    one lookup, degree-5 gates, 2^10-point extended blocks, the smallest MSM windows -- gives the oracle's bytes and verifies."""
+    import zg_b200
+    from test_frontend_pinned import hash_circuit
+    from zg_b200.plonk.circuit import Assembly, SimpleFloorPlanner
+    from zg_b200.prover import ParamsKZG, create_proof, keygen
+    k = 9
+    srs = H.Srs(k, 0x1234567)
+
+    def synth(x):
+        cs, fn = hash_circuit(x)
+        asm = Assembly(cs, k)
+        fn(SimpleFloorPlanner(asm))
+        return cs, asm
+    cs0, asm0 = synth(42)
+    opk = H.keygen(srs, cs0, asm0)
+    oproof = H.create_proof(srs, opk, asm0.advice, [[3]], H.XorShiftRng(SEED))
+    assert H.verify_proof(srs, opk, [[3]], oproof)
+    cs1, asm1 = synth(42)
+    params = ParamsKZG(k, srs.g, srs.g_lagrange, srs.g2, srs.s_g2)
+    pk = keygen(ctx, params, cs1, asm1)
+    assert pk.fixed_commitments == opk.fixed_commitments and pk.perm_commitments == opk.perm_commitments
+    proof = create_proof(params, pk, asm1.advice, [[3]], zg_b200.lib.XorShift.from_seed(SEED))
+    assert proof == oproof
+    assert pk.get_vk().verify(params, [[3]], proof) and not pk.get_vk().verify(params, [[2]], proof)
+    pk.close()

@@ -147,3 +147,29 @@ def test_vk_file_round_trip_verifies(tiny_case, tmp_path):
     circ4, _ = wnn.synthesize(np.zeros(wnn.img_shape(), dtype=np.uint8), k)
     with pytest.raises(ValueError):
         load_verifying_key(circ4.cs, pyio.BytesIO(raw + b"\0"))
+
+
+def test_verifier_on_a_gadget_circuit():
+    """not specific to the WNN circuit: the hash gadget's test circuit (src/gadgets/hash.rs:222-372) at k = 9, one instance
+    value (42^3 mod 11 mod 8 = 3)"""
+    from test_frontend_pinned import hash_circuit
+    from zg_b200.plonk.circuit import Assembly, SimpleFloorPlanner
+    k = 9
+    srs = H.Srs(k, 0x1234567)
+
+    def synth():
+        cs, fn = hash_circuit(42)
+        asm = Assembly(cs, k)
+        fn(SimpleFloorPlanner(asm))
+        return cs, asm
+    cs, asm = synth()
+    opk = H.keygen(srs, cs, asm)
+    proof = H.create_proof(srs, opk, asm.advice, [[3]], H.XorShiftRng(bytes(range(16))))
+    cs1, asm1 = synth()
+    finalize_fixed(cs1, asm1)
+    words, constants = serialize_cs(cs1)
+    vk = VerifyingKey(k, words, constants, bn254.g1_affine_to_limbs(opk.fixed_commitments),
+                      bn254.g1_affine_to_limbs(opk.perm_commitments), opk.transcript_repr)
+    params = ParamsKZG(k, srs.g, srs.g_lagrange, srs.g2, srs.s_g2)
+    assert vk.verify(params, [[3]], proof) and H.verify_proof(srs, opk, [[3]], proof)
+    assert not vk.verify(params, [[2]], proof) and not H.verify_proof(srs, opk, [[2]], proof)
