@@ -197,6 +197,7 @@ void zg_ctx_destroy(zg_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->comm) zg_comm_destroy(ctx);
   if (ctx->d_gather) cudaFree(ctx->d_gather);
+  if (ctx->d_gather_fr) cudaFree(ctx->d_gather_fr);
   ctx->srs_release();
   for (auto& kv : ctx->domains) cudaFree(kv.second.tw);
   if (ctx->ws_msm.p) cudaFree(ctx->ws_msm.p);

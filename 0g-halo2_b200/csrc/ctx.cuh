@@ -84,6 +84,8 @@ struct zg_ctx {
   bool dist_columns = false;
   zg::G1Jac* d_gather = nullptr;
   size_t gather_cap = 0;
+  zg::Fr* d_gather_fr = nullptr;       // staging of dist_allgather_blocks
+  size_t gather_fr_cap = 0;
 
   zg::Workspace ws_msm, ws_ntt, ws_stage;
   zg::G1Jac* d_msm_out = nullptr;  // small result staging (64 results)
@@ -107,6 +109,8 @@ int msm_dev_mixed(zg_ctx* ctx, int basis, const Fr* scalars_dev, size_t stride, 
                   G1Jac* out_dev);
 // the commitments of one round into ctx->d_msm_out[0..count) -- locally, or spread over the ranks of ctx->comm (dist.cu)
 int msm_round(zg_ctx* ctx, int basis, const Fr* cols, size_t stride, size_t n, size_t count, uint32_t other_mask);
+// col holds nblocks blocks of B elements; block c was computed by rank c mod G: all-gather so that every rank holds all of them
+int dist_allgather_blocks(zg_ctx* ctx, Fr* col, size_t B, uint32_t nblocks);
 }  // namespace zg
 
 // CUDA's current device is per host thread: every entry point selects the context's device first

@@ -127,6 +127,39 @@ int msm_round(zg_ctx* ctx, int basis, const Fr* cols, size_t stride, size_t n, s
   return ZG_OK;
 }
 
+int dist_allgather_blocks(zg_ctx* ctx, Fr* col, size_t B, uint32_t nblocks) {
+  NcclApi* a = nccl_api();
+  if (!a || !ctx->comm) return ctx->fail(ZG_E_STATE, "NCCL is not available");
+  const uint32_t G = (uint32_t)ctx->nranks, rank = (uint32_t)ctx->rank;
+  const uint32_t per = (nblocks + G - 1) / G;
+  const size_t need = (size_t)per * B * (G + 1);
+  if (ctx->gather_fr_cap < need) {
+    if (ctx->d_gather_fr) cudaFree(ctx->d_gather_fr);
+    ctx->d_gather_fr = nullptr;
+    ctx->gather_fr_cap = 0;
+    cudaError_t e = cudaMalloc(&ctx->d_gather_fr, sizeof(Fr) * need);
+    if (e != cudaSuccess) return ctx->cuda_fail(e, "gather buffer");
+    ctx->gather_fr_cap = need;
+  }
+  Fr* mine = ctx->d_gather_fr;                 // per blocks, then the gathered G * per
+  Fr* all = mine + (size_t)per * B;
+  for (uint32_t i = 0; i < per; i++) {
+    const uint32_t c = rank + i * G;
+    if (c < nblocks)
+      ZG_CUDA(cudaMemcpyAsync(mine + (size_t)i * B, col + (size_t)c * B, sizeof(Fr) * B, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  ncclResult_t r = a->AllGather(mine, all, sizeof(Fr) * per * B, ncclUint8, (ncclComm_t)ctx->comm, ctx->stream);
+  if (r != ncclSuccess) return nccl_fail(ctx, r, "ncclAllGather");
+  for (uint32_t g = 0; g < G; g++)
+    for (uint32_t i = 0; i < per; i++) {
+      const uint32_t c = g + i * G;
+      if (c < nblocks && g != rank)
+        ZG_CUDA(cudaMemcpyAsync(col + (size_t)c * B, all + ((size_t)g * per + i) * B, sizeof(Fr) * B, cudaMemcpyDeviceToDevice,
+                                ctx->stream));
+    }
+  return ZG_OK;
+}
+
 }  // namespace zg
 
 extern "C" {

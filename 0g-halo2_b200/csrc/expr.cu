@@ -89,7 +89,7 @@ __device__ Fr compress(const ExprEnv& E, const uint32_t* prog_off, uint32_t firs
 
 __global__ void __launch_bounds__(EX_THREADS) k_compress_lookups(ExprEnv E, LookupProgs lp, Fr theta, Fr* out_in, Fr* out_tab,
                                                                  size_t out_stride) {
-  uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t idx = E.row0 + blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t l = blockIdx.y;
   if (idx >= E.size) return;
   stf(out_in + l * out_stride + idx, compress(E, lp.prog_off, lp.in_first[l], lp.in_count[l], theta, idx));
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(EX_THREADS) k_compress_lookups(ExprEnv E, Look
 }
 
 __global__ void __launch_bounds__(EX_THREADS) k_h_gates(ExprEnv E, const uint32_t* prog_off, uint32_t nprogs, Fr y, Fr* h) {
-  uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t idx = E.row0 + blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= E.size) return;
   Fr acc = fp_zero<FrParams>();
   for (uint32_t p = 0; p < nprogs; p++) acc = fp_add(fp_mul(acc, y), eval_program(E, prog_off[p], prog_off[p + 1], idx));
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(EX_THREADS) k_h_gates(ExprEnv E, const uint32_
 }
 
 __global__ void __launch_bounds__(EX_THREADS) k_h_permutation(PermEnv P, Fr beta, Fr gamma, Fr y, Fr delta, Fr* h) {
-  uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t idx = P.row0 + blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= P.size) return;
   const uint32_t r_next = rot_idx(idx, 1, P.rot_scale, P.wrap_mask);
   const uint32_t r_last = rot_idx(idx, P.last_rot, P.rot_scale, P.wrap_mask);
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(EX_THREADS) k_h_permutation(PermEnv P, Fr beta
 
 __global__ void __launch_bounds__(EX_THREADS) k_h_lookup(ExprEnv E, LookupProgs lp, uint32_t l, LookupHEnv L, Fr theta, Fr beta,
                                                          Fr gamma, Fr y, Fr* h) {
-  uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t idx = E.row0 + blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= E.size) return;
   const uint32_t r_next = rot_idx(idx, 1, E.rot_scale, E.wrap_mask);
   const uint32_t r_prev = rot_idx(idx, -1, E.rot_scale, E.wrap_mask);
@@ -173,23 +173,23 @@ inline uint32_t nblk(uint32_t n) { return (n + EX_THREADS - 1) / EX_THREADS; }
 void expr_compress_lookups(const ExprEnv& env, const LookupProgs& lp, uint32_t n_lookups, const Fr& theta, Fr* out_in, Fr* out_tab,
                            size_t out_stride, cudaStream_t st, LaunchCounter lc) {
   if (!n_lookups) return;
-  k_compress_lookups<<<dim3(nblk(env.size), n_lookups), EX_THREADS, 0, st>>>(env, lp, theta, out_in, out_tab, out_stride);
+  k_compress_lookups<<<dim3(nblk(env.size - env.row0), n_lookups), EX_THREADS, 0, st>>>(env, lp, theta, out_in, out_tab, out_stride);
   lc++;
 }
 void expr_h_gates(const ExprEnv& env, const uint32_t* prog_off, uint32_t n_gate_progs, const Fr& y, Fr* h, cudaStream_t st,
                   LaunchCounter lc) {
-  k_h_gates<<<nblk(env.size), EX_THREADS, 0, st>>>(env, prog_off, n_gate_progs, y, h);
+  k_h_gates<<<nblk(env.size - env.row0), EX_THREADS, 0, st>>>(env, prog_off, n_gate_progs, y, h);
   lc++;
 }
 void expr_h_permutation(const PermEnv& pe, const Fr& beta, const Fr& gamma, const Fr& y, const Fr& delta, Fr* h, cudaStream_t st,
                         LaunchCounter lc) {
   if (!pe.nsets) return;
-  k_h_permutation<<<nblk(pe.size), EX_THREADS, 0, st>>>(pe, beta, gamma, y, delta, h);
+  k_h_permutation<<<nblk(pe.size - pe.row0), EX_THREADS, 0, st>>>(pe, beta, gamma, y, delta, h);
   lc++;
 }
 void expr_h_lookup(const ExprEnv& env, const LookupProgs& lp, uint32_t l, const LookupHEnv& le, const Fr& theta, const Fr& beta,
                    const Fr& gamma, const Fr& y, Fr* h, cudaStream_t st, LaunchCounter lc) {
-  k_h_lookup<<<nblk(env.size), EX_THREADS, 0, st>>>(env, lp, l, le, theta, beta, gamma, y, h);
+  k_h_lookup<<<nblk(env.size - env.row0), EX_THREADS, 0, st>>>(env, lp, l, le, theta, beta, gamma, y, h);
   lc++;
 }
 

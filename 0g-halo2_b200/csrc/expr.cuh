@@ -18,7 +18,8 @@ struct ExprEnv {
   const int32_t* qrot[3];        // query -> rotation
   const Fr* constants;           // constant pool (Montgomery)
   const uint32_t* ops;           // all programs, concatenated
-  uint32_t size;                 // rows: 2^k, or cosets * B on the extended domain (extdomain.cuh)
+  uint32_t row0 = 0;             // the launch covers rows [row0, size): a rank's coset block when a proof is spread over GPUs
+  uint32_t size;                 // end row: 2^k, or cosets * B on the extended domain (extdomain.cuh)
   uint32_t rot_scale;            // 1 on the 2^k domain, B / n on the extended domain
   uint32_t wrap_mask;            // rotations wrap inside blocks of wrap_mask + 1 rows (2^k - 1, or B - 1)
 };
@@ -48,6 +49,7 @@ struct PermEnv {
   const Fr* l_active;
   const Fr* coset_x;             // X = zeta * ext_omega^idx
   uint32_t nsets, m, chunk, size, rot_scale, wrap_mask;
+  uint32_t row0 = 0;             // rows [row0, size)
   int32_t last_rot;              // -(blinding_factors + 1)
 };
 void expr_h_permutation(const PermEnv& pe, const Fr& beta, const Fr& gamma, const Fr& y, const Fr& delta, Fr* h,

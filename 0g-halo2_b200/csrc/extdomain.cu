@@ -124,8 +124,10 @@ int ext_domain_init(zg_ctx* ctx, ExtDomain& d, Fr* mem, Fr* scratch, Fr* fill) {
   return ZG_OK;
 }
 
-int ext_from_coeff(zg_ctx* ctx, const ExtDomain& d, const Fr* coeff, size_t in_stride, Fr* out, size_t out_stride, size_t batch) {
-  if (batch == 0) return ZG_OK;
+int ext_from_coeff(zg_ctx* ctx, const ExtDomain& d, const Fr* coeff, size_t in_stride, Fr* out, size_t out_stride, size_t batch,
+                   uint32_t first, uint32_t step) {
+  if (batch == 0 || first >= d.cosets) return ZG_OK;
+  const uint32_t mine = (d.cosets - first + step - 1) / step;
   if (batch * d.cosets > 65535) return ctx->fail(ZG_E_INVALID, "ext_from_coeff: batch too large");
   Domain* dom;
   int rc = get_domain(ctx, d.bk, d.omega_B, &dom);
@@ -137,7 +139,7 @@ int ext_from_coeff(zg_ctx* ctx, const ExtDomain& d, const Fr* coeff, size_t in_s
   P.out = out; P.out_stride = out_stride; P.out_coset_stride = d.B;
   P.tmp = (Fr*)ctx->ws_ntt.p; P.tmp_stride = d.B;
   P.tw = dom->tw;
-  P.logn = d.bk; P.batch = (uint32_t)batch; P.cosets = d.cosets;
+  P.logn = d.bk; P.batch = (uint32_t)batch; P.cosets = mine; P.coset_first = first; P.coset_step = step;
   P.n_in = (uint32_t)d.n; P.n_out = (uint32_t)d.B; P.flags = 0;
   for (int i = 0; i < 3; i++) P.in_scale[i] = P.out_scale[i] = fp_one<FrParams>();
   P.in_table = d.pow_tab; P.in_table_stride = d.n;

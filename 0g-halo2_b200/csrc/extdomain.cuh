@@ -37,7 +37,9 @@ inline size_t ext_domain_table_elems(const ExtDomain& d) { return d.cosets * (d.
 // fill_buf >= B Fr
 int ext_domain_init(zg_ctx* ctx, ExtDomain& d, Fr* mem, Fr* scan_scratch, Fr* fill_buf);
 // `batch` polynomials of n coefficients (stride in_stride) -> their values on D (stride out_stride >= N)
-int ext_from_coeff(zg_ctx* ctx, const ExtDomain& d, const Fr* coeff, size_t in_stride, Fr* out, size_t out_stride, size_t batch);
+// only the coset blocks first, first + step, ... are computed (the others are left untouched): a rank's share of the rows
+int ext_from_coeff(zg_ctx* ctx, const ExtDomain& d, const Fr* coeff, size_t in_stride, Fr* out, size_t out_stride, size_t batch,
+                   uint32_t first = 0, uint32_t step = 1);
 // values on D of a polynomial of degree < N -> its first `keep` coefficients; work holds N elements
 int ext_to_coeff(zg_ctx* ctx, const ExtDomain& d, const Fr* ext, Fr* work, size_t keep, Fr* out);
 // h[i] /= (X_i^n - 1)

@@ -86,8 +86,9 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(NttPassArgs A) {
   const uint32_t S = A.S, logc = A.logc, lo = A.lo, logn = A.logn;
   const uint32_t R = 1u << S, C = 1u << logc;
   const uint32_t poly = blockIdx.y / A.cosets, cz = blockIdx.y - poly * A.cosets;
-  const Fr* in = A.in + (size_t)poly * A.in_stride + (size_t)cz * A.in_coset_stride;
-  Fr* out = A.out + (size_t)poly * A.out_stride + (size_t)cz * A.out_coset_stride;
+  const uint32_t ctab = A.tab_cid_base + cz * A.tab_cid_step;
+  const Fr* in = A.in + (size_t)poly * A.in_stride + (size_t)(A.in_cid_base + cz * A.in_cid_step) * A.in_coset_stride;
+  Fr* out = A.out + (size_t)poly * A.out_stride + (size_t)(A.out_cid_base + cz * A.out_cid_step) * A.out_coset_stride;
   const uint32_t tile = blockIdx.x;
   const uint32_t tid = threadIdx.x;
   const uint32_t total = R << logc;
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(NttPassArgs A) {
       Fr v;
       if (idx < A.n_in) {
         v = ld_fr(in + idx);
-        if (A.in_table) v = fp_mul(v, ld_fr(A.in_table + (size_t)cz * A.in_table_stride + idx));
+        if (A.in_table) v = fp_mul(v, ld_fr(A.in_table + (size_t)ctab * A.in_table_stride + idx));
         else if (A.flags & NTT_IN_COSET) {
           uint32_t m = idx % 3;
           if (m) v = fp_mul(v, A.in_scale[m]);
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(NttPassArgs A) {
       Fr v;
       if (idx < A.n_in) {
         v = ld_fr(in + idx);
-        if (A.in_table) v = fp_mul(v, ld_fr(A.in_table + (size_t)cz * A.in_table_stride + idx));
+        if (A.in_table) v = fp_mul(v, ld_fr(A.in_table + (size_t)ctab * A.in_table_stride + idx));
         else if (A.flags & NTT_IN_COSET) {
           uint32_t m = idx % 3;
           if (m) v = fp_mul(v, A.in_scale[m]);
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(NttPassArgs A) {
       uint32_t pos = (jr << (logn - S)) | (rest_rev << logc) | cr;
       if (pos >= A.n_out) continue;
       Fr v = sm.get((c << S) | j);
-      if (A.out_table) v = fp_mul(v, ld_fr(A.out_table + (size_t)cz * A.out_table_stride + pos));
+      if (A.out_table) v = fp_mul(v, ld_fr(A.out_table + (size_t)ctab * A.out_table_stride + pos));
       else if (A.flags & NTT_OUT_SCALE) v = fp_mul(v, A.out_scale[(A.flags & NTT_OUT_MOD3) ? pos % 3 : 0]);
       st_fr(out + pos, v);
     }
@@ -251,6 +252,9 @@ cudaError_t ntt_run(const NttPlan& P, cudaStream_t stream, uint64_t* nl) {
     A.in = first ? P.in : P.tmp;
     A.in_stride = first ? P.in_stride : P.tmp_stride * cosets;
     A.in_coset_stride = first ? P.in_coset_stride : P.tmp_stride;
+    A.tab_cid_base = P.coset_first; A.tab_cid_step = P.coset_step;
+    A.in_cid_base = first ? P.coset_first : 0; A.in_cid_step = first ? P.coset_step : 1;
+    A.out_cid_base = last ? P.coset_first : 0; A.out_cid_step = last ? P.coset_step : 1;
     if (last) {
       A.out = P.out;
       A.out_stride = P.out_stride;

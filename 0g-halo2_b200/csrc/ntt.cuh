@@ -37,6 +37,9 @@ struct NttPassArgs {
   Fr out_scale[3];
   // per-element scale tables and several cosets per polynomial (see NttPlan)
   uint32_t cosets;
+  // coset slot z of this launch is coset id base + z * step for the input offset / the output offset / the tables
+  // (a rank that owns a subset of the cosets; dense slots in the scratch passes in between)
+  uint32_t in_cid_base, in_cid_step, out_cid_base, out_cid_step, tab_cid_base, tab_cid_step;
   size_t in_coset_stride, out_coset_stride, in_table_stride, out_table_stride;
   const Fr* in_table;
   const Fr* out_table;
@@ -55,6 +58,7 @@ struct NttPlan {
   // `cosets` transforms per polynomial that differ in the per-element input table (coset c multiplies input i by
   // in_table[c * in_table_stride + i]) or output table: the prover's 3 x 2n extended domain (extdomain.cuh)
   uint32_t cosets = 1;
+  uint32_t coset_first = 0, coset_step = 1;     // the launch covers coset ids coset_first + z * coset_step, z < cosets
   size_t in_coset_stride = 0, out_coset_stride = 0;
   const Fr* in_table = nullptr;
   size_t in_table_stride = 0;

@@ -186,6 +186,7 @@ struct zg_pk {
   size_t n = 0, N = 0;                        // N = ext.N rows of the internal extended domain
   ExtDomain ext;
   Fr* ext_mem = nullptr;
+  uint32_t blk_first = 0, blk_step = 1;       // coset blocks this rank computes in the current proof (all: 0, 1)
   uint32_t A = 0, F = 0, I = 0, degree = 0, bf = 0, usable = 0, qdeg = 0;
   std::vector<std::pair<uint32_t, int32_t>> q[3];
   std::vector<std::pair<uint32_t, uint32_t>> perm;  // (kind, index)
@@ -375,20 +376,21 @@ static ExprEnv make_env(const zg_pk* pk, bool ext) {
 // extended-coset forms of the per-proof polynomials (coefficient form -> zeta * <omega_ext>), in the batches the prover
 // builds them: advice + instance, lookup permuted [a | s], product polynomials (permutation z, lookup z)
 static int coset_advice_instance(zg_ctx* ctx, zg_pk* pk) {
-  int rc = ext_from_coeff(ctx, pk->ext, pk->adv_polys, pk->n, pk->adv_cosets, pk->N, pk->A);
+  int rc = ext_from_coeff(ctx, pk->ext, pk->adv_polys, pk->n, pk->adv_cosets, pk->N, pk->A, pk->blk_first, pk->blk_step);
   if (rc || !pk->I) return rc;
-  return ext_from_coeff(ctx, pk->ext, pk->inst_polys, pk->n, pk->inst_cosets, pk->N, pk->I);
+  return ext_from_coeff(ctx, pk->ext, pk->inst_polys, pk->n, pk->inst_cosets, pk->N, pk->I, pk->blk_first, pk->blk_step);
 }
 static int coset_lookup_permuted(zg_ctx* ctx, zg_pk* pk) {
   if (!pk->n_lookups) return ZG_OK;
-  return ext_from_coeff(ctx, pk->ext, pk->pa_poly, pk->n, pk->lk_cosets, pk->N, 2 * pk->n_lookups);
+  return ext_from_coeff(ctx, pk->ext, pk->pa_poly, pk->n, pk->lk_cosets, pk->N, 2 * pk->n_lookups, pk->blk_first, pk->blk_step);
 }
 static int coset_products(zg_ctx* ctx, zg_pk* pk) {
   int rc = ZG_OK;
   if (pk->nsets)
-    rc = ext_from_coeff(ctx, pk->ext, pk->pz_poly, pk->n, pk->pz_coset, pk->N, pk->nsets);
+    rc = ext_from_coeff(ctx, pk->ext, pk->pz_poly, pk->n, pk->pz_coset, pk->N, pk->nsets, pk->blk_first, pk->blk_step);
   if (rc || !pk->n_lookups) return rc;
-  return ext_from_coeff(ctx, pk->ext, pk->lz_poly, pk->n, pk->lk_cosets + 2 * (size_t)pk->n_lookups * pk->N, pk->N, pk->n_lookups);
+  return ext_from_coeff(ctx, pk->ext, pk->lz_poly, pk->n, pk->lk_cosets + 2 * (size_t)pk->n_lookups * pk->N, pk->N, pk->n_lookups,
+                        pk->blk_first, pk->blk_step);
 }
 
 // Evaluator::evaluate_h: reads the coefficient forms in the pk workspace (adv_polys, inst_polys, pz_poly, pa_poly | ps_poly,
@@ -410,23 +412,33 @@ static int quotient_numerator(zg_ctx* ctx, zg_pk* pk, const Fr& theta, const Fr&
     rc = coset_lookup_permuted(ctx, pk);
     if (rc) return rc;
   }
-  ExprEnv ext_env = make_env(pk, true);
-  expr_h_gates(ext_env, pk->prog_off, pk->n_gate_progs, y, pk->h, st, lc);
-  if (S) {
-    PermEnv pe;
-    pe.z_cosets = pk->d_z_cosets; pe.col_cosets = pk->d_perm_cosets; pe.sigma_cosets = pk->d_sigma_cosets;
-    pe.l0 = pk->l0; pe.l_last = pk->l_last; pe.l_active = pk->l_active; pe.coset_x = pk->coset_x;
-    pe.nsets = S; pe.m = m; pe.chunk = pk->chunk; pe.size = (uint32_t)N; pe.rot_scale = pk->rot_scale;
-    pe.wrap_mask = (uint32_t)(pk->ext.B - 1);
-    pe.last_rot = -(int32_t)(bf + 1);
-    expr_h_permutation(pe, beta, gamma, y, pk->delta, pk->h, st, lc);
-  }
-  if (Lk) {
-    Fr* as_cos = pk->lk_cosets;                           // [a | s] (2 Lk columns), then z (Lk)
-    Fr* z_cos = pk->lk_cosets + 2 * (size_t)Lk * N;
-    for (uint32_t l = 0; l < Lk; l++) {
-      LookupHEnv le{z_cos + l * N, as_cos + l * N, as_cos + (Lk + l) * N, pk->l0, pk->l_last, pk->l_active};
-      expr_h_lookup(ext_env, lp, l, le, theta, beta, gamma, y, pk->h, st, lc);
+  // rows: the whole domain, or -- when the proof is spread over GPUs -- the coset blocks this rank owns (rotations
+  // never leave a block, so a block's rows need nothing from the others)
+  const bool all_rows = pk->blk_first == 0 && pk->blk_step == 1;
+  for (uint32_t c = pk->blk_first; c < (all_rows ? 1u : pk->ext.cosets); c += pk->blk_step) {
+    ExprEnv ext_env = make_env(pk, true);
+    if (!all_rows) {
+      ext_env.row0 = (uint32_t)(c * pk->ext.B);
+      ext_env.size = (uint32_t)((c + 1) * pk->ext.B);
+    }
+    expr_h_gates(ext_env, pk->prog_off, pk->n_gate_progs, y, pk->h, st, lc);
+    if (S) {
+      PermEnv pe;
+      pe.z_cosets = pk->d_z_cosets; pe.col_cosets = pk->d_perm_cosets; pe.sigma_cosets = pk->d_sigma_cosets;
+      pe.l0 = pk->l0; pe.l_last = pk->l_last; pe.l_active = pk->l_active; pe.coset_x = pk->coset_x;
+      pe.nsets = S; pe.m = m; pe.chunk = pk->chunk; pe.rot_scale = pk->rot_scale;
+      pe.row0 = ext_env.row0; pe.size = ext_env.size;
+      pe.wrap_mask = (uint32_t)(pk->ext.B - 1);
+      pe.last_rot = -(int32_t)(bf + 1);
+      expr_h_permutation(pe, beta, gamma, y, pk->delta, pk->h, st, lc);
+    }
+    if (Lk) {
+      Fr* as_cos = pk->lk_cosets;                           // [a | s] (2 Lk columns), then z (Lk)
+      Fr* z_cos = pk->lk_cosets + 2 * (size_t)Lk * N;
+      for (uint32_t l = 0; l < Lk; l++) {
+        LookupHEnv le{z_cos + l * N, as_cos + l * N, as_cos + (Lk + l) * N, pk->l0, pk->l_last, pk->l_active};
+        expr_h_lookup(ext_env, lp, l, le, theta, beta, gamma, y, pk->h, st, lc);
+      }
     }
   }
   return ZG_OK;
@@ -837,6 +849,11 @@ static int create_proof_impl(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice,
   cudaStream_t st = ctx->stream;
   LaunchCounter lc{&ctx->launches};
   int rc;
+  // a proof spread over GPUs (dist.cu): this rank builds the extended forms and the quotient numerator only on the coset
+  // blocks c = rank (mod G); the blocks of h are all-gathered before the division by the vanishing polynomial
+  const bool dist_rows = ctx->comm && ctx->nranks > 1 && ctx->dist_columns && pk->ext.cosets > 1;
+  pk->blk_first = dist_rows ? (uint32_t)ctx->rank : 0;
+  pk->blk_step = dist_rows ? (uint32_t)ctx->nranks : 1;
   struct StageEvents {                       // destroyed on every return path
     cudaEvent_t e[9] = {};
     ~StageEvents() { for (auto x : e) if (x) cudaEventDestroy(x); }
@@ -1080,6 +1097,10 @@ static int create_proof_impl(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice,
   ZG_CUDA(join_aux(ctx));   // every coset form is ready
   rc = quotient_numerator(ctx, pk, theta, beta, gamma, y, /*transform=*/false);
   if (rc) return rc;
+  if (dist_rows) {
+    rc = dist_allgather_blocks(ctx, pk->h, pk->ext.B, pk->ext.cosets);
+    if (rc) return rc;
+  }
   ZG_CUDA(cudaEventRecord(ev[4], st));
   // ---- 8. vanishing::construct: divide, back to coefficients, commit the pieces ---------------------------------------------
   ext_divide_by_vanishing(pk->ext, pk->h, st, lc);
@@ -1251,6 +1272,8 @@ int zg_evaluate_h(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice_polys, cons
   ZG_CUDA(up(pk->lz_poly, lookup_product_polys, Lk));
   Fr ch[4];
   memcpy(ch, challenges, sizeof(ch));   // theta, beta, gamma, y
+  pk->blk_first = 0;
+  pk->blk_step = 1;
   int rc = quotient_numerator(ctx, pk, ch[0], ch[1], ch[2], ch[3], /*transform=*/true);
   if (rc) return rc;
   // The numerator lives on the internal domain (extdomain.cuh).  The ABI speaks halo2's coset zeta * <omega_ext>:
