@@ -5,10 +5,12 @@
 //   zg_msm_sharded*      ONE large MSM split by point range (BASELINE configs[3] / [4]): rank g holds bases
 //                        [g n/G, (g+1) n/G) and their window table, computes a partial sum; ncclAllGather of G x 96 B
 //                        and G - 1 device-side additions (EC addition is not an NCCL reduction, so no all-reduce).
-//   column distribution  the commitments of one Fiat-Shamir round of ONE proof spread over the ranks (column j -> rank
-//                        j mod G), results all-gathered; used by zg_create_proof when the context has a communicator and
-//                        ZG_DIST_COLUMNS is set.  Every rank runs the same proof on the same inputs and RNG stream
-//                        (SPMD), so no column ever crosses NVLink -- only 96 bytes per commitment do.
+//   spread proof         ONE proof over the ranks (zg_create_proof with ZG_DIST_COLUMNS): every rank runs the same proof on
+//                        the same inputs and RNG stream (SPMD) but computes only a share of the two heavy parts --
+//                        the commitments of a Fiat-Shamir round by column (column j -> rank j mod G; 96 bytes per
+//                        commitment all-gathered, no column crosses NVLink), and the extended forms + quotient numerator
+//                        by coset block of the internal extended domain (block c -> rank c mod G; rotations never leave
+//                        a block, so only the finished blocks of h, 8 MiB each at k = 17, are all-gathered).
 // NCCL is resolved with dlopen at the first use (the library torch has loaded, else the system libnccl.so.2):
 // libzg_b200.so itself does not link against it and single-GPU users never touch it.
 #include <dlfcn.h>

@@ -317,7 +317,8 @@ def main():
         lane_streams = [stream] + [torch.cuda.Stream() for _ in range(K - 1)]
         contexts = [ctx] + [zg_b200.Context(local, lane_streams[i].cuda_stream) for i in range(1, K)]
         job_counter = itertools.count(1)
-        seeded = lambda _job: zg_b200.lib.XorShift.from_seed(int(next(job_counter)).to_bytes(16, "little"))
+        # SPMD ranks must draw the same stream: a ChaCha20 stream keyed by the job number (same generator as production)
+        seeded = lambda _job: zg_b200.lib.ChaCha20Rng.from_key(int(next(job_counter)).to_bytes(32, "little"))
         # e2e draws from the production RNG (OS-seeded ChaCha20, the reference's OsRng) unless the ranks must agree (SPMD)
         service = ProofService(wnn, ParamsKZG(k, srs.g, srs.g_lagrange, srs.g2, srs.s_g2), device=local, lanes=K,
                                rng_factory=seeded if shard_cols else None, contexts=contexts)
@@ -338,6 +339,8 @@ def main():
 
             def rng(self):
                 self.seed += 1
+                if shard_cols:
+                    return zg_b200.lib.ChaCha20Rng.from_key(int(self.seed).to_bytes(32, "little"))
                 return zg_b200.lib.XorShift.from_seed(int(self.seed).to_bytes(16, "little"))
 
             def _next(self):
@@ -405,7 +408,8 @@ def main():
         extra["images"] = "example_image_7.png" if nimg == 1 else "%d synthetic MNIST-shaped images per rank" % nimg
         extra["e2e_starts_from"] = ("image (native witness synthesis timed, pipelined one image ahead per lane by ProofService)"
                                     if native is not None else "synthesized advice columns")
-        extra["e2e_rng"] = "seeded XorShift (SPMD ranks must agree)" if shard_cols or native is None else "ChaCha20 keyed from the OS per proof"
+        extra["e2e_rng"] = ("ChaCha20 keyed by the job number (SPMD ranks must agree)" if shard_cols else
+                            "seeded XorShift" if native is None else "ChaCha20 keyed from the OS per proof")
         if not args.no_cpu_baseline and rank == 0:
             cpu_fn = lambda: H.create_proof(srs, opk, asm_advice, [outputs], H.XorShiftRng(bytes(range(16))), real_msm=True)
             cpu_units = 1

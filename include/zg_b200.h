@@ -215,9 +215,11 @@ int zg_evaluate_h(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice_polys, cons
  *  - zg_msm_sharded / _dev: ONE large MSM split by point range (BASELINE configs[3], [4]): the context's SRS holds this
  *    rank's slice of the bases (zg_srs_load with the slice), `scalars` the matching slice; the G partial sums (96 B each)
  *    are all-gathered and added on the device; every rank receives the total.
- *  - zg_ctx_set_distribution(ZG_DIST_COLUMNS): zg_create_proof spreads the commitments of every Fiat-Shamir round over
- *    the ranks (column j -> rank j mod G) and all-gathers the points.  Every rank must call zg_create_proof with the
- *    same key, witness, instances and RNG stream (SPMD); every rank returns the same proof bytes. */
+ *  - zg_ctx_set_distribution(ZG_DIST_COLUMNS): zg_create_proof spreads ONE proof over the ranks: the commitments of every
+ *    Fiat-Shamir round by column (column j -> rank j mod G, the 96-byte points all-gathered), the extended forms and the
+ *    quotient numerator by coset block of the internal extended domain (block c -> rank c mod G, the blocks of h
+ *    all-gathered).  Every rank must call zg_create_proof with the same key, witness, instances and RNG stream (SPMD);
+ *    every rank returns the same proof bytes. */
 enum { ZG_DIST_NONE = 0, ZG_DIST_COLUMNS = 1 };
 int zg_comm_unique_id(uint8_t out[128]);
 int zg_comm_init(zg_ctx* ctx, int nranks, int rank, const uint8_t unique_id[128]);

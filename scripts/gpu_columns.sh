@@ -5,7 +5,7 @@ set -u
 cd "${GRAFT_REPO_ROOT:-.}"
 N=${1:-2}; O=gpurun_out/columns_n$N; mkdir -p $O
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533"
-timeout 600 $TR bench.py --gpus $N --model large --shard columns --steps 10 --warmup 3 --no-cpu-baseline > $O/proof_large_columns.json 2> $O/proof_large_columns.err; echo "proof columns exit $?"
+ZG_RNG_THREADS=4 timeout 600 $TR bench.py --gpus $N --model large --shard columns --steps 10 --warmup 3 --no-cpu-baseline > $O/proof_large_columns.json 2> $O/proof_large_columns.err; echo "proof columns exit $?"
 O=$O python - <<'PY'
 import json, os
 O = os.environ['O']
