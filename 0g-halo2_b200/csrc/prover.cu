@@ -869,6 +869,17 @@ static int create_proof_impl(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice,
   rng(rng_state, pk->rnd_words_host, 8 * small_draws);
   ZG_CUDA(cudaMemcpyAsync(pk->rnd_words_dev, pk->rnd_words_host, 64 * small_draws, cudaMemcpyHostToDevice, st));
   fr_from_u512(pk->rnd_words_dev, pk->rnd, small_draws, st, lc);
+  bool big_drawn = false;
+  auto draw_big = [&]() -> int {           // host draw + upload + conversion of everything after the small draws
+    if (big_drawn) return ZG_OK;
+    const size_t rest = pk->n_draws - small_draws;
+    rng(rng_state, pk->rnd_words_host + 8 * small_draws, 8 * rest);
+    ZG_CUDA(cudaMemcpyAsync(pk->rnd_words_dev + 8 * small_draws, pk->rnd_words_host + 8 * small_draws, 64 * rest,
+                            cudaMemcpyHostToDevice, st));
+    fr_from_u512(pk->rnd_words_dev + 8 * small_draws, pk->rnd + small_draws, rest, st, lc);
+    big_drawn = true;
+    return ZG_OK;
+  };
   size_t draw = 0;  // next unused draw index
   auto blind_rows = [&](Fr* col, size_t first_row, size_t count) -> cudaError_t {
     cudaError_t e = cudaMemcpyAsync(col + first_row, pk->rnd + draw, sizeof(Fr) * count, cudaMemcpyDeviceToDevice, st);
@@ -910,14 +921,15 @@ static int create_proof_impl(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice,
     std::vector<Affine> aff(A);
     rc = msm_round(ctx, ZG_BASIS_LAGRANGE, pk->adv_values, n, n, A, 0);
     if (rc) return rc;
-    // the big random polynomial is drawn on the host while the GPU commits
-    const size_t rest = pk->n_draws - small_draws;
-    rng(rng_state, pk->rnd_words_host + 8 * small_draws, 8 * rest);
+    // The big random polynomial (n + 1 draws: 8.4 MB at k = 17, 2-3 ms of host time) is drawn while the GPU works: behind
+    // the lookup round's kernels when the circuit has lookups (the advice commitment alone is shorter than the draw),
+    // here otherwise.  The caller's RNG sees the same call order either way: all small draws, then this one.
+    if (!Lk) {
+      int drc = draw_big();
+      if (drc) return drc;
+    }
     std::vector<G1Jac> jac(A);
     ZG_CUDA(cudaMemcpyAsync(jac.data(), ctx->d_msm_out, sizeof(G1Jac) * A, cudaMemcpyDeviceToHost, st));
-    ZG_CUDA(cudaMemcpyAsync(pk->rnd_words_dev + 8 * small_draws, pk->rnd_words_host + 8 * small_draws, 64 * rest,
-                            cudaMemcpyHostToDevice, st));
-    fr_from_u512(pk->rnd_words_dev + 8 * small_draws, pk->rnd + small_draws, rest, st, lc);
     ZG_CUDA(cudaEventRecord(ev[1], st));
     ZG_CUDA(cudaStreamSynchronize(st));
     batch_normalize(jac.data(), A, aff.data());
@@ -983,6 +995,8 @@ static int create_proof_impl(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice,
         if (rc) return rc;
       }
       rc = msm_round(ctx, ZG_BASIS_LAGRANGE, pk->pa, n, n, 2 * Lk, 0);
+      if (rc) return rc;
+      rc = draw_big();                       // host work while the lookup round's kernels run
       if (rc) return rc;
       std::vector<G1Jac> jac(2 * Lk);
       std::vector<uint32_t> status(2 * Lk);
