@@ -7,6 +7,7 @@
 // msm.cu, poly.cu, expr.cu and lookup.cu; the host only sequences rounds, hashes (keccak256) and
 // normalises <= 8 commitments per round.  Witness synthesis is the caller's (BASELINE north_star).
 #include <algorithm>
+#include <cstdlib>
 #include <atomic>
 #include <memory>
 #include "ctx.cuh"
@@ -924,7 +925,8 @@ static int create_proof_impl(zg_ctx* ctx, zg_pk* pk, const zg_fr* const* advice,
     // The big random polynomial (n + 1 draws: 8.4 MB at k = 17, 2-3 ms of host time) is drawn while the GPU works: behind
     // the lookup round's kernels when the circuit has lookups (the advice commitment alone is shorter than the draw),
     // here otherwise.  The caller's RNG sees the same call order either way: all small draws, then this one.
-    if (!Lk) {
+    static const bool rng_early = getenv("ZG_RNG_EARLY") != nullptr;      // A/B switch: draw inside the advice round
+    if (!Lk || rng_early) {
       int drc = draw_big();
       if (drc) return drc;
     }
