@@ -16,7 +16,12 @@
 //   * twiddles come from a stage-major table T_t[j] = w_{2^(t+1)}^j (offset 2^t - 1) so that
 //     lanes that walk consecutive columns read consecutive table entries.
 //   * 254-bit Montgomery butterflies make this kernel integer-pipe bound (about 10 mulmods per
-//     element at 2^20 against 64 B of traffic per pass), see DESIGN.md.
+//     element at 2^20 against 64 B of traffic per pass), see DESIGN.md: ncu inside the k = 17 proof shows
+//     sm__pipe_fmaheavy_cycles_active 67-82 % for the batched passes (profiles/r02_ncu_full_ntt_proof_large.txt).
+//   * one launch covers a batch of polynomials and, per polynomial, several COSETS that differ only in a per-element
+//     input table (coset c multiplies coefficient i by g_c^i) or output table: the prover's internal extended domain
+//     is three cosets of the 2n-point subgroup (extdomain.cuh), so coefficient -> extended is one launch per pass for
+//     all columns of a round and all three cosets; a rank that owns a subset of the cosets passes (first, step).
 #include <atomic>
 #include <cstdlib>
 #include "ntt.cuh"

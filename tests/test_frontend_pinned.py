@@ -384,3 +384,37 @@ def test_refcs_matches_product_on_models(name):
     circ, asm = wnn.synthesize(np.zeros(wnn.img_shape(), dtype=np.uint8), k)
     ref = _compare_with_refcs(circ, asm)
     assert ref.num_fixed == 16                      # SURVEY A.1 ("16 fixed columns after compression")
+
+
+@pytest.mark.parametrize("which", ["hash", "greater_than", "bloom"])
+def test_refcs_matches_product_on_gadget_circuits(which):
+    """the same cross-check on three gadget test circuits: other selector mixes, other degrees, other query tables"""
+    class Holder:
+        pass
+    if which == "hash":
+        cs, synth = hash_circuit(42)
+        k = 9
+    elif which == "greater_than":
+        cs, synth = gt_circuit(129, 64)
+        k = 9
+    else:
+        cs = ConstraintSystem()
+        instance = cs.instance_column()
+        adv = [cs.advice_column() for _ in range(6)]
+        for a in adv:
+            cs.enable_equality(a)
+        cs.enable_equality(instance)
+        cs.enable_constant(cs.fixed_column())
+        chip = G.BloomFilter(cs, adv, n_hashes=2, bits_per_hash=10)
+        chip.array.set_arrays(np.ones((1, 1024), dtype=bool))
+
+        def synth(lay):
+            cell = lay.assign_region("input", lambda r: r.assign_advice(adv[0], 0, 8))
+            chip.load(lay)
+            lay.constrain_instance(chip.bloom_lookup(lay, cell, 0), instance, 0)
+        k = 14
+    asm = Assembly(cs, k)
+    synth(SimpleFloorPlanner(asm))
+    h = Holder()
+    h.cs = cs
+    _compare_with_refcs(h, asm)
