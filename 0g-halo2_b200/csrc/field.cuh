@@ -509,6 +509,71 @@ ZG_HD Fp<P> fp_sqr(const Fp<P>& a) {
   return fp_mul<P>(a, a);
 }
 
+}  // namespace zg
+// dedicated squaring and the two-product ("lazy reduction") multiply-add: generated straight-line PTX bodies, modelled
+// instruction for instruction on the CPU (scripts/gen_field_ops.py, tests/test_field_gen.py)
+#ifndef ZG_FIELD_GEN
+#define ZG_FIELD_GEN 1
+#endif
+#include "field_gen.cuh"
+namespace zg {
+
+#if defined(__CUDA_ARCH__) && defined(ZG_FP_MUL_NOINLINE)
+template <class P>
+__device__ __noinline__ Fp<P> fp_sqr_gen_outlined(Fp<P> a) {
+  return fp_sqr_gen<P>(a);
+}
+template <class P>
+__device__ __noinline__ Fp<P> fp_mul2_gen_outlined(Fp<P> a, Fp<P> b, Fp<P> c, Fp<P> d) {
+  return fp_mul2_gen<P>(a, b, c, d);
+}
+#endif
+
+// a^2 with the dedicated squaring body on the device (100 wide products instead of 128)
+template <class P>
+ZG_HD Fp<P> fp_sqr_fast(const Fp<P>& a) {
+#if defined(__CUDA_ARCH__) && ZG_FIELD_GEN && defined(ZG_FP_MUL_NOINLINE)
+  return fp_sqr_gen_outlined<P>(a);
+#elif defined(__CUDA_ARCH__) && ZG_FIELD_GEN
+  return fp_sqr_gen<P>(a);
+#else
+  return fp_mul<P>(a, a);
+#endif
+}
+// a*b + c*d with ONE Montgomery reduction on the device (192 wide products instead of 256); a, b, c, d <= p
+template <class P>
+ZG_HD Fp<P> fp_mul2add(const Fp<P>& a, const Fp<P>& b, const Fp<P>& c, const Fp<P>& d) {
+#if defined(__CUDA_ARCH__) && ZG_FIELD_GEN && defined(ZG_FP_MUL_NOINLINE)
+  return fp_mul2_gen_outlined<P>(a, b, c, d);
+#elif defined(__CUDA_ARCH__) && ZG_FIELD_GEN
+  return fp_mul2_gen<P>(a, b, c, d);
+#else
+  return fp_add<P>(fp_mul<P>(a, b), fp_mul<P>(c, d));
+#endif
+}
+// -a as an OPERAND of fp_mul2add: p - a without the zero check (0 -> p, which the two-product body accepts)
+template <class P>
+ZG_HD Fp<P> fp_neg_lazy(const Fp<P>& a) {
+#if defined(__CUDA_ARCH__) && ZG_FIELD_GEN
+  Fp<P> r;
+  asm("sub.cc.u32 %0, %8, %16;\n\t"
+      "subc.cc.u32 %1, %9, %17;\n\t"
+      "subc.cc.u32 %2, %10, %18;\n\t"
+      "subc.cc.u32 %3, %11, %19;\n\t"
+      "subc.cc.u32 %4, %12, %20;\n\t"
+      "subc.cc.u32 %5, %13, %21;\n\t"
+      "subc.cc.u32 %6, %14, %22;\n\t"
+      "subc.u32 %7, %15, %23;"
+      : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+      : "n"(P::mod(0)), "n"(P::mod(1)), "n"(P::mod(2)), "n"(P::mod(3)), "n"(P::mod(4)), "n"(P::mod(5)), "n"(P::mod(6)),
+        "n"(P::mod(7)), "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]),
+        "r"(a.v[7]));
+  return r;
+#else
+  return fp_neg<P>(a);
+#endif
+}
+
 // canonical (non-Montgomery) integer -> Montgomery form
 template <class P>
 ZG_HD Fp<P> fp_to_mont(const Fp<P>& raw) {

@@ -93,7 +93,9 @@ __global__ void __launch_bounds__(MB_THREADS) mb_mulmod_kernel(Fr* out, Fr seed,
 #if defined(__CUDA_ARCH__)
       if (VARIANT == 0) x[i] = fp_mul_portable(x[i], y);
       else if (VARIANT == 1) x[i] = fp_mul_ptx(x[i], y);
-      else x[i] = fp_mul_eo(x[i], y);
+      else if (VARIANT == 2) x[i] = fp_mul_eo(x[i], y);
+      else if (VARIANT == 3) x[i] = fp_sqr_fast(x[i]);
+      else x[i] = fp_mul2add(x[i], y, y, x[i]);   // counted as two products
 #endif
     }
   }
@@ -139,6 +141,14 @@ extern "C" int zg_bench_int_pipe(zg_ctx* ctx, int kind, uint32_t iters, double* 
       case 4:
         mb_mulmod_kernel<2><<<blocks, MB_THREADS, 0, ctx->stream>>>((Fr*)scratch, seed, iters);
         ops_per_thread = 4.0 * iters;
+        break;
+      case 8:   // dedicated squaring
+        mb_mulmod_kernel<3><<<blocks, MB_THREADS, 0, ctx->stream>>>((Fr*)scratch, seed, iters);
+        ops_per_thread = 4.0 * iters;
+        break;
+      case 9:   // two-product multiply-add with one reduction: rate in PRODUCTS per second
+        mb_mulmod_kernel<4><<<blocks, MB_THREADS, 0, ctx->stream>>>((Fr*)scratch, seed, iters);
+        ops_per_thread = 8.0 * iters;
         break;
       case 5:
         mb_dfma_kernel<false><<<blocks, MB_THREADS, 0, ctx->stream>>>((double*)scratch, 0.999999, 1e-7, 0x9e3779b1u, iters);
@@ -186,6 +196,9 @@ __global__ void dbg_field_kernel(int op, const Fp<P>* a, const Fp<P>* b, Fp<P>* 
     case 6: r = fp_from_mont(x); break;
     case 7: r = fp_to_mont(x); break;
     case 8: r = fp_mul_eo(x, y); break;
+    case 9: r = fp_sqr_fast(x); break;                                   // dedicated squaring (field_gen.cuh)
+    case 10: r = fp_mul2add(x, y, fp_add(x, y), x); break;               // x*y + (x+y)*x, one reduction
+    case 11: r = fp_mul2add(x, x, fp_neg_lazy(y), y); break;             // x^2 - y^2 (y = 0: the operand is p itself)
     default: r = fp_zero<P>(); break;
   }
   o[i] = r;
@@ -197,7 +210,7 @@ extern "C" int zg_debug_field_op(zg_ctx* ctx, int field, int op, const void* a, 
                                  size_t n) {
   ZG_ENTER(ctx);
   if (n == 0) return ZG_OK;
-  if (op < 0 || op > 8 || field < 0 || field > 1) return ctx->fail(ZG_E_INVALID, "debug_field_op: bad op/field");
+  if (op < 0 || op > 11 || field < 0 || field > 1) return ctx->fail(ZG_E_INVALID, "debug_field_op: bad op/field");
   int rc = ws_reserve(ctx, ctx->ws_stage, 96 * n);
   if (rc) return rc;
   uint8_t* d = ctx->ws_stage.p;

@@ -29,6 +29,10 @@
 #include "msm.cuh"
 #include "scan.cuh"
 
+#ifndef ZG_MSM_MADD_DEFAULT
+#define ZG_MSM_MADD_DEFAULT 1
+#endif
+
 namespace zg {
 
 __device__ __forceinline__ void ld_fq2(const G1Affine* p, Fq& x, Fq& y) {
@@ -166,6 +170,7 @@ __global__ void msm_hist_offsets_kernel(uint32_t* __restrict__ H, uint32_t J, ui
 // affine window table.  (The XYZZ-partial levels live in msm_tail.cu.)
 // Thread t owns entries [t*K, t*K+K).  Runs strictly inside the chunk go straight to their bucket
 // (nobody else holds that key); the first and last runs go to partial slots 2t, 2t+1.
+template <bool LAZY>
 __global__ void __launch_bounds__(128, 4) msm_accumulate_kernel(
     const uint2* __restrict__ entries, const uint32_t* __restrict__ count_ptr, const G1Affine* __restrict__ table,
     const G1Affine* __restrict__ alt_table, uint32_t alt_mask, uint32_t log_nb,
@@ -207,7 +212,7 @@ __global__ void __launch_bounds__(128, 4) msm_accumulate_kernel(
     ld_fq2(tb + (ent.y & 0x7fffffffu), x, y);
     if (!(fp_is_zero(x) && fp_is_zero(y))) {
       if (ent.y >> 31) y = fp_neg(y);
-      xyzz_madd(acc, x, y);
+      xyzz_madd_t<LAZY>(acc, x, y);
     }
     ent = nxt;
   }
@@ -238,13 +243,23 @@ static uint32_t msm_accumulate_wave_threads() {
   uint32_t v = cached[dev & 63].load(std::memory_order_acquire);
   if (v) return v;
   int per_sm = 0, sms = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, msm_accumulate_kernel, 128, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, msm_accumulate_kernel<true>, 128, 0);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (per_sm < 1) per_sm = 3;
   if (sms < 1) sms = 148;
   v = (uint32_t)per_sm * (uint32_t)sms * 128u;
   cached[dev & 63].store(v, std::memory_order_release);
   return v;
+}
+
+// mixed addition of the level-0 accumulation: 1 (default) = dedicated squarings + one lazily reduced two-product for Y3
+// (curve.cuh::xyzz_madd_t<true>), 0 = ten fully reduced products.  Same bucket contents bit for bit; ZG_MSM_MADD selects.
+static bool msm_madd_lazy() {
+  static const int v = [] {
+    const char* e = getenv("ZG_MSM_MADD");
+    return e ? atoi(e) : ZG_MSM_MADD_DEFAULT;
+  }();
+  return v != 0;
 }
 
 uint32_t msm_pick_c(uint32_t k) {
@@ -380,8 +395,12 @@ cudaError_t msm_run(const MsmTable& tb, const Fr* scalars, size_t stride, uint32
     }
     cudaEventRecord(probe->ev[2 * probe->used], st);
   }
-  msm_accumulate_kernel<<<(T0 + 127) / 128, 128, 0, st>>>(entries, offsets + cnt, tb.pts, alt_pts ? alt_pts : tb.pts,
-                                                          alt_pts ? alt_mask : 0u, tb.c - 1, l.K0, buckets, pk[0], pp[0], T0);
+  if (msm_madd_lazy())
+    msm_accumulate_kernel<true><<<(T0 + 127) / 128, 128, 0, st>>>(entries, offsets + cnt, tb.pts, alt_pts ? alt_pts : tb.pts,
+                                                                alt_pts ? alt_mask : 0u, tb.c - 1, l.K0, buckets, pk[0], pp[0], T0);
+  else
+    msm_accumulate_kernel<false><<<(T0 + 127) / 128, 128, 0, st>>>(entries, offsets + cnt, tb.pts, alt_pts ? alt_pts : tb.pts,
+                                                                 alt_pts ? alt_mask : 0u, tb.c - 1, l.K0, buckets, pk[0], pp[0], T0);
   if (probing) {
     cudaEventRecord(probe->ev[2 * probe->used + 1], st);
     cudaMemcpyAsync(probe->counts + probe->used, offsets + cnt, 4, cudaMemcpyDeviceToHost, st);

@@ -611,7 +611,8 @@ def main():
     mulmod_ptx_rate = ctx.bench_int_pipe(3, 256)
     mulmod_eo_rate = ctx.bench_int_pipe(4, 256)
     int_pipe = {"imad_gops": imad_peak, "imad_wide_gops": imad_wide, "fr_mulmod_portable_gops": mulmod_rate,
-                "fr_mulmod_ptx_gops": mulmod_ptx_rate, "fr_mulmod_evenodd_gops": mulmod_eo_rate}
+                "fr_mulmod_ptx_gops": mulmod_ptx_rate, "fr_mulmod_evenodd_gops": mulmod_eo_rate,
+                "fr_sqr_dedicated_gops": ctx.bench_int_pipe(8, 256), "fr_two_product_gops": ctx.bench_int_pipe(9, 256)}
     if args.workload == "ntt":
         ach = ntt_bytes(logn) / 1e9 / (ms_per_step * 1e-3)
         roof = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,

@@ -279,7 +279,9 @@ int zg_wnn_synthesize(const zg_wnn* w, const uint8_t* image, uint32_t k, uint32_
  * achieved rate in 1e9 thread-instructions per second; kind 0 = IMAD (32-bit), 1 = IMAD.WIDE,
  * 2 = Fr Montgomery multiplications, portable body (result in 1e9 mulmod/s), 3 = same, row-wise PTX
  * carry-chain body, 4 = same, even/odd carry-chain body (the one the kernels use); 5 = DFMA (FP64 pipe), 6 = DFMA and
- * IMAD.WIDE interleaved 1:1 (rate counts both), 7 = IMAD.WIDE with 16 independent accumulators and nothing else */
+ * IMAD.WIDE interleaved 1:1 (rate counts both), 7 = IMAD.WIDE with 16 independent accumulators and nothing else,
+ * 8 = Fr squarings, dedicated squaring body, 9 = Fr two-product multiply-adds with one reduction (rate counts BOTH
+ * products of a call; csrc/field_gen.cuh) */
 int zg_bench_int_pipe(zg_ctx* ctx, int kind, uint32_t iters, double* giga_per_s);
 
 /* live timing of the dominant kernel (msm_accumulate_kernel, the level-0 bucket accumulation of every MSM): while
@@ -291,7 +293,8 @@ int zg_probe_read(zg_ctx* ctx, double* kernel_ms, uint64_t* launches, uint64_t* 
 /* ---- diagnostics (parity tests) --------------------------------------------------------- */
 /* element-wise device field op on host arrays of n elements; field 0 = Fr, 1 = Fq;
  * op 0 mul, 1 mul (portable body), 2 mul (row-wise PTX body), 3 add, 4 sub, 5 inverse(a), 6 from_mont(a),
- * 7 to_mont(a), 8 mul (even/odd carry-chain body) */
+ * 7 to_mont(a), 8 mul (even/odd carry-chain body), 9 a^2 (dedicated squaring body), 10 a*b + (a+b)*a and
+ * 11 a^2 - b^2 (two-product body with one Montgomery reduction; csrc/field_gen.cuh) */
 int zg_debug_field_op(zg_ctx* ctx, int field, int op, const void* a, const void* b, void* out, size_t n);
 /* keccak256 as used by the EvmTranscript inside zg_create_proof (host code; needs no context and no GPU) */
 void zg_debug_keccak256(const uint8_t* data, size_t len, uint8_t out[32]);

@@ -32,6 +32,10 @@ def test_field_ops_bit_exact(ctx, field, mod):
         assert (ctx.debug_field_op(field, op, A, B) == exp_mul).all(), op
     assert (ctx.debug_field_op(field, 3, A, B) == bn254.ints_to_limbs([x + y for x, y in zip(a, b)], mod)).all()
     assert (ctx.debug_field_op(field, 4, A, B) == bn254.ints_to_limbs([x - y for x, y in zip(a, b)], mod)).all()
+    # generated bodies (csrc/field_gen.cuh): dedicated squaring, two products under one Montgomery reduction
+    assert (ctx.debug_field_op(field, 9, A, B) == bn254.ints_to_limbs([x * x for x in a], mod)).all()
+    assert (ctx.debug_field_op(field, 10, A, B) == bn254.ints_to_limbs([x * y + (x + y) * x for x, y in zip(a, b)], mod)).all()
+    assert (ctx.debug_field_op(field, 11, A, B) == bn254.ints_to_limbs([x * x - y * y for x, y in zip(a, b)], mod)).all()
     raw = bn254.ints_to_limbs(a, mod, mont=False)
     assert (ctx.debug_field_op(field, 6, A) == raw).all()
     assert (ctx.debug_field_op(field, 7, raw) == A).all()
