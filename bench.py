@@ -658,6 +658,8 @@ def main():
     if "scaling_override" in extra:
         out["scaling"] = extra.pop("scaling_override")
     out.update(extra)
+    # library tuning switches in force (unset = the built-in defaults: lazy two-product mixed addition and Horner steps)
+    out["knobs"] = {k: v for k, v in sorted(os.environ.items()) if k.startswith("ZG_") and not k.startswith("ZG_BENCH_")}
     if cpu_fn is not None:
         import cpu_ref
         cores = cpu_ref.use_all_cores()

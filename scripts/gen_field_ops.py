@@ -14,6 +14,11 @@ Each body is ONE asm statement (the carry flag never leaves it).  The same instr
 (2) interpreted here with exact carry-flag semantics, so the text that ptxas compiles is the text that the CPU tests
 (tests/test_field_gen.py) check against Python big integers -- there is no GPU in the build container.
 
+A third body, `mulk` (one level of subtractive Karatsuba on the 8 x 8-limb product: 48 + 64 wide products), is kept in
+the generator and in the CPU tests but NOT in the shipped header: compiled for sm_100a (`--with-karatsuba`) it is 99
+IMAD.WIDE + 13 IMAD.HI + 32 IMAD + ~160 ALU-pipe instructions per product = 512 FMA-pipe cycles against 544 for
+fp_mul_eo (120 + 8 + 16 and ~58) -- 6 % fewer heavy-pipe cycles for almost three times the ALU-pipe work.
+
 Usage:  python scripts/gen_field_ops.py            # rewrite 0g-halo2_b200/csrc/field_gen.cuh
         python scripts/gen_field_ops.py --check    # exit 1 if the committed header differs from the generator
 """
@@ -102,6 +107,8 @@ class Prog:
             elif base == "shf":      # shf.l.wrap.b32 d, lo, hi, n  ->  upper word of (hi:lo) << n
                 n = s[2] & 31
                 res, co = ((((s[1] << 32) | s[0]) << n) >> 32) & M32, None
+            elif base == "xor":
+                res, co = s[0] ^ s[1], None
             elif base == "mov":
                 res, co = s[0], None
             else:
@@ -125,7 +132,7 @@ class Prog:
                 return "0x%08x" % (x & M32)
             return idx.get(x, x)
 
-        suffix = {"shf": ".b32"}
+        suffix = {"shf": ".b32", "xor": ".b32"}
         out = []
         for ins in self.ins:
             name, ops = ins[0], ins[1:]
@@ -322,6 +329,90 @@ def gen_sqr(mod):
     return p
 
 
+def product4(p, X, Y):
+    """4 x 4 limbs -> 8 limbs: even-position products in E, odd-position products in O (one carry chain per row and
+    parity, issued so that every chain's carry limb lies above what was written before), then E + O."""
+    E, O = Acc(8), Acc(8)
+    for j in range(4):
+        ev = [(X[0], Y[j]), (X[2], Y[j])]      # positions j, j + 2
+        od = [(X[1], Y[j]), (X[3], Y[j])]      # positions j + 1, j + 3
+        arr_ev, arr_od = (E, O) if j % 2 == 0 else (O, E)
+        wide_chain(p, arr_ev, j, ev)
+        wide_chain(p, arr_od, j + 1, od)
+    Z = [E.v[0]]
+    for k in range(1, 8):
+        d = p.tmp()
+        p.op("add.cc" if k == 1 else ("addc.cc" if k < 7 else "addc"), d, E.get(k), O.get(k))
+        Z.append(d)
+    return Z
+
+
+def abs_diff4(p, X, Y):
+    """|X - Y| over 4 limbs and the sign mask (0 or 0xffffffff)"""
+    d = [p.tmp() for _ in range(4)]
+    for k in range(4):
+        p.op("sub.cc" if k == 0 else "subc.cc", d[k], X[k], Y[k])
+    m = p.tmp()
+    p.op("subc", m, 0, 0)
+    x = [p.tmp() for _ in range(4)]
+    for k in range(4):
+        p.op("xor", x[k], d[k], m)
+    r = [p.tmp() for _ in range(4)]
+    for k in range(4):
+        p.op("sub.cc" if k == 0 else ("subc.cc" if k < 3 else "subc"), r[k], x[k], m)
+    return r, m
+
+
+def gen_mulk(mod):
+    """a*b / 2^256 mod p as a value < 2p with ONE level of (subtractive) Karatsuba on the 8 x 8-limb product: three 4 x 4
+    products (48 wide multiplies instead of 64), then the reduction rows of gen_sqr."""
+    pm, inv = limbs(mod), mont_inv32(mod)
+    A = ["a%d" % i for i in range(8)]
+    B = ["b%d" % i for i in range(8)]
+    outs = ["r%d" % i for i in range(8)]
+    p = Prog(A + B, outs)
+    z0 = product4(p, A[:4], B[:4])
+    z2 = product4(p, A[4:], B[4:])
+    da, ma = abs_diff4(p, A[:4], A[4:])        # a_lo - a_hi
+    db, mb = abs_diff4(p, B[4:], B[:4])        # b_hi - b_lo
+    zm = product4(p, da, db)
+    sg = p.tmp()
+    p.op("xor", sg, ma, mb)                     # all ones when (a_lo - a_hi)(b_hi - b_lo) < 0
+    # t = z0 + z2 (9 limbs)
+    t = [p.tmp() for _ in range(9)]
+    for k in range(8):
+        p.op("add.cc" if k == 0 else "addc.cc", t[k], z0[k], z2[k])
+    p.op("addc", t[8], 0, 0)
+    # z1 = t +- zm = a_lo*b_hi + a_hi*b_lo (>= 0, < 2^257)
+    zx = [p.tmp() for _ in range(8)]
+    for k in range(8):
+        p.op("xor", zx[k], zm[k], sg)
+    cy = p.tmp()
+    p.op("add.cc", cy, sg, 1)                   # carry flag := (sg != 0): the +1 of the two's complement
+    z1 = [p.tmp() for _ in range(9)]
+    for k in range(8):
+        p.op("addc.cc", z1[k], t[k], zx[k])
+    p.op("addc", z1[8], t[8], sg)
+    # T = z0 + z1 * 2^128 + z2 * 2^256
+    T = list(z0[:4])
+    for k in range(4, 16):
+        d = p.tmp()
+        lo = z0[k] if k < 8 else z2[k - 8]
+        hi = z1[k - 4] if k - 4 < 9 else 0
+        p.op("add.cc" if k == 4 else ("addc.cc" if k < 15 else "addc"), d, lo, hi)
+        T.append(d)
+    u, w = Acc(8), Acc(8)
+    u.v = list(T[:8])
+    for i in range(8):
+        carry = False
+        if i > 0:
+            u, w = shift_row(p, u, w, T[7 + i])
+            carry = True
+        reduce_row(p, u, w, pm, inv, carry_in=carry)
+    final_combine(p, u, w, T[15], outs)
+    return p
+
+
 # ---- header --------------------------------------------------------------------------------------------
 HEADER = '''// GENERATED by scripts/gen_field_ops.py -- do not edit; `python scripts/gen_field_ops.py --check` compares.
 //
@@ -336,6 +427,8 @@ namespace zg {
 template <class P> __device__ __forceinline__ Fp<P> fp_sqr_gen(const Fp<P>& a);
 template <class P> __device__ __forceinline__ Fp<P> fp_mul2_gen(const Fp<P>& a, const Fp<P>& b, const Fp<P>& c, const Fp<P>& d);
 '''
+HEADER_K = "template <class P> __device__ __forceinline__ Fp<P> fp_mulk_gen(const Fp<P>& a, const Fp<P>& b);\n"
+
 
 
 def emit_function(kind, field, prog):
@@ -343,6 +436,8 @@ def emit_function(kind, field, prog):
     nout = len(prog.outputs)
     if kind == "sqr":
         L.append("template <> __device__ __forceinline__ Fp<%s> fp_sqr_gen<%s>(const Fp<%s>& a) {" % (field, field, field))
+    elif kind == "mulk":
+        L.append("template <> __device__ __forceinline__ Fp<%s> fp_mulk_gen<%s>(const Fp<%s>& a, const Fp<%s>& b) {" % ((field,) * 4))
     else:
         L.append("template <> __device__ __forceinline__ Fp<%s> fp_mul2_gen<%s>(const Fp<%s>& a, const Fp<%s>& b, "
                  "const Fp<%s>& c, const Fp<%s>& d) {" % ((field,) * 6))
@@ -369,9 +464,9 @@ def emit_function(kind, field, prog):
 
 
 def header_text():
-    parts = [HEADER]
+    parts = [HEADER + (HEADER_K if "--with-karatsuba" in sys.argv else "")]
     for field, mod in FIELDS.items():
-        for kind, gen in (("sqr", gen_sqr), ("mul2", gen_mul2)):
+        for kind, gen in (("sqr", gen_sqr), ("mul2", gen_mul2)) + ((("mulk", gen_mulk),) if "--with-karatsuba" in sys.argv else ()):
             prog = gen(mod)
             parts.append("// %s %s: %d PTX instructions, %d multiply(-add) halves = %d wide products + 8 mul.lo for m" % (
                 field, kind, len(prog.ins), prog.count("mad") + prog.count("mul"),
