@@ -9,7 +9,6 @@
 // constraint system); a thread owns one row of the (extended) domain, evaluates every program with a
 // small register/local stack and folds the results with Horner in y.  One thread per row keeps every
 // column read coalesced across the warp (rotations are a constant row offset).
-#include <cstdlib>
 #include "expr.cuh"
 
 namespace zg {
@@ -37,8 +36,9 @@ __device__ __forceinline__ uint32_t rot_idx(uint32_t idx, int32_t rot, uint32_t 
   return (idx & ~mask) | ((uint32_t)((int32_t)idx + rot * (int32_t)scale) & mask);
 }
 
-// executes ops [begin, end) on the stack `st` (depth `sp` on entry); returns the new depth
-__device__ __forceinline__ int run_ops(const ExprEnv& E, uint32_t begin, uint32_t end, uint32_t idx, Fr* st, int sp) {
+__device__ Fr eval_program(const ExprEnv& E, uint32_t begin, uint32_t end, uint32_t idx) {
+  Fr st[EXPR_STACK];
+  int sp = 0;
   for (uint32_t pc = begin; pc < end; pc++) {
     const uint32_t w = E.ops[pc];
     const uint32_t op = w & 0xff, arg = w >> 8;
@@ -76,47 +76,14 @@ __device__ __forceinline__ int run_ops(const ExprEnv& E, uint32_t begin, uint32_
         break;
     }
   }
-  return sp;
-}
-
-__device__ Fr eval_program(const ExprEnv& E, uint32_t begin, uint32_t end, uint32_t idx) {
-  Fr st[EXPR_STACK];
-  run_ops(E, begin, end, idx, st, 0);
   return st[0];
 }
 
-// acc * y + x * l: with LAZY both products share one Montgomery reduction (field.cuh::fp_mul2add, same canonical result)
-template <bool LAZY>
-__device__ __forceinline__ Fr horner_term(const Fr& acc, const Fr& y, const Fr& x, const Fr& l) {
-  return LAZY ? fp_mul2add(acc, y, x, l) : fp_add(fp_mul(acc, y), fp_mul(x, l));
-}
-
-// acc * y + program(idx).  Gate polynomials are `selector * (...)`: when the program ends in a product, that product
-// and acc * y are evaluated as ONE two-product (LAZY); any other program takes the plain path.
-// one shared copy of the interpreter for the folded Horner steps below (they call it up to twice per program; inlining
-// every call site grew k_h_lookup from 97 KB to 147 KB of SASS)
-__device__ __noinline__ int run_ops_shared(const ExprEnv& E, uint32_t begin, uint32_t end, uint32_t idx, Fr* st, int sp) {
-  return run_ops(E, begin, end, idx, st, sp);
-}
-template <bool LAZY>
-__device__ Fr horner_program(const ExprEnv& E, uint32_t begin, uint32_t end, uint32_t idx, const Fr& acc, const Fr& y) {
-  if (!LAZY) return fp_add(fp_mul(acc, y), eval_program(E, begin, end, idx));
-  Fr st[EXPR_STACK];
-  const uint32_t w = E.ops[end - 1];
-  const uint32_t op = w & 0xff, arg = w >> 8;
-  const bool tail_product = op == OP_MUL || op == OP_SCALE;
-  int sp = run_ops_shared(E, begin, tail_product ? end - 1 : end, idx, st, 0);
-  if (op == OP_MUL && sp == 2) return fp_mul2add(acc, y, st[0], st[1]);
-  if (op == OP_SCALE && sp == 1) return fp_mul2add(acc, y, st[0], ldf(E.constants + arg));
-  if (tail_product) run_ops_shared(E, end - 1, end, idx, st, sp);
-  return fp_add(fp_mul(acc, y), st[0]);
-}
-
 // theta-Horner over programs [first, first+count): acc = acc * theta + expr
-template <bool LAZY>
 __device__ Fr compress(const ExprEnv& E, const uint32_t* prog_off, uint32_t first, uint32_t count, const Fr& theta, uint32_t idx) {
   Fr acc = eval_program(E, prog_off[first], prog_off[first + 1], idx);
-  for (uint32_t p = first + 1; p < first + count; p++) acc = horner_program<LAZY>(E, prog_off[p], prog_off[p + 1], idx, acc, theta);
+  for (uint32_t p = first + 1; p < first + count; p++)
+    acc = fp_add(fp_mul(acc, theta), eval_program(E, prog_off[p], prog_off[p + 1], idx));
   return acc;
 }
 
@@ -125,16 +92,15 @@ __global__ void __launch_bounds__(EX_THREADS) k_compress_lookups(ExprEnv E, Look
   uint32_t idx = E.row0 + blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t l = blockIdx.y;
   if (idx >= E.size) return;
-  stf(out_in + l * out_stride + idx, compress<false>(E, lp.prog_off, lp.in_first[l], lp.in_count[l], theta, idx));
-  stf(out_tab + l * out_stride + idx, compress<false>(E, lp.prog_off, lp.tab_first[l], lp.tab_count[l], theta, idx));
+  stf(out_in + l * out_stride + idx, compress(E, lp.prog_off, lp.in_first[l], lp.in_count[l], theta, idx));
+  stf(out_tab + l * out_stride + idx, compress(E, lp.prog_off, lp.tab_first[l], lp.tab_count[l], theta, idx));
 }
 
-template <bool LAZY>
 __global__ void __launch_bounds__(EX_THREADS) k_h_gates(ExprEnv E, const uint32_t* prog_off, uint32_t nprogs, Fr y, Fr* h) {
   uint32_t idx = E.row0 + blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= E.size) return;
   Fr acc = fp_zero<FrParams>();
-  for (uint32_t p = 0; p < nprogs; p++) acc = horner_program<LAZY>(E, prog_off[p], prog_off[p + 1], idx, acc, y);
+  for (uint32_t p = 0; p < nprogs; p++) acc = fp_add(fp_mul(acc, y), eval_program(E, prog_off[p], prog_off[p + 1], idx));
   stf(h + idx, acc);
 }
 
@@ -176,7 +142,6 @@ __global__ void __launch_bounds__(EX_THREADS) k_h_permutation(PermEnv P, Fr beta
   stf(h + idx, acc);
 }
 
-template <bool LAZY>
 __global__ void __launch_bounds__(EX_THREADS) k_h_lookup(ExprEnv E, LookupProgs lp, uint32_t l, LookupHEnv L, Fr theta, Fr beta,
                                                          Fr gamma, Fr y, Fr* h) {
   uint32_t idx = E.row0 + blockIdx.x * blockDim.x + threadIdx.x;
@@ -184,33 +149,21 @@ __global__ void __launch_bounds__(EX_THREADS) k_h_lookup(ExprEnv E, LookupProgs 
   const uint32_t r_next = rot_idx(idx, 1, E.rot_scale, E.wrap_mask);
   const uint32_t r_prev = rot_idx(idx, -1, E.rot_scale, E.wrap_mask);
   const Fr one = fp_one<FrParams>();
-  Fr ci = compress<LAZY>(E, lp.prog_off, lp.in_first[l], lp.in_count[l], theta, idx);
-  Fr ct = compress<LAZY>(E, lp.prog_off, lp.tab_first[l], lp.tab_count[l], theta, idx);
+  Fr ci = compress(E, lp.prog_off, lp.in_first[l], lp.in_count[l], theta, idx);
+  Fr ct = compress(E, lp.prog_off, lp.tab_first[l], lp.tab_count[l], theta, idx);
   Fr table_value = fp_mul(fp_add(ci, beta), fp_add(ct, gamma));
   Fr z = ldf(L.z + idx), z_next = ldf(L.z + r_next);
   Fr a = ldf(L.a + idx), a_prev = ldf(L.a + r_prev), s = ldf(L.s + idx);
   Fr l0 = ldf(L.l0 + idx), l_last = ldf(L.l_last + idx), l_active = ldf(L.l_active + idx);
   Fr a_minus_s = fp_sub(a, s);
   Fr acc = ldf(h + idx);
-  // every Horner step acc * y + term * l is one two-product when LAZY (6 of the 9 reductions of this block go away)
-  acc = horner_term<LAZY>(acc, y, fp_sub(one, z), l0);
-  acc = horner_term<LAZY>(acc, y, fp_sub(LAZY ? fp_sqr_fast(z) : fp_sqr(z), z), l_last);
-  Fr zn = fp_mul(z_next, fp_add(a, beta));
-  Fr t = LAZY ? fp_mul2add(zn, fp_add(s, gamma), fp_neg_lazy(z), table_value)
-              : fp_sub(fp_mul(zn, fp_add(s, gamma)), fp_mul(z, table_value));
-  acc = horner_term<LAZY>(acc, y, t, l_active);
-  acc = horner_term<LAZY>(acc, y, a_minus_s, l0);
-  acc = horner_term<LAZY>(acc, y, fp_mul(a_minus_s, fp_sub(a, a_prev)), l_active);
+  acc = fp_add(fp_mul(acc, y), fp_mul(fp_sub(one, z), l0));
+  acc = fp_add(fp_mul(acc, y), fp_mul(fp_sub(fp_sqr(z), z), l_last));
+  Fr t = fp_sub(fp_mul(fp_mul(z_next, fp_add(a, beta)), fp_add(s, gamma)), fp_mul(z, table_value));
+  acc = fp_add(fp_mul(acc, y), fp_mul(t, l_active));
+  acc = fp_add(fp_mul(acc, y), fp_mul(a_minus_s, l0));
+  acc = fp_add(fp_mul(acc, y), fp_mul(fp_mul(a_minus_s, fp_sub(a, a_prev)), l_active));
   stf(h + idx, acc);
-}
-
-// ZG_H_LAZY=0 selects the kernels without two-product steps (same results; kept for A/B measurements)
-bool h_lazy() {
-  static const int v = [] {
-    const char* e = getenv("ZG_H_LAZY");
-    return e ? atoi(e) : 1;
-  }();
-  return v != 0;
 }
 
 inline uint32_t nblk(uint32_t n) { return (n + EX_THREADS - 1) / EX_THREADS; }
@@ -225,10 +178,7 @@ void expr_compress_lookups(const ExprEnv& env, const LookupProgs& lp, uint32_t n
 }
 void expr_h_gates(const ExprEnv& env, const uint32_t* prog_off, uint32_t n_gate_progs, const Fr& y, Fr* h, cudaStream_t st,
                   LaunchCounter lc) {
-  if (h_lazy())
-    k_h_gates<true><<<nblk(env.size - env.row0), EX_THREADS, 0, st>>>(env, prog_off, n_gate_progs, y, h);
-  else
-    k_h_gates<false><<<nblk(env.size - env.row0), EX_THREADS, 0, st>>>(env, prog_off, n_gate_progs, y, h);
+  k_h_gates<<<nblk(env.size - env.row0), EX_THREADS, 0, st>>>(env, prog_off, n_gate_progs, y, h);
   lc++;
 }
 void expr_h_permutation(const PermEnv& pe, const Fr& beta, const Fr& gamma, const Fr& y, const Fr& delta, Fr* h, cudaStream_t st,
@@ -239,10 +189,7 @@ void expr_h_permutation(const PermEnv& pe, const Fr& beta, const Fr& gamma, cons
 }
 void expr_h_lookup(const ExprEnv& env, const LookupProgs& lp, uint32_t l, const LookupHEnv& le, const Fr& theta, const Fr& beta,
                    const Fr& gamma, const Fr& y, Fr* h, cudaStream_t st, LaunchCounter lc) {
-  if (h_lazy())
-    k_h_lookup<true><<<nblk(env.size - env.row0), EX_THREADS, 0, st>>>(env, lp, l, le, theta, beta, gamma, y, h);
-  else
-    k_h_lookup<false><<<nblk(env.size - env.row0), EX_THREADS, 0, st>>>(env, lp, l, le, theta, beta, gamma, y, h);
+  k_h_lookup<<<nblk(env.size - env.row0), EX_THREADS, 0, st>>>(env, lp, l, le, theta, beta, gamma, y, h);
   lc++;
 }
 

@@ -115,6 +115,76 @@ ZG_HD bool fp_eq(const Fp<P>& a, const Fp<P>& b) {
   return o == 0;
 }
 
+#if !defined(__CUDA_ARCH__)
+// Host-side view of an element as 4 x 64-bit limbs (same bytes on a little-endian host): the host arithmetic below
+// (verifier, witness synthesis, per-round point normalisation) runs on it.
+template <class P>
+struct FpHost64 {
+  static constexpr uint64_t mod(int i) { return (uint64_t)P::mod(2 * i) | ((uint64_t)P::mod(2 * i + 1) << 32); }
+  // -p^-1 mod 2^64 from the 32-bit constant by one Newton step
+  static constexpr uint64_t inv() {
+    uint64_t x = (uint64_t)(0u - P::INV);          // p^-1 mod 2^32
+    x = x * (2 - mod(0) * x);                      // p^-1 mod 2^64
+    return 0 - x;
+  }
+};
+template <class P>
+inline void fp_load64(const Fp<P>& a, uint64_t (&x)[4]) {
+  for (int i = 0; i < 4; i++) x[i] = (uint64_t)a.v[2 * i] | ((uint64_t)a.v[2 * i + 1] << 32);
+}
+template <class P>
+inline Fp<P> fp_store64(const uint64_t (&x)[4]) {
+  Fp<P> r;
+  for (int i = 0; i < 4; i++) {
+    r.v[2 * i] = (uint32_t)x[i];
+    r.v[2 * i + 1] = (uint32_t)(x[i] >> 32);
+  }
+  return r;
+}
+// x + y mod p and x - y mod p on the 64-bit view (x, y < p)
+template <class P>
+inline Fp<P> fp_add_host64(const Fp<P>& a, const Fp<P>& b) {
+  typedef unsigned __int128 u128;
+  uint64_t x[4], y[4], t[4], u[4];
+  fp_load64(a, x);
+  fp_load64(b, y);
+  u128 c = 0;
+  for (int i = 0; i < 4; i++) {
+    c += (u128)x[i] + y[i];
+    t[i] = (uint64_t)c;
+    c >>= 64;
+  }
+  u128 bw = 0;
+  for (int i = 0; i < 4; i++) {
+    u128 d = (u128)t[i] - FpHost64<P>::mod(i) - (uint64_t)bw;
+    u[i] = (uint64_t)d;
+    bw = (d >> 64) & 1;
+  }
+  return bw ? fp_store64<P>(t) : fp_store64<P>(u);   // a + b < 2p < 2^255: no carry out of limb 3
+}
+template <class P>
+inline Fp<P> fp_sub_host64(const Fp<P>& a, const Fp<P>& b) {
+  typedef unsigned __int128 u128;
+  uint64_t x[4], y[4], t[4];
+  fp_load64(a, x);
+  fp_load64(b, y);
+  u128 bw = 0;
+  for (int i = 0; i < 4; i++) {
+    u128 d = (u128)x[i] - y[i] - (uint64_t)bw;
+    t[i] = (uint64_t)d;
+    bw = (d >> 64) & 1;
+  }
+  const uint64_t mask = 0 - (uint64_t)bw;
+  u128 c = 0;
+  for (int i = 0; i < 4; i++) {
+    c += (u128)t[i] + (FpHost64<P>::mod(i) & mask);
+    t[i] = (uint64_t)c;
+    c >>= 64;
+  }
+  return fp_store64<P>(t);
+}
+#endif
+
 // r = (t >= p) ? t - p : t, for t < 2p
 template <class P>
 ZG_HD void fp_final_sub(uint32_t (&t)[8]) {
@@ -151,6 +221,9 @@ ZG_HD void fp_final_sub(uint32_t (&t)[8]) {
 
 template <class P>
 ZG_HD Fp<P> fp_add(const Fp<P>& a, const Fp<P>& b) {
+#if !defined(__CUDA_ARCH__)
+  return fp_add_host64<P>(a, b);
+#else
   uint32_t t[8];
 #if defined(__CUDA_ARCH__)
   asm("add.cc.u32 %0, %8, %16;\n\t"
@@ -179,10 +252,14 @@ ZG_HD Fp<P> fp_add(const Fp<P>& a, const Fp<P>& b) {
 #pragma unroll
   for (int i = 0; i < 8; i++) r.v[i] = t[i];
   return r;
+#endif
 }
 
 template <class P>
 ZG_HD Fp<P> fp_sub(const Fp<P>& a, const Fp<P>& b) {
+#if !defined(__CUDA_ARCH__)
+  return fp_sub_host64<P>(a, b);
+#else
   uint32_t t[8];
   Fp<P> r;
 #if defined(__CUDA_ARCH__)
@@ -232,6 +309,7 @@ ZG_HD Fp<P> fp_sub(const Fp<P>& a, const Fp<P>& b) {
   }
 #endif
   return r;
+#endif
 }
 
 template <class P>
@@ -274,6 +352,60 @@ ZG_HD Fp<P> fp_mul_portable(const Fp<P>& a, const Fp<P>& b) {
   for (int i = 0; i < 8; i++) r.v[i] = t[i];
   return r;
 }
+
+#if !defined(__CUDA_ARCH__)
+// Host multiplier: the same function on 4 x 64-bit limbs with 128-bit accumulators (same bytes in memory on a
+// little-endian host).  The host-side verifier (pairing, GWC multi-scalar product), the witness synthesizer and the
+// per-round point normalisation of the prover run on it; about five times the speed of the 32-bit-limb body above.
+template <class P>
+inline Fp<P> fp_mul_host64(const Fp<P>& a, const Fp<P>& b) {
+  typedef unsigned __int128 u128;
+  uint64_t A[4], B[4], t[5] = {0, 0, 0, 0, 0};
+  fp_load64(a, A);
+  fp_load64(b, B);
+  constexpr uint64_t M0 = FpHost64<P>::mod(0), M1 = FpHost64<P>::mod(1), M2 = FpHost64<P>::mod(2), M3 = FpHost64<P>::mod(3);
+  constexpr uint64_t INV = FpHost64<P>::inv();
+  for (int i = 0; i < 4; i++) {
+    u128 c = (u128)A[0] * B[i] + t[0];
+    t[0] = (uint64_t)c;
+    c = (c >> 64) + (u128)A[1] * B[i] + t[1];
+    t[1] = (uint64_t)c;
+    c = (c >> 64) + (u128)A[2] * B[i] + t[2];
+    t[2] = (uint64_t)c;
+    c = (c >> 64) + (u128)A[3] * B[i] + t[3];
+    t[3] = (uint64_t)c;
+    c = (c >> 64) + t[4];
+    t[4] = (uint64_t)c;                            // T < 2p * 2^64 < 2^319: no sixth limb
+    const uint64_t m = t[0] * INV;
+    c = (u128)m * M0 + t[0];
+    c = (c >> 64) + (u128)m * M1 + t[1];
+    t[0] = (uint64_t)c;
+    c = (c >> 64) + (u128)m * M2 + t[2];
+    t[1] = (uint64_t)c;
+    c = (c >> 64) + (u128)m * M3 + t[3];
+    t[2] = (uint64_t)c;
+    c = (c >> 64) + t[4];
+    t[3] = (uint64_t)c;
+    t[4] = (uint64_t)(c >> 64);
+  }
+  // t < 2p < 2^255: t[4] == 0; one conditional subtraction
+  uint64_t u[4];
+  u128 bw = 0;
+  const uint64_t M[4] = {M0, M1, M2, M3};
+  for (int i = 0; i < 4; i++) {
+    u128 d = (u128)t[i] - M[i] - (uint64_t)bw;
+    u[i] = (uint64_t)d;
+    bw = (d >> 64) & 1;
+  }
+  Fp<P> r;
+  for (int i = 0; i < 4; i++) {
+    const uint64_t x = bw ? t[i] : u[i];
+    r.v[2 * i] = (uint32_t)x;
+    r.v[2 * i + 1] = (uint32_t)(x >> 32);
+  }
+  return r;
+}
+#endif
 
 #if defined(__CUDA_ARCH__)
 // One CIOS row as a single asm statement, so the carry flag never crosses a statement
@@ -500,8 +632,10 @@ ZG_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
   return fp_mul_eo<P>(a, b);
 #elif defined(__CUDA_ARCH__) && ZG_MUL_VARIANT == 1
   return fp_mul_ptx<P>(a, b);
-#else
+#elif defined(__CUDA_ARCH__)
   return fp_mul_portable<P>(a, b);
+#else
+  return fp_mul_host64<P>(a, b);
 #endif
 }
 template <class P>
@@ -629,13 +763,110 @@ ZG_HD Fp<P> fp_pow_var(const Fp<P>& a, uint64_t e) {
 }
 // Fermat inverse a^(p-2); maps 0 -> 0 (same convention as ff::Field::invert().unwrap_or(0)
 // inside halo2's batch_invert, which skips zeros).
+#if !defined(__CUDA_ARCH__)
+// Host inversion: Kaliski's almost-inverse (shifts, additions and subtractions on 256-bit integers, no modular step
+// inside the loop) gives x = (a R)^-1 * 2^k mod p with 254 <= k <= 508; two Montgomery products by powers of two then
+// land on a^-1 R.  About 3 us against 20 us for the 380 products of the Fermat exponentiation.  Same function as the
+// device body below (the inverse is unique; 0 -> 0).
+template <class P>
+inline Fp<P> fp_inv_host(const Fp<P>& a) {
+  typedef unsigned __int128 u128;
+  if (fp_is_zero(a)) return a;
+  const uint64_t M[4] = {FpHost64<P>::mod(0), FpHost64<P>::mod(1), FpHost64<P>::mod(2), FpHost64<P>::mod(3)};
+  uint64_t u[4], v[4], r[4] = {0, 0, 0, 0}, s[4] = {1, 0, 0, 0};
+  for (int i = 0; i < 4; i++) {
+    u[i] = M[i];
+    v[i] = (uint64_t)a.v[2 * i] | ((uint64_t)a.v[2 * i + 1] << 32);
+  }
+  auto shr1 = [](uint64_t* x) {
+    x[0] = (x[0] >> 1) | (x[1] << 63);
+    x[1] = (x[1] >> 1) | (x[2] << 63);
+    x[2] = (x[2] >> 1) | (x[3] << 63);
+    x[3] >>= 1;
+  };
+  auto shl1 = [](uint64_t* x) {
+    x[3] = (x[3] << 1) | (x[2] >> 63);
+    x[2] = (x[2] << 1) | (x[1] >> 63);
+    x[1] = (x[1] << 1) | (x[0] >> 63);
+    x[0] <<= 1;
+  };
+  auto gt = [](const uint64_t* x, const uint64_t* y) {
+    for (int i = 3; i >= 0; i--)
+      if (x[i] != y[i]) return x[i] > y[i];
+    return false;
+  };
+  auto add = [](uint64_t* x, const uint64_t* y) {
+    u128 c = 0;
+    for (int i = 0; i < 4; i++) {
+      c += (u128)x[i] + y[i];
+      x[i] = (uint64_t)c;
+      c >>= 64;
+    }
+  };
+  auto sub = [](uint64_t* x, const uint64_t* y) {
+    u128 bw = 0;
+    for (int i = 0; i < 4; i++) {
+      u128 d = (u128)x[i] - y[i] - (uint64_t)bw;
+      x[i] = (uint64_t)d;
+      bw = (d >> 64) & 1;
+    }
+  };
+  uint32_t k = 0;
+  while ((v[0] | v[1] | v[2] | v[3]) != 0) {      // r, s < 2p < 2^255 throughout
+    if (!(u[0] & 1)) {
+      shr1(u);
+      shl1(s);
+    } else if (!(v[0] & 1)) {
+      shr1(v);
+      shl1(r);
+    } else if (gt(u, v)) {
+      sub(u, v);
+      shr1(u);
+      add(r, s);
+      shl1(s);
+    } else {
+      sub(v, u);
+      shr1(v);
+      add(s, r);
+      shl1(r);
+    }
+    k++;
+  }
+  if (!gt(M, r)) sub(r, M);                         // r >= p
+  uint64_t x[4] = {M[0], M[1], M[2], M[3]};
+  sub(x, r);                                         // x = p - r = (aR)^-1 * 2^k mod p
+  Fp<P> t, r2, pw;
+  for (int i = 0; i < 4; i++) {
+    t.v[2 * i] = (uint32_t)x[i];
+    t.v[2 * i + 1] = (uint32_t)(x[i] >> 32);
+  }
+  for (int i = 0; i < 8; i++) r2.v[i] = P::r2(i);
+  // a^-1 R = x * 2^(512 - k); mont(x, mont(R^2, 2^e)) = x * 2^e for 2^e < p (e <= 253)
+  uint32_t e = 512 - k;
+  auto pow2 = [&](uint32_t b) {
+    Fp<P> o = fp_zero<P>();
+    o.v[b >> 5] = 1u << (b & 31);
+    return fp_mul_host64<P>(r2, o);                  // Montgomery form of 2^b
+  };
+  if (e > 253) {
+    t = fp_mul_host64<P>(t, pow2(253));
+    e -= 253;
+  }
+  return fp_mul_host64<P>(t, pow2(e));
+}
+#endif
+
 template <class P>
 ZG_HD Fp<P> fp_inv(const Fp<P>& a) {
+#if !defined(__CUDA_ARCH__)
+  return fp_inv_host<P>(a);
+#else
   uint32_t e[8];
 #pragma unroll
   for (int i = 0; i < 8; i++) e[i] = P::mod(i);
   e[0] -= 2;  // low limb of both moduli is >= 2, no borrow
   return fp_pow<P>(a, e, 8);
+#endif
 }
 
 }  // namespace zg

@@ -299,6 +299,24 @@ MsmWorkspaceLayout msm_workspace_layout(uint32_t n, uint32_t c, uint32_t W, uint
   }
   const uint64_t t_dense = (lmax + l.K0 - 1) / l.K0;
   l.T0 = (uint32_t)(t_dense < t_cap ? t_dense : t_cap);
+  // Few-wave launches (the commitment rounds of a proof: 1.1 - 4.3 waves of resident CTAs at K0 entries per thread) lose
+  // up to half of their last wave.  When the dense grid is w waves and ceil(w) / w exceeds what a grid of exactly
+  // floor(w) waves loses to SMs finishing unevenly (measured with ZG_MSM_WAVES at 2^20: 10 % at one wave, 6 % at two,
+  // 2.5 % at four), launch floor(w) whole waves instead: the kernel then hands every thread L / threads > K0 entries.
+  // Long lists (w > 6) keep the dense grid -- its back-fill wins there.  ZG_MSM_AUTOWAVES=0 disables the rule.
+  static const bool auto_waves = [] {
+    const char* e = getenv("ZG_MSM_AUTOWAVES");
+    return !e || atoi(e) != 0;
+  }();
+  if (auto_waves && t_cap == ~0ull) {
+    const uint64_t wt = msm_accumulate_wave_threads();
+    const uint64_t nw = t_dense / wt;
+    if (nw >= 1 && nw <= 6 && t_dense % wt != 0) {
+      static const double loss[7] = {0, 0.10, 0.06, 0.04, 0.03, 0.025, 0.02};
+      const double w = (double)t_dense / (double)wt;
+      if ((double)(nw + 1) / w > 1.0 + loss[nw]) l.T0 = (uint32_t)(nw * wt);
+    }
+  }
   l.slots_a = 2 * l.T0;
   // level 1 (serial, K = 16) or first warp level consumes slots_a
   uint32_t t1s = (l.slots_a + MSM_LEVEL1_K - 1) / MSM_LEVEL1_K, t1w = (l.slots_a + 31) / 32;

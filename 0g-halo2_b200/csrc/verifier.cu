@@ -6,7 +6,8 @@
 // (read side).  Verification stays on the host in the reference as well (one small MSM and two pairings); nothing here
 // launches a kernel, so a proof can be checked where no GPU exists.  The optimal-ate pairing below (tower
 // Fq2 = Fq[u]/(u^2+1), Fq6 = Fq2[v]/(v^3 - (9+u)), Fq12 = Fq6[w]/(w^2 - v); D-type twist; affine Miller loop over
-// 6x+2, two Frobenius lines, final exponentiation as conj/inverse followed by one plain square-and-multiply) is
+// 6x+2, two Frobenius lines, final exponentiation = easy part by conjugation / inversion / p^2-Frobenius, hard part
+// (p^4 - p^2 + 1)/r by the BN addition chain over f^x, f^(x^2), f^(x^3) and their Frobenius images) is
 // written for this file; the test-only pairing of the CPU checker under oracle/ is the independent implementation
 // (tests/test_verifier.py compares the two on bilinearity and on accept / reject of whole proofs).
 #include <algorithm>
@@ -129,25 +130,26 @@ Fq2 f2_pow_bits(const Fq2& a, const std::vector<uint8_t>& bits) {
 const char* const HEX_6X_PLUS_2 = "19d797039be763ba8";
 const char* const HEX_P_MINUS_1_OVER_3 = "10216f7ba065e00de81ac1e7808072c9dd2b2385cd7b438469602eb24829a9c2";
 const char* const HEX_P_MINUS_1_OVER_2 = "183227397098d014dc2822db40c0ac2ecbc0b548b438e5469e10460b6c3e7ea3";
-// the part of (p^12 - 1)/r left after the easy exponent p^6 - 1: (p^6 + 1)/r = (p^2 + 1)(p^4 - p^2 + 1)/r  (1270 bits)
-const char* const HEX_HARD_EXPONENT =
-    "fd14cc52f5b83fbdea556c23998e4150e578c5084015bb37f601919667af5051c6d1aa5afdd1707409206c82d647ec2d1ea74a391cae91d2"
-    "e5726e39276a1ca64c0fd82eb59e1df6d76bdcf51b0d8a733cd65b14bb3b5c901bf1887c6042c758e4408ecc9952c0fcc420e48c3454c42a"
-    "d1f5e50ef364494f69f6b84e09bf6a8ce2533be36c7a2d1138bf54d5bd1d4a5635f15967890515250a54036e3f812";
+const char* const HEX_P_MINUS_1_OVER_6 = "810b7bdd032f006f40d60f3c0403964ee9591c2e6bda1c234b017592414d4e1";
+const char* const HEX_X = "44e992b44a6909f1";   // the BN parameter x
 
 struct G2Aff { Fq2 x, y; bool inf; };
 
 struct PairingConsts {
-  std::vector<uint8_t> loop_bits, hard_bits;
+  std::vector<uint8_t> loop_bits, x_bits;
   Fq2 frob_x, frob_y;       // xi^((p-1)/3), xi^((p-1)/2): the p-power Frobenius on twist coordinates
+  Fq2 gamma[6];             // gamma[i] = xi^(i (p-1)/6): the p-power Frobenius on Fq12 = Fq2[W]/(W^6 - xi)
   Fq2 twist_b;              // 3 / (9 + u)
   PairingConsts() {
     loop_bits = hex_bits_msb_first(HEX_6X_PLUS_2);
-    hard_bits = hex_bits_msb_first(HEX_HARD_EXPONENT);
+    x_bits = hex_bits_msb_first(HEX_X);
     Fq nine = fp_from_u64<FqParams>(9);
     Fq2 xi{nine, fq1()};
     frob_x = f2_pow_bits(xi, hex_bits_msb_first(HEX_P_MINUS_1_OVER_3));
     frob_y = f2_pow_bits(xi, hex_bits_msb_first(HEX_P_MINUS_1_OVER_2));
+    gamma[0] = f2_one();
+    gamma[1] = f2_pow_bits(xi, hex_bits_msb_first(HEX_P_MINUS_1_OVER_6));
+    for (int i = 2; i < 6; i++) gamma[i] = f2_mul(gamma[i - 1], gamma[1]);
     twist_b = f2_mul_fq(f2_inv(xi), fp_from_u64<FqParams>(3));
   }
 };
@@ -197,6 +199,50 @@ Fq12 line_and_add(G2Aff& T, const G2Aff& Q, const Fq& xP, const Fq& yP, bool dbl
   return l;
 }
 
+// a^p for a = sum_i a_i W^i (a_i in Fq2; c0 = (a_0, a_2, a_4), c1 = (a_1, a_3, a_5)): conj(a_i) * gamma[i]
+Fq12 f12_frobenius(const Fq12& a) {
+  const PairingConsts& C = consts();
+  Fq12 r;
+  r.c0.c0 = f2_conj(a.c0.c0);
+  r.c0.c1 = f2_mul(f2_conj(a.c0.c1), C.gamma[2]);
+  r.c0.c2 = f2_mul(f2_conj(a.c0.c2), C.gamma[4]);
+  r.c1.c0 = f2_mul(f2_conj(a.c1.c0), C.gamma[1]);
+  r.c1.c1 = f2_mul(f2_conj(a.c1.c1), C.gamma[3]);
+  r.c1.c2 = f2_mul(f2_conj(a.c1.c2), C.gamma[5]);
+  return r;
+}
+Fq12 f12_pow_x(const Fq12& a) {
+  Fq12 r = f12_one();
+  for (uint8_t b : consts().x_bits) {
+    r = f12_sqr(r);
+    if (b) r = f12_mul(r, a);
+  }
+  return r;
+}
+// f^((p^12 - 1)/r).  Easy part: f^((p^6 - 1)(p^2 + 1)); afterwards the inverse is the conjugate.  Hard part
+// (p^4 - p^2 + 1)/r = p + p^2 + p^3 - 2 + 6 x^2 p^2 - 12 x p - 18 (x + x^2 p) - 30 x^2 - 36 (x^3 + x^3 p)  (checked as an
+// integer identity for this x), evaluated with the exponent vector (1, 2, 6, 12, 18, 30, 36) addition chain.
+Fq12 final_exponentiation(const Fq12& f) {
+  Fq12 g = f12_mul(f12_conj(f), f12_inv(f));                 // f^(p^6 - 1)
+  g = f12_mul(f12_frobenius(f12_frobenius(g)), g);           // ^(p^2 + 1)
+  const Fq12 gx = f12_pow_x(g), gx2 = f12_pow_x(gx), gx3 = f12_pow_x(gx2);
+  const Fq12 gp = f12_frobenius(g), gp2 = f12_frobenius(gp), gp3 = f12_frobenius(gp2);
+  const Fq12 y0 = f12_mul(f12_mul(gp, gp2), gp3);
+  const Fq12 y1 = f12_conj(g);
+  const Fq12 y2 = f12_frobenius(f12_frobenius(gx2));
+  const Fq12 y3 = f12_conj(f12_frobenius(gx));
+  const Fq12 y4 = f12_conj(f12_mul(gx, f12_frobenius(gx2)));
+  const Fq12 y5 = f12_conj(gx2);
+  const Fq12 y6 = f12_conj(f12_mul(gx3, f12_frobenius(gx3)));
+  Fq12 t0 = f12_mul(f12_mul(f12_sqr(y6), y4), y5);
+  Fq12 t1 = f12_mul(f12_mul(y3, y5), t0);
+  t0 = f12_mul(t0, y2);
+  t1 = f12_sqr(f12_mul(f12_sqr(t1), t0));
+  t0 = f12_mul(t1, y1);
+  t1 = f12_mul(t1, y0);
+  return f12_mul(f12_sqr(t0), t1);
+}
+
 // prod_i e(P_i, Q_i) == 1 ?   (P_i in G1 affine, Q_i on the twist)
 bool pairing_product_is_one(const std::vector<G1Affine>& P, const std::vector<G2Aff>& Q) {
   const PairingConsts& C = consts();
@@ -223,14 +269,7 @@ bool pairing_product_is_one(const std::vector<G1Affine>& P, const std::vector<G2
     f = f12_mul(f, line_and_add(T[i], q1, P[i].x, P[i].y, false));
     f = f12_mul(f, line_and_add(T[i], q2, P[i].x, P[i].y, false));
   }
-  // final exponentiation: f^(p^6 - 1) = conj(f) / f, then the remaining exponent (p^6 + 1) / r bit by bit
-  Fq12 g = f12_mul(f12_conj(f), f12_inv(f));
-  Fq12 r = f12_one();
-  for (uint8_t bit : C.hard_bits) {
-    r = f12_sqr(r);
-    if (bit) r = f12_mul(r, g);
-  }
-  return f12_is_one(r);
+  return f12_is_one(final_exponentiation(f));
 }
 
 // ---- G1 helpers on the host ----------------------------------------------------------------------------------------------

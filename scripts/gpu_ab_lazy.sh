@@ -1,6 +1,7 @@
 #!/bin/bash
-# A/B of the lazy-reduction kernels on ONE GPU: ZG_MSM_MADD (mixed addition of msm_accumulate_kernel) and ZG_H_LAZY
-# (two-product Horner steps of k_h_lookup / k_h_gates), parity tests under both settings, bench lines per setting.
+# A/B of the lazy-reduction mixed addition of msm_accumulate_kernel on ONE GPU (ZG_MSM_MADD=0|1): parity tests under both
+# settings, bench lines per setting.  (ZG_H_LAZY selected two-product Horner steps in k_h_lookup / k_h_gates when this
+# script was first run; they measured no gain -- profiles/r02_notes.md -- and were removed; the variable is now ignored.)
 set -u
 cd "${GRAFT_REPO_ROOT:-.}"
 O=gpurun_out/ab_lazy; mkdir -p $O
