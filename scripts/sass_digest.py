@@ -12,7 +12,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "0g-halo2_b200", "csrc")
 KERNELS = ["msm_accumulate_kernel", "ntt_pass_kernel", "k_h_lookup", "k_h_gates", "k_h_permutation", "msm_finish_kernel",
-           "msm_bucket_l1_kernel", "msm_digits_kernel", "k_rs_scatter", "k_bi2_apply", "fp_mul_outlined"]
+           "msm_bucket_l1_kernel", "msm_digits_kernel", "k_rs_scatter", "k_bi2_apply", "fp_mul_outlined", "fp_sqr_gen_outlined",
+           "fp_mul2_gen_outlined"]
 
 
 def registers_table(out):
@@ -56,7 +57,7 @@ def sass_digests(outdir):
                     lines.append(line.rstrip())
             total = sum(ops.values())
             short = re.sub(r"[^A-Za-z0-9_]", "_", hit[0])
-            tag = "_" + re.sub(r"\.o$", "", os.path.basename(obj)) if hit[0] == "fp_mul_outlined" else ""
+            tag = "_" + re.sub(r"\.o$", "", os.path.basename(obj)) if "outlined" in hit[0] else ""
             with open(os.path.join(outdir, "r02_sass_%s%s.txt" % (short, tag)), "w") as f:
                 f.write("%s\n%s: %d SASS instructions (%d bytes)\n\n" % (fn, os.path.basename(obj), total, total * 16))
                 grp = collections.Counter()
