@@ -38,20 +38,6 @@ struct MsmProbe {
   size_t cap = 0, used = 0;
 };
 
-// Cooperative form of the small, latency-bound tail launches (msm_tail_coop.cu: every EC addition computed by the four
-// warps of a CTA).  ZG_MSM_TAIL_COOP=0|1 selects at run time.
-#ifndef ZG_MSM_TAIL_COOP_DEFAULT
-#define ZG_MSM_TAIL_COOP_DEFAULT 0
-#endif
-bool msm_tail_coop_enabled();
-// a warp-shuffle level with at most this many groups of 32 entries runs one CTA per group
-constexpr uint32_t MSM_COOP_MAX_GROUPS = 1184;
-void msm_tail_warp_level_coop(const uint32_t* keys, const G1Xyzz* pts, uint32_t slots, G1Xyzz* buckets, uint32_t* pkeys_out,
-                              G1Xyzz* ppts_out, uint32_t nwarps, int fin, cudaStream_t st);
-void msm_tail_l1_coop(const G1Xyzz* buckets, uint32_t NB, uint32_t M, uint32_t n1, G1Xyzz* s1, G1Xyzz* t1, cudaStream_t st);
-void msm_tail_l2_finish_coop(const G1Xyzz* s1, const G1Xyzz* t1, uint32_t n1, uint32_t M, G1Xyzz* l2out, G1Jac* out,
-                             cudaStream_t st);
-
 cudaError_t msm_precompute_table(const G1Affine* base, uint32_t n, uint32_t c, uint32_t W,
                                  G1Affine* table, cudaStream_t stream);
 

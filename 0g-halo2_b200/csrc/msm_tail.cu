@@ -283,25 +283,11 @@ void msm_tail_serial_level(const uint32_t* keys, const G1Xyzz* pts, uint32_t slo
 }
 void msm_tail_warp_level(const uint32_t* keys, const G1Xyzz* pts, uint32_t slots, G1Xyzz* buckets, uint32_t* pkeys_out,
                          G1Xyzz* ppts_out, uint32_t nwarps, int fin, cudaStream_t st) {
-  if (nwarps <= MSM_COOP_MAX_GROUPS && msm_tail_coop_enabled()) {   // small level: latency-bound, one CTA per group
-    msm_tail_warp_level_coop(keys, pts, slots, buckets, pkeys_out, ppts_out, nwarps, fin, st);
-    return;
-  }
   msm_warp_reduce_kernel<<<(nwarps + 3) / 4, 128, 0, st>>>(keys, pts, slots, buckets, pkeys_out, ppts_out, nwarps, fin);
 }
 void msm_tail_buckets(const G1Xyzz* buckets, uint32_t NB, uint32_t M, G1Xyzz* s1, G1Xyzz* t1, G1Xyzz* l2out, G1Jac* out,
                       cudaStream_t st) {
   uint32_t n1 = (NB + 31) / 32;
-  if (msm_tail_coop_enabled()) {
-    // the first level keeps the work-efficient eight-buckets-per-lane kernel when it is throughput-bound; the
-    // latency-bound levels run in the cooperative form
-    if ((uint64_t)n1 * M <= MSM_COOP_MAX_GROUPS)
-      msm_tail_l1_coop(buckets, NB, M, n1, s1, t1, st);
-    else
-      msm_bucket_l1_kernel<<<dim3((4 * n1 + 127) / 128, M), 128, 0, st>>>(buckets, NB, n1, s1, t1);
-    msm_tail_l2_finish_coop(s1, t1, n1, M, l2out, out, st);
-    return;
-  }
   // <= 2 warps per SM sub-partition in the one-bucket-per-lane form: the chain of 10 additions decides; beyond that
   // the 8-buckets-per-lane form (4x fewer lane-additions) wins
   if ((uint64_t)n1 * M <= 2 * 592)

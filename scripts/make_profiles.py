@@ -52,7 +52,7 @@ def main(tag):
     # ---- proof lines
     L += ["## Proof workload: proofs/s, image -> proof e2e, latency, CPU baseline", "",
           "`bench.py` default = the north-star target (49input_8192entry_4hash_6bpi shape, k = 17, synthetic stand-in), 4 proofs in "
-          "flight, 8 proofs per step; e2e = image -> `zg_wnn_synthesize` -> pinned buffers -> `zg_create_proof` -> proof bytes "
+          "flight, 16 proofs per step; e2e = image -> `zg_wnn_synthesize` -> pinned buffers -> `zg_create_proof` -> proof bytes "
           "through `ProofService.prove_many`, production RNG.", "",
           "| model | k | in flight | proofs/s (advice in HBM) | proofs/s (e2e from the image) | single-proof latency ms | kernel frac | CPU oracle proofs/s (cores) | e2e / CPU |",
           "|---|---|---|---|---|---|---|---|---|"]
