@@ -11,6 +11,10 @@ void h_fr_sub(const Fr* a, const Fr* b, Fr* o, int n) { for (int i = 0; i < n; i
 void h_fq_add(const Fq* a, const Fq* b, Fq* o, int n) { for (int i = 0; i < n; i++) o[i] = fp_add(a[i], b[i]); }
 void h_fq_sub(const Fq* a, const Fq* b, Fq* o, int n) { for (int i = 0; i < n; i++) o[i] = fp_sub(a[i], b[i]); }
 void h_fr_inv(const Fr* a, Fr* o, int n) { for (int i = 0; i < n; i++) o[i] = fp_inv(a[i]); }
+void h_fq_inv(const Fq* a, Fq* o, int n) { for (int i = 0; i < n; i++) o[i] = fp_inv(a[i]); }
+// the 8 x 32-bit-limb body (device multiplier variant 0), which the host no longer uses for fp_mul
+void h_fr_mul_portable(const Fr* a, const Fr* b, Fr* o, int n) { for (int i = 0; i < n; i++) o[i] = fp_mul_portable(a[i], b[i]); }
+void h_fq_mul_portable(const Fq* a, const Fq* b, Fq* o, int n) { for (int i = 0; i < n; i++) o[i] = fp_mul_portable(a[i], b[i]); }
 void h_fr_to_mont(const Fr* a, Fr* o, int n) { for (int i = 0; i < n; i++) o[i] = fp_to_mont(a[i]); }
 void h_fr_from_mont(const Fr* a, Fr* o, int n) { for (int i = 0; i < n; i++) o[i] = fp_from_mont(a[i]); }
 // acc (xyzz) += affine points one by one; returns Jacobian

@@ -1,5 +1,6 @@
 """CPU-side checks of the device code's logic:
-  * the portable (host) path of csrc/field.cuh + curve.cuh against Python big integers;
+  * the host paths of csrc/field.cuh + curve.cuh (4 x 64-bit-limb multiplier / adder / subtractor, almost-inverse, and the
+    8 x 32-bit-limb body that the device's variant 0 uses) against Python big integers;
   * the Python models of the NTT pass planner and the MSM segmented-reduction pipeline
     (tests/models/*) against the naive DFT / scalar MSM.
 No GPU needed; the kernels themselves are exercised by the -m gpu tests."""
@@ -45,6 +46,28 @@ def test_portable_field_ops(harness, name, mod):
     for op, f in (("mul", lambda x, y: x * y % mod), ("add", lambda x, y: (x + y) % mod), ("sub", lambda x, y: (x - y) % mod)):
         getattr(harness, "h_%s_%s" % (name, op))(P(A), P(B), P(O), n)
         assert bn254.limbs_to_ints(O, mod) == [f(x, y) for x, y in zip(a, b)], (name, op)
+
+
+@pytest.mark.parametrize("name,mod", [("fr", R_MOD), ("fq", Q_MOD)])
+def test_host_64bit_bodies_edge_operands(harness, name, mod):
+    """the host's 4 x 64-bit-limb multiplier / adder / subtractor and the 8 x 32-bit-limb body on operands that stress the
+    carries and the final subtraction; Kaliski's almost-inverse on both fields (0 -> 0)"""
+    rnd = random.Random(9)
+    edge = [0, 1, 2, mod - 1, mod - 2, (mod - 1) // 2, (mod + 1) // 2, (1 << 64) - 1, 1 << 64, (1 << 128) - 1, 1 << 128,
+            (1 << 192) - 1, 1 << 192, (1 << 253) - 1, 1 << 253, mod - (1 << 64), mod - (1 << 128), int("f" * 63, 16) % mod]
+    a = [x for x in edge for _ in edge] + [rnd.randrange(mod) for _ in range(500)]
+    b = [y for _ in edge for y in edge] + [rnd.randrange(mod) for _ in range(500)]
+    A, B = bn254.ints_to_limbs(a, mod), bn254.ints_to_limbs(b, mod)
+    O = np.zeros_like(A)
+    for op, f in (("mul", lambda x, y: x * y % mod), ("mul_portable", lambda x, y: x * y % mod),
+                  ("add", lambda x, y: (x + y) % mod), ("sub", lambda x, y: (x - y) % mod)):
+        getattr(harness, "h_%s_%s" % (name, op))(P(A), P(B), P(O), len(a))
+        assert bn254.limbs_to_ints(O, mod) == [f(x, y) for x, y in zip(a, b)], (name, op)
+    inv_in = edge + [rnd.randrange(mod) for _ in range(300)]
+    I = bn254.ints_to_limbs(inv_in, mod)
+    OI = np.zeros_like(I)
+    getattr(harness, "h_%s_inv" % name)(P(I), P(OI), len(inv_in))
+    assert bn254.limbs_to_ints(OI, mod) == [pow(x, -1, mod) if x % mod else 0 for x in inv_in]
 
 
 def test_portable_inverse_and_mont(harness):
