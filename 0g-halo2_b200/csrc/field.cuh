@@ -6,13 +6,17 @@
 // /root/reference/Cargo.toml:14-18 pins; call sites reach it through create_proof
 // (/root/reference/src/wnn.rs:242-259).
 //
-// Three multiplier bodies:
-//   * a portable 64-bit-accumulator CIOS (host + device; the host build is what the CPU-side
-//     unit tests exercise against Python big integers),
-//   * a row-wise PTX mad.lo.cc / madc.hi.cc CIOS (device only, ZG_MUL_VARIANT=1), and
+// Multiplier bodies:
+//   * a portable 64-bit-accumulator CIOS on 8 x 32-bit limbs (device variant 0; kept in step with the others by the tests),
+//   * a row-wise PTX mad.lo.cc / madc.hi.cc CIOS (device only, ZG_MUL_VARIANT=1),
 //   * the even/odd carry-chain CIOS (device only, ZG_MUL_VARIANT=2, the default): 120 IMAD.WIDE.U32(.X)
-//     per product instead of 120 IMAD.WIDE + ~90 IMAD + ~240 IADD3 in what nvcc makes of the portable body.
-// All compute the same function bit for bit; tests/test_gpu_field.py checks them against each other.
+//     per product instead of 120 IMAD.WIDE + ~90 IMAD + ~240 IADD3 in what nvcc makes of the portable body,
+//   * generated straight-line bodies for a dedicated squaring and for a*b + c*d under ONE Montgomery reduction
+//     (field_gen.cuh, written and modelled instruction by instruction by scripts/gen_field_ops.py), and
+//   * the HOST body: 4 x 64-bit limbs with 128-bit accumulators, plus 64-bit add / subtract and Kaliski's almost-inverse
+//     (what the verifier, the witness synthesizer and the prover's per-round point normalisation run on).
+// All compute the same functions bit for bit; tests/test_gpu_field.py (device) and tests/test_host_models.py (host) check
+// them against Python big integers and each other.
 #pragma once
 #include <stdint.h>
 

@@ -389,6 +389,7 @@ def main():
             service.prove_many([imgs[w] for w in ws])
         if native is not None:
             extra["run_e2e"] = run_e2e_stream
+            extra["run_e2e_stream"] = True
         # every measured proof is a real proof: check one per lane against the restated verifier (untimed)
         opk = None
         if rank == 0 or shard_cols:                    # (column sharding: the proofs are collectives, every rank takes part)
@@ -590,6 +591,7 @@ def main():
     # e2e: host buffers through the plain C-ABI call (H2D + compute + D2H of the result)
     # (proof workload from the image: the timed steps are ONE ProofService.prove_many call over all their images -- the
     #  call a user with a queue of images makes -- so the witness pipeline fills once, not once per step)
+    e2e_streams = extra.pop("run_e2e_stream", False)
     run_e2e = extra.pop("run_e2e", None) or (lambda steps: [step_e2e() for _ in range(steps)])
     run_e2e(2)
     barrier()
@@ -648,7 +650,9 @@ def main():
         "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
         "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u256 (8x32-bit Montgomery limbs)", "data": "synthetic",
-        "config": dict({"workload": workload_name(args), "l2": "flushed between steps"},
+        "config": dict({"workload": workload_name(args),
+                        "l2": "flushed between steps" + ("; the e2e leg streams %.0f MB of freshly synthesized witness columns per step through "
+                                                         "the GPU (larger than L2)" % (h2d / 1e6) if e2e_streams else "")},
                        **({"batch": "%d independent proofs in flight per GPU, %d proofs per step" % (extra["inflight"], extra["proofs_per_step"]),
                            "synthesis": "e2e: " + extra["e2e_starts_from"] + "; value: advice columns resident in HBM"}
                           if "inflight" in extra else {})),
