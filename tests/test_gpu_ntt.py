@@ -128,3 +128,9 @@ def test_ntt_large_properties(ctx, log_n):
     assert (ta.cpu().numpy().view(np.uint64) == a).all()
     if log_n == 20:
         assert (fa == cpu_ref.best_fft(a, w, log_n)).all()
+    else:
+        # exact on sampled outputs: output i of the transform is the polynomial evaluated at omega^i (the oracle's Horner
+        # evaluation is O(n) per point; tests/test_oracle.py checks this identity against best_fft on the CPU)
+        om = bn254.omega(log_n)
+        for i in (0, 1, 2, 12345, n // 3, n // 2, n - 2, n - 1):
+            assert (fa[i] == cpu_ref.fr_eval_poly(a, W(pow(om, i, R_MOD))[0])).all(), i

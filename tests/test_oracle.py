@@ -54,6 +54,23 @@ def test_best_fft_large_matches_bigint_ntt_and_threads_agree():
     assert bn254.fr_from_limbs(r1) == bn254.ntt(a, w)
 
 
+def test_fft_output_is_the_polynomial_at_powers_of_omega():
+    """output i of best_fft == Horner evaluation at omega^i (big-int check of the evaluation, then the identity that
+    tests/test_gpu_ntt.py uses to check sampled outputs of transforms too large to restate in full)"""
+    rnd = random.Random(21)
+    log_n = 11
+    n = 1 << log_n
+    a = [rnd.randrange(R_MOD) for _ in range(n)]
+    A = bn254.fr_to_limbs(a)
+    w = bn254.omega(log_n)
+    f = cpu_ref.best_fft(A, bn254.fr_to_limbs([w]), log_n)
+    for i in (0, 1, 2, 777, n // 3, n // 2, n - 2, n - 1):
+        x = pow(w, i, R_MOD)
+        got = cpu_ref.fr_eval_poly(A, bn254.fr_to_limbs([x])[0])
+        assert bn254.fr_from_limbs(got.reshape(1, 4)) == [sum(c * pow(x, j, R_MOD) for j, c in enumerate(a)) % R_MOD]
+        assert (got == f[i]).all(), i
+
+
 def test_best_multiexp_matches_double_and_add():
     rnd = random.Random(5)
     n = 48
