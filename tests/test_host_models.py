@@ -167,36 +167,3 @@ def test_msm_pipeline_model():
     check(128, 6, 1, lambda: R_MOD - 1)
     check(128, 6, 2, lambda: 1)
     check(128, 8, 1, lambda: 0)
-
-
-def test_fp64_montgomery_multiplication_prototype():
-    """csrc/experimental/field52.cuh (round-2 groundwork, not used by any kernel): five 52-bit limbs in doubles, exact
-    limb products from two round-toward-zero FMAs, Montgomery radix 2^260 -- against Python big integers for Fr and Fq."""
-    src = os.path.join(HERE, "host", "host_field52.cpp")
-    so = os.path.join(HERE, "host", "libhost_field52.so")
-    hdr = os.path.join(HERE, "..", "0g-halo2_b200", "csrc", "experimental", "field52.cuh")
-    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-frounding-math", "-ffp-contract=off", "-shared", "-fPIC", src, "-o", so])
-    lib = ctypes.CDLL(so)
-    rnd = random.Random(52)
-    M64 = (1 << 64) - 1
-
-    def words(vals):
-        return np.array([[(v >> (64 * i)) & M64 for i in range(4)] for v in vals], dtype=np.uint64)
-    for mod in (R_MOD, Q_MOD):
-        pinv = (-pow(mod, -1, 1 << 52)) % (1 << 52)
-        n = 2000
-        a = [rnd.randrange(mod) for _ in range(n)]
-        b = [rnd.randrange(mod) for _ in range(n)]
-        edge = [0, 1, mod - 1, (1 << 52) - 1, 1 << 52, (1 << 104) - 1, (1 << 208) + 12345, mod - (1 << 52)]
-        a[:len(edge)] = edge
-        b[:len(edge)] = list(reversed(edge))
-        a[len(edge):2 * len(edge)] = edge
-        b[len(edge):2 * len(edge)] = edge
-        A, B = words(a), words(b)
-        O = np.zeros_like(A)
-        lib.h_mul52(P(A), P(B), P(O), n, P(words([mod])), ctypes.c_uint64(pinv))
-        rinv = pow(1 << 260, -1, mod)
-        got = [sum(int(O[i, j]) << (64 * j) for j in range(4)) for i in range(n)]
-        assert got == [x * y * rinv % mod for x, y in zip(a, b)]
-
